@@ -1,0 +1,480 @@
+// CUDA-core kernels of the frame-synthesis path: the stem convolution (tiny K, HBM-write bound), the bilinear
+// decoder upsample, frame-pair packing, output post-processing and the fused SSIM+PSNR metric kernel.
+#include "aux_kernels.cuh"
+#include "ptx.cuh"
+
+namespace fi {
+
+namespace {
+
+__device__ __forceinline__ float norm_u8(uint8_t u) {
+    // image.astype(float32)/255.0 then 2.0*image-1.0, each rounded to fp32 (reference model/inference.py:32-35)
+    return __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(static_cast<float>(u), 255.0f)), 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------ stem conv
+// inc.double_conv.0 (reference model/unet.py:12-14 with C_in = n_channels): conv3x3 + folded BN + ReLU, K = 9*C_in <= 72.
+// Arithmetic intensity ~17 FLOP/B -> bound by the 128 B/pixel bf16 NHWC write; fp32 CUDA-core math on exact inputs.
+constexpr int ST_TH = 8;
+constexpr int ST_TW = 32;
+constexpr int ST_MAXC = 8;
+
+template <bool U8>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const StemDesc d) {
+    __shared__ float in_s[ST_MAXC][ST_TH + 2][ST_TW + 2];
+    __shared__ __align__(16) float w_s[9 * ST_MAXC * 64];
+    __shared__ __align__(16) float b_s[64];
+
+    const int tid = threadIdx.x;
+    const int tiles_x = (d.W + ST_TW - 1) / ST_TW;
+    const int tiles_y = (d.H + ST_TH - 1) / ST_TH;
+    int t = blockIdx.x;
+    const int n = t / (tiles_x * tiles_y);
+    t -= n * tiles_x * tiles_y;
+    const int y0 = (t / tiles_x) * ST_TH;
+    const int x0 = (t % tiles_x) * ST_TW;
+
+    for (int i = tid; i < 9 * d.cin * 64; i += 256) w_s[i] = d.w[i];
+    if (tid < 64) b_s[tid] = d.bias[tid];
+
+    const int halo = (ST_TH + 2) * (ST_TW + 2);
+    for (int i = tid; i < d.cin * halo; i += 256) {
+        const int c = i / halo;
+        const int r = (i - c * halo) / (ST_TW + 2);
+        const int col = i - c * halo - r * (ST_TW + 2);
+        const int y = y0 + r - 1, x = x0 + col - 1;
+        float v = 0.0f;  // zero padding of the (already normalised) input
+        if (y >= 0 && y < d.H && x >= 0 && x < d.W) {
+            const bool first = c < d.src[0].channels;
+            const PlaneSrc& s = first ? d.src[0] : d.src[1];
+            const int cc = first ? c : c - d.src[0].channels;
+            const long long off = n * s.batch_stride + cc * s.chan_stride + y * s.row_stride + x * s.px_stride;
+            if (U8) v = norm_u8(static_cast<const uint8_t*>(s.ptr)[off]);
+            else v = static_cast<const float*>(s.ptr)[off];
+        }
+        in_s[c][r][col] = v;
+    }
+    __syncthreads();
+
+    const int cg = tid & 7;   // output channels [8cg, 8cg+8)
+    const int pl = tid >> 3;  // tile column
+    float acc[ST_TH][8];
+#pragma unroll
+    for (int r = 0; r < ST_TH; ++r)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[r][j] = b_s[cg * 8 + j];
+
+    const float4* w4 = reinterpret_cast<const float4*>(w_s);
+    for (int c = 0; c < d.cin; ++c) {
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            float col[ST_TH + 2];
+#pragma unroll
+            for (int r = 0; r < ST_TH + 2; ++r) col[r] = in_s[c][r][pl + dx];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const int wi = (((dy * 3 + dx) * d.cin + c) * 64 + cg * 8) >> 2;
+                const float4 wa = w4[wi], wb = w4[wi + 1];
+#pragma unroll
+                for (int r = 0; r < ST_TH; ++r) {
+                    const float v = col[r + dy];
+                    acc[r][0] = fmaf(v, wa.x, acc[r][0]);
+                    acc[r][1] = fmaf(v, wa.y, acc[r][1]);
+                    acc[r][2] = fmaf(v, wa.z, acc[r][2]);
+                    acc[r][3] = fmaf(v, wa.w, acc[r][3]);
+                    acc[r][4] = fmaf(v, wb.x, acc[r][4]);
+                    acc[r][5] = fmaf(v, wb.y, acc[r][5]);
+                    acc[r][6] = fmaf(v, wb.z, acc[r][6]);
+                    acc[r][7] = fmaf(v, wb.w, acc[r][7]);
+                }
+            }
+        }
+    }
+
+    const int x = x0 + pl;
+    if (x < d.W) {
+        uint4* dst = static_cast<uint4*>(d.dst);
+#pragma unroll
+        for (int r = 0; r < ST_TH; ++r) {
+            const int y = y0 + r;
+            if (y < d.H) {
+                uint4 o;
+                o.x = pack_bf16x2(fmaxf(acc[r][0], 0.f), fmaxf(acc[r][1], 0.f));
+                o.y = pack_bf16x2(fmaxf(acc[r][2], 0.f), fmaxf(acc[r][3], 0.f));
+                o.z = pack_bf16x2(fmaxf(acc[r][4], 0.f), fmaxf(acc[r][5], 0.f));
+                o.w = pack_bf16x2(fmaxf(acc[r][6], 0.f), fmaxf(acc[r][7], 0.f));
+                dst[((static_cast<size_t>(n) * d.H + y) * d.W + x) * 8 + cg] = o;  // 8 x 16 B per pixel
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ bilinear x2
+__device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int h, int w, int c8) {
+    const int oh = 2 * h, ow = 2 * w;
+    const size_t total = static_cast<size_t>(N) * oh * ow * c8;
+    const float rh = oh > 1 ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.f;
+    const float rw = ow > 1 ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) : 0.f;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int cg = static_cast<int>(i % c8);
+        size_t r = i / c8;
+        const int ox = static_cast<int>(r % ow);
+        r /= ow;
+        const int oy = static_cast<int>(r % oh);
+        const int n = static_cast<int>(r / oh);
+        const float fy = rh * oy, fx = rw * ox;
+        const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float ly = fy - y0, lx = fx - x0;
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const size_t base = static_cast<size_t>(n) * h * w;
+        const uint4 p00 = __ldg(src + (base + static_cast<size_t>(y0) * w + x0) * c8 + cg);
+        const uint4 p01 = __ldg(src + (base + static_cast<size_t>(y0) * w + x1) * c8 + cg);
+        const uint4 p10 = __ldg(src + (base + static_cast<size_t>(y1) * w + x0) * c8 + cg);
+        const uint4 p11 = __ldg(src + (base + static_cast<size_t>(y1) * w + x1) * c8 + cg);
+        const uint32_t a[4] = {p00.x, p00.y, p00.z, p00.w}, b[4] = {p01.x, p01.y, p01.z, p01.w};
+        const uint32_t c[4] = {p10.x, p10.y, p10.z, p10.w}, e[4] = {p11.x, p11.y, p11.z, p11.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float lo = hy * (hx * bf_lo(a[k]) + lx * bf_lo(b[k])) + ly * (hx * bf_lo(c[k]) + lx * bf_lo(e[k]));
+            const float hi = hy * (hx * bf_hi(a[k]) + lx * bf_hi(b[k])) + ly * (hx * bf_hi(c[k]) + lx * bf_hi(e[k]));
+            o[k] = pack_bf16x2(lo, hi);
+        }
+        dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pack / post
+// out[n, k, :, :] = 2*(f[n, k mod C]/255) - 1 with f = f0 for k < C else f1: 16 pixels (one 128-bit load) per thread.
+__global__ void __launch_bounds__(256)
+pack_pair_kernel(const uint8_t* __restrict__ f0, const uint8_t* __restrict__ f1, float* __restrict__ out, int N, int C,
+                 size_t plane, int vec) {
+    if (vec) {
+        const size_t plane16 = plane / 16;
+        const size_t total = static_cast<size_t>(N) * 2 * C * plane16;
+        for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+             i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+            const size_t pi = i % plane16;
+            const size_t nk = i / plane16;
+            const int k = static_cast<int>(nk % (2 * C));
+            const size_t n = nk / (2 * C);
+            const uint8_t* srcp = (k < C ? f0 : f1) + (n * C + (k < C ? k : k - C)) * plane;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(srcp) + pi);
+            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+            float4* o = reinterpret_cast<float4*>(out + nk * plane) + pi * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 r;
+                r.x = norm_u8(wv[q] & 0xff);
+                r.y = norm_u8((wv[q] >> 8) & 0xff);
+                r.z = norm_u8((wv[q] >> 16) & 0xff);
+                r.w = norm_u8(wv[q] >> 24);
+                o[q] = r;
+            }
+        }
+    } else {
+        const size_t total = static_cast<size_t>(N) * 2 * C * plane;
+        for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+             i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+            const size_t pi = i % plane;
+            const size_t nk = i / plane;
+            const int k = static_cast<int>(nk % (2 * C));
+            const size_t n = nk / (2 * C);
+            const uint8_t* srcp = (k < C ? f0 : f1) + (n * C + (k < C ? k : k - C)) * plane;
+            out[i] = norm_u8(srcp[pi]);
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t post_u8(float t) {
+    float u = __fmul_rn(__fadd_rn(t, 1.0f), 0.5f);  // (tensor + 1.0) / 2.0
+    u = fminf(fmaxf(u, 0.0f), 1.0f);                // clamp(0, 1)
+    return static_cast<uint32_t>(__fmul_rn(u, 255.0f)) & 0xff;  // *255 -> astype(uint8) truncates
+}
+
+__global__ void __launch_bounds__(256)
+head_post_kernel(const float* __restrict__ y, uint8_t* __restrict__ out, size_t n, int vec) {
+    const size_t n16 = vec ? n / 16 : 0;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4* p = reinterpret_cast<const float4*>(y) + i * 4;
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = __ldg(p + q);
+            o[q] = post_u8(v.x) | (post_u8(v.y) << 8) | (post_u8(v.z) << 16) | (post_u8(v.w) << 24);
+        }
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    for (size_t i = n16 * 16 + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        out[i] = static_cast<uint8_t>(post_u8(y[i]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ SSIM + PSNR
+// compute_ssim / compute_psnr of the reference (model/evaluation.py:194-218) call scikit-image with data_range=255:
+// 7x7 uniform window, sample covariance (x49/48), K1=.01, K2=.03, mean over the image cropped by 3; PSNR from the MSE.
+// All 49-pixel window sums of u8 data are exact in int32, so the per-pixel ratio is formed from exact integers:
+//   S = (2 Sx Sy + C1 49^2)(2(49 Sxy - Sx Sy) + C2 48 49) / ((Sx^2 + Sy^2 + C1 49^2)(49 Sqq - Sx^2 - Sy^2 + C2 48 49))
+// with Sx = sum x, Sy = sum y, Sqq = sum (x^2 + y^2), Sxy = sum x y over the window.
+// Thread = 4 adjacent columns, sliding down SS_ROWS rows: horizontal window sums slide along x, vertical along y.
+constexpr int SS_THREADS = 128;
+constexpr int SS_COLS = 4 * SS_THREADS;  // columns per block
+constexpr int SS_ROWS = 36;              // owned rows per block (+6 halo rows streamed)
+
+__device__ __forceinline__ uint32_t load_word_guarded(const uint8_t* rowp, int c0, int W, bool aligned) {
+    if (c0 >= 0 && c0 + 3 < W && aligned) return __ldg(reinterpret_cast<const uint32_t*>(rowp + c0));
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + k;
+        if (c >= 0 && c < W) v |= static_cast<uint32_t>(__ldg(rowp + c)) << (8 * k);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(SS_THREADS)
+ssim_psnr_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int H, int W, int aligned,
+                 double* __restrict__ part_ssim, unsigned long long* __restrict__ part_ssd) {
+    const int tid = threadIdx.x;
+    const int n = blockIdx.z;
+    const int xb = blockIdx.x * SS_COLS + 4 * tid;  // first owned column
+    const int ty0 = blockIdx.y * SS_ROWS;
+    const uint8_t* ia = a + static_cast<size_t>(n) * H * W;
+    const uint8_t* ib = b + static_cast<size_t>(n) * H * W;
+
+    uint32_t ring1[7][4], ringq[7][4], ringp[7][4];
+    uint32_t v1[4] = {0, 0, 0, 0}, vq[4] = {0, 0, 0, 0}, vp[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int s = 0; s < 7; ++s)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ring1[s][j] = ringq[s][j] = ringp[s][j] = 0;
+
+    float ssim_acc = 0.f;
+    uint32_t ssd = 0;
+    const float K1 = 6.5025f * 2401.0f;   // C1 * 49^2
+    const float K2 = 58.5225f * 2352.0f;  // C2 * 48 * 49
+
+    for (int rb = 0; rb < SS_ROWS + 6; rb += 7) {
+#pragma unroll
+        for (int s = 0; s < 7; ++s) {
+            const int i = rb + s;
+            if (i < SS_ROWS + 6) {
+                const int yin = ty0 - 3 + i;
+                uint32_t wa[3] = {0, 0, 0}, wb[3] = {0, 0, 0};
+                if (yin >= 0 && yin < H && xb - 4 < W) {
+                    const uint8_t* ra = ia + static_cast<size_t>(yin) * W;
+                    const uint8_t* rbp = ib + static_cast<size_t>(yin) * W;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        wa[k] = load_word_guarded(ra, xb - 4 + 4 * k, W, aligned);
+                        wb[k] = load_word_guarded(rbp, xb - 4 + 4 * k, W, aligned);
+                    }
+                }
+                // pixels xb-3 .. xb+6 = bytes 1..10 of the 12-byte span
+                uint32_t p1[10], pq[10], pp[10];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) {
+                    const int byte = k + 1;
+                    const uint32_t pa = (wa[byte >> 2] >> (8 * (byte & 3))) & 0xff;
+                    const uint32_t pb = (wb[byte >> 2] >> (8 * (byte & 3))) & 0xff;
+                    p1[k] = pa | (pb << 16);
+                    pq[k] = pa * pa + pb * pb;
+                    pp[k] = pa * pb;
+                }
+                if (yin >= ty0 && yin < ty0 + SS_ROWS) {  // squared error of the owned pixels (zero outside the image)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int dlt = static_cast<int>(p1[3 + j] & 0xffff) - static_cast<int>(p1[3 + j] >> 16);
+                        ssd += static_cast<uint32_t>(dlt * dlt);
+                    }
+                }
+                uint32_t h1[4], hq[4], hp[4];
+                h1[0] = p1[0] + p1[1] + p1[2] + p1[3] + p1[4] + p1[5] + p1[6];
+                hq[0] = pq[0] + pq[1] + pq[2] + pq[3] + pq[4] + pq[5] + pq[6];
+                hp[0] = pp[0] + pp[1] + pp[2] + pp[3] + pp[4] + pp[5] + pp[6];
+#pragma unroll
+                for (int j = 1; j < 4; ++j) {
+                    h1[j] = h1[j - 1] + p1[j + 6] - p1[j - 1];
+                    hq[j] = hq[j - 1] + pq[j + 6] - pq[j - 1];
+                    hp[j] = hp[j - 1] + pp[j + 6] - pp[j - 1];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v1[j] += h1[j] - ring1[s][j];
+                    vq[j] += hq[j] - ringq[s][j];
+                    vp[j] += hp[j] - ringp[s][j];
+                    ring1[s][j] = h1[j];
+                    ringq[s][j] = hq[j];
+                    ringp[s][j] = hp[j];
+                }
+                const int yo = yin - 3;  // window centre row of the sums now held
+                if (i >= 6 && yo >= 3 && yo < H - 3) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int xo = xb + j;
+                        if (xo >= 3 && xo < W - 3) {
+                            const int sx = static_cast<int>(v1[j] & 0xffff), sy = static_cast<int>(v1[j] >> 16);
+                            const int sxsy = sx * sy;
+                            const int sq2 = sx * sx + sy * sy;
+                            const float a1 = static_cast<float>(2 * sxsy) + K1;
+                            const float b1 = static_cast<float>(sq2) + K1;
+                            const float a2 = static_cast<float>(2 * (49 * static_cast<int>(vp[j]) - sxsy)) + K2;
+                            const float b2 = static_cast<float>(49 * static_cast<int>(vq[j]) - sq2) + K2;
+                            ssim_acc += (a1 * a2) / (b1 * b2);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // block reduction (fixed order -> deterministic partials)
+    double ds = static_cast<double>(ssim_acc);
+    unsigned long long du = ssd;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ds += __shfl_down_sync(0xffffffffu, ds, o);
+        du += __shfl_down_sync(0xffffffffu, du, o);
+    }
+    __shared__ double sh_s[SS_THREADS / 32];
+    __shared__ unsigned long long sh_u[SS_THREADS / 32];
+    if ((tid & 31) == 0) {
+        sh_s[tid >> 5] = ds;
+        sh_u[tid >> 5] = du;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double ts = 0.0;
+        unsigned long long tu = 0;
+        for (int k = 0; k < SS_THREADS / 32; ++k) {
+            ts += sh_s[k];
+            tu += sh_u[k];
+        }
+        const size_t slot = (static_cast<size_t>(n) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        part_ssim[slot] = ts;
+        part_ssd[slot] = tu;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ssim_psnr_finalize_kernel(const double* __restrict__ part_ssim, const unsigned long long* __restrict__ part_ssd,
+                          int nblk, int H, int W, double* __restrict__ out) {
+    const int n = blockIdx.x;
+    __shared__ double sh_s[256];
+    __shared__ unsigned long long sh_u[256];
+    double s = 0.0;
+    unsigned long long u = 0;
+    for (int i = threadIdx.x; i < nblk; i += 256) {
+        s += part_ssim[static_cast<size_t>(n) * nblk + i];
+        u += part_ssd[static_cast<size_t>(n) * nblk + i];
+    }
+    sh_s[threadIdx.x] = s;
+    sh_u[threadIdx.x] = u;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sh_s[threadIdx.x] += sh_s[threadIdx.x + o];
+            sh_u[threadIdx.x] += sh_u[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double mse = static_cast<double>(sh_u[0]) / (static_cast<double>(H) * W);
+        // skimage peak_signal_noise_ratio: 10*log10(data_range^2 / mse); identical images -> inf
+        out[2 * n + 0] = sh_u[0] == 0 ? __longlong_as_double(0x7ff0000000000000LL) : 10.0 * log10(65025.0 / mse);
+        out[2 * n + 1] = sh_s[0] / (static_cast<double>(H - 6) * (W - 6));
+    }
+}
+
+int grid_for(size_t work_items, int threads) {
+    size_t g = (work_items + threads - 1) / threads;
+    const size_t cap = 148 * 16;  // grid-stride loops: a few waves of the 148 SMs is enough
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+const char* last_launch_error() {
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace
+
+const char* stem_conv_launch(const StemDesc& d, cudaStream_t stream) {
+    if (d.cin < 1 || d.cin > ST_MAXC) return "stem: 1..8 input channels supported";
+    if (d.src[0].channels + d.src[1].channels != d.cin) return "stem: plane sources do not add up to cin";
+    if (d.N <= 0 || d.H <= 0 || d.W <= 0) return "stem: empty shape";
+    const long long tiles = static_cast<long long>(d.N) * ((d.H + ST_TH - 1) / ST_TH) * ((d.W + ST_TW - 1) / ST_TW);
+    if (tiles > 0x7fffffffLL) return "stem: too many tiles";
+    if (d.is_u8) stem_conv_kernel<true><<<static_cast<int>(tiles), 256, 0, stream>>>(d);
+    else stem_conv_kernel<false><<<static_cast<int>(tiles), 256, 0, stream>>>(d);
+    return last_launch_error();
+}
+
+const char* upsample2x_launch(const void* src, void* dst, int N, int h, int w, int C, cudaStream_t stream) {
+    if (C % 8) return "upsample: channels must be a multiple of 8";
+    if (N <= 0 || h <= 0 || w <= 0) return "upsample: empty shape";
+    const size_t total = static_cast<size_t>(N) * 4 * h * w * (C / 8);
+    upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(src),
+                                                                 static_cast<uint4*>(dst), N, h, w, C / 8);
+    return last_launch_error();
+}
+
+const char* pack_pair_launch(const uint8_t* f0, const uint8_t* f1, float* out, int N, int C, int H, int W,
+                             cudaStream_t stream) {
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return "pack: empty shape";
+    const size_t plane = static_cast<size_t>(H) * W;
+    const int vec = (plane % 16 == 0) && ((reinterpret_cast<uintptr_t>(f0) | reinterpret_cast<uintptr_t>(f1) |
+                                           reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+    const size_t items = static_cast<size_t>(N) * 2 * C * (vec ? plane / 16 : plane);
+    pack_pair_kernel<<<grid_for(items, 256), 256, 0, stream>>>(f0, f1, out, N, C, plane, vec);
+    return last_launch_error();
+}
+
+const char* head_post_launch(const float* y, uint8_t* out, size_t n, cudaStream_t stream) {
+    if (n == 0) return nullptr;
+    const int vec = (reinterpret_cast<uintptr_t>(y) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+    head_post_kernel<<<grid_for(vec ? (n + 15) / 16 : n, 256), 256, 0, stream>>>(y, out, n, vec);
+    return last_launch_error();
+}
+
+static void ssim_grid(int H, int W, int* gx, int* gy) {
+    *gx = (W + SS_COLS - 1) / SS_COLS;
+    *gy = (H + SS_ROWS - 1) / SS_ROWS;
+}
+
+size_t ssim_psnr_workspace_bytes(int N, int H, int W) {
+    int gx, gy;
+    ssim_grid(H, W, &gx, &gy);
+    return static_cast<size_t>(N) * gx * gy * 16;
+}
+
+const char* ssim_psnr_launch(const uint8_t* a, const uint8_t* b, int N, int H, int W, double* out, void* workspace,
+                             cudaStream_t stream) {
+    if (N <= 0) return "ssim: empty batch";
+    if (H < 7 || W < 7) return "ssim: win_size 7 exceeds image extent (skimage raises ValueError here too)";
+    if (N > 65535) return "ssim: at most 65535 image pairs per call";
+    if (!a || !b || !out || !workspace) return "ssim: null operand";
+    int gx, gy;
+    ssim_grid(H, W, &gx, &gy);
+    const int nblk = gx * gy;
+    double* part_ssim = static_cast<double*>(workspace);
+    unsigned long long* part_ssd = reinterpret_cast<unsigned long long*>(part_ssim + static_cast<size_t>(N) * nblk);
+    const int aligned = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) % 4 == 0);
+    ssim_psnr_kernel<<<dim3(gx, gy, N), SS_THREADS, 0, stream>>>(a, b, H, W, aligned, part_ssim, part_ssd);
+    const char* e = last_launch_error();
+    if (e) return e;
+    ssim_psnr_finalize_kernel<<<N, 256, 0, stream>>>(part_ssim, part_ssd, nblk, H, W, out);
+    return last_launch_error();
+}
+
+}  // namespace fi

@@ -1,0 +1,497 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for the UNet frame-synthesis path.
+//
+// Replaces, per launch, what the reference runs as separate eager ops (reference model/unet.py):
+//   conv3x3(pad 1, no bias) -> BatchNorm2d(eval) -> ReLU          unet.py:12-17  (BN folded into W / bias on the host)
+//   MaxPool2d(2)                                                   unet.py:28     (EPI_STORE_POOL: dual store)
+//   F.pad + torch.cat([skip, up], 1)                               unet.py:49-54  (second K-range source + OOB zero fill)
+//   ConvTranspose2d(k=2, s=2) + bias                               unet.py:43     (EPI_CONVT: 1-tap GEMM, pixel-scatter store)
+//   Conv2d(64, n_classes, 1) + bias and postprocess_image          unet.py:60, inference.py:54-61 (EPI_HEAD)
+//
+// GEMM view: M = pixels (one CTA tile = 8x16 pixels of one image), N = output channels, K = taps x input channels.
+// A operand: for every (tap, 64-channel slab) one TMA box {64ch,16,8,1} of the NHWC activation, start coordinate
+//            shifted by the tap; out-of-bounds elements are zero-filled by TMA = the conv zero padding (and F.pad).
+// B operand: BN-folded weights, bf16 [N][K] K-major, one TMA box {64, BLOCK_N} per K slab.
+// Both land in 128B-swizzled K-major smem tiles that tcgen05.mma reads through shared-memory descriptors.
+// Accumulators: fp32 in TMEM, double buffered (2 x BLOCK_N columns) so the epilogue of tile i overlaps tile i+1.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
+#include "conv_gemm.cuh"
+#include "ptx.cuh"
+
+#include <cstdio>
+#include <cstring>
+
+namespace fi {
+
+namespace {
+
+constexpr int NUM_THREADS = 192;
+constexpr int A_STAGE_BYTES = BLOCK_M * 128;             // 16 KB
+constexpr int STAGING_BYTES_PER_WARP = 2 * 4096;         // 2 x (32 rows x 128 B)
+constexpr int POOL_BYTES_PER_WARP = 2 * 1024;            // 2 x (8 rows x 128 B)
+constexpr int EPI_BYTES = 4 * (STAGING_BYTES_PER_WARP + POOL_BYTES_PER_WARP);
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_LIMIT = 232448;                       // 227 KB usable per CTA on sm_100
+
+__host__ __device__ constexpr int b_stage_bytes(int block_n) { return block_n * 128; }
+__host__ __device__ constexpr int num_stages(int block_n) {
+    int s = (SMEM_LIMIT - 1024 - BAR_BYTES - EPI_BYTES) / (A_STAGE_BYTES + b_stage_bytes(block_n));
+    return s > 8 ? 8 : s;
+}
+__host__ __device__ constexpr int smem_bytes(int block_n) {
+    return 1024 + num_stages(block_n) * (A_STAGE_BYTES + b_stage_bytes(block_n)) + EPI_BYTES + BAR_BYTES;
+}
+__host__ __device__ constexpr int tmem_cols(int block_n) { return 2 * block_n < 32 ? 32 : 2 * block_n; }
+
+struct TileCoord {
+    int nb, img, y0, x0;
+};
+__device__ __forceinline__ TileCoord decode_tile(int t, const ConvKernelParams& p) {
+    // Tiles that share a weight block are adjacent in time across the grid so the B slabs stay hot in L2.
+    const int per_img = p.tiles_y * p.tiles_x;
+    const int m_tiles = p.n_img * per_img;
+    TileCoord c;
+    c.nb = t / m_tiles;
+    int m = t - c.nb * m_tiles;
+    c.img = m / per_img;
+    m -= c.img * per_img;
+    const int ty = m / p.tiles_x;
+    c.y0 = ty * TILE_H;
+    c.x0 = (m - ty * p.tiles_x) * TILE_W;
+    return c;
+}
+
+template <int BLOCK_N, int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
+                 const __grid_constant__ CUtensorMap map_pool, const ConvKernelParams p) {
+    constexpr int STAGES = num_stages(BLOCK_N);
+    constexpr int B_STAGE_BYTES = b_stage_bytes(BLOCK_N);
+    constexpr uint32_t STAGE_TX = A_STAGE_BYTES + B_STAGE_BYTES;
+    constexpr int TMEM_COLS = tmem_cols(BLOCK_N);
+    constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    static_assert(MODE != EPI_HEAD || BLOCK_N == 64, "head epilogue consumes exactly 64 channels");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_b = smem_a + STAGES * A_STAGE_BYTES;
+    const uint32_t smem_stage = smem_b + STAGES * B_STAGE_BYTES;
+    const uint32_t smem_pool = smem_stage + 4 * STAGING_BYTES_PER_WARP;
+    const uint32_t smem_bar = smem_pool + 4 * POOL_BYTES_PER_WARP;
+    const uint32_t bar_full = smem_bar;                     // STAGES x 8 B
+    const uint32_t bar_empty = smem_bar + 8 * STAGES;       // STAGES x 8 B
+    const uint32_t bar_tfull = smem_bar + 16 * STAGES;      // 2 x 8 B
+    const uint32_t bar_tempty = bar_tfull + 16;             // 2 x 8 B
+    const uint32_t tmem_slot = bar_tempty + 16;             // 4 B
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a0);
+        tma_prefetch_desc(&map_a1);
+        tma_prefetch_desc(&map_b);
+        if (MODE != EPI_HEAD) tma_prefetch_desc(&map_out);
+        if (MODE == EPI_STORE_POOL) tma_prefetch_desc(&map_pool);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int total_tiles = p.n_blocks * p.n_img * p.tiles_y * p.tiles_x;
+    const int slabs = p.slabs0 + p.slabs1;
+    const int k_iters = p.taps * slabs;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (one lane)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(t, p);
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+                    const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+                    for (int s = 0; s < slabs; ++s) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t full = bar_full + 8 * stage;
+                        mbar_expect_tx(full, STAGE_TX);
+                        if (s < p.slabs0) {
+                            tma_load_4d(smem_a + stage * A_STAGE_BYTES, &map_a0, full, s * BLOCK_K, tc.x0 + dx,
+                                        tc.y0 + dy, tc.img);
+                        } else {
+                            tma_load_4d(smem_a + stage * A_STAGE_BYTES, &map_a1, full, (s - p.slabs0) * BLOCK_K,
+                                        tc.x0 + dx - p.off_x, tc.y0 + dy - p.off_y, tc.img);
+                        }
+                        tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full, (tap * slabs + s) * BLOCK_K,
+                                    tc.nb * BLOCK_N);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one lane)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < k_iters; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(smem_a + stage * A_STAGE_BYTES);
+                    const uint64_t db = umma_desc_sw128(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                        // +32 bytes along K inside the 128B swizzle row = +2 in the (addr >> 4) field
+                        umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
+                    }
+                    umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps 2..5
+        const int q = warp & 3;  // TMEM lanes [32q, 32q+32) <-> tile rows 2q, 2q+1
+        const uint32_t my_stage = smem_stage + q * STAGING_BYTES_PER_WARP;
+        const uint32_t my_pool = smem_pool + q * POOL_BYTES_PER_WARP;
+        int buf = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const TileCoord tc = decode_tile(t, p);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 64; ++c) {
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32b_x32(taddr + c * 64, v0);
+                tmem_ld_32x32b_x32(taddr + c * 64 + 32, v1);
+                tmem_ld_wait();
+                const int n_glob = tc.nb * BLOCK_N + c * 64;
+                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n_glob);
+                float f[64];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = __ldg(bias4 + j);
+                    f[4 * j + 0] = __uint_as_float(v0[4 * j + 0]) + b.x;
+                    f[4 * j + 1] = __uint_as_float(v0[4 * j + 1]) + b.y;
+                    f[4 * j + 2] = __uint_as_float(v0[4 * j + 2]) + b.z;
+                    f[4 * j + 3] = __uint_as_float(v0[4 * j + 3]) + b.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = __ldg(bias4 + 8 + j);
+                    f[32 + 4 * j + 0] = __uint_as_float(v1[4 * j + 0]) + b.x;
+                    f[32 + 4 * j + 1] = __uint_as_float(v1[4 * j + 1]) + b.y;
+                    f[32 + 4 * j + 2] = __uint_as_float(v1[4 * j + 2]) + b.z;
+                    f[32 + 4 * j + 3] = __uint_as_float(v1[4 * j + 3]) + b.w;
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
+                }
+
+                if constexpr (MODE == EPI_HEAD) {
+                    // 1x1 head on the fp32 (un-rounded) activations; thread = pixel.
+                    const int y = tc.y0 + 2 * q + (lane >> 4);
+                    const int x = tc.x0 + (lane & 15);
+                    const bool inside = (y < p.H) && (x < p.W);
+                    for (int k = 0; k < p.n_classes; ++k) {
+                        const float4* w4 = reinterpret_cast<const float4*>(p.head_w + k * 64);
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float4 w = __ldg(w4 + j);
+                            a0 = fmaf(f[4 * j + 0], w.x, a0);
+                            a1 = fmaf(f[4 * j + 1], w.y, a1);
+                            a2 = fmaf(f[4 * j + 2], w.z, a2);
+                            a3 = fmaf(f[4 * j + 3], w.w, a3);
+                        }
+                        const float yv = (a0 + a1) + (a2 + a3) + __ldg(p.head_b + k);
+                        if (inside) {
+                            const size_t o = ((static_cast<size_t>(tc.img) * p.n_classes + k) * p.H + y) * p.W + x;
+                            if (p.out_f32) p.out_f32[o] = yv;
+                            if (p.out_u8) {
+                                // postprocess_image (reference model/inference.py:54-61): (t+1)/2, clamp, *255, truncate
+                                float u = __fmul_rn(__fadd_rn(yv, 1.0f), 0.5f);
+                                u = fminf(fmaxf(u, 0.0f), 1.0f);
+                                p.out_u8[o] = static_cast<uint8_t>(__fmul_rn(u, 255.0f));
+                            }
+                        }
+                    }
+                } else {
+                    uint32_t pk[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                    // The staging buffer used two chunks ago must have been read by its TMA store.
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
+                    const uint32_t sbuf = my_stage + buf * 4096;
+                    const uint32_t row = sbuf + lane * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        st_shared_v4(row + ((j ^ (lane & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2],
+                                     pk[4 * j + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (MODE == EPI_CONVT) {
+                            const int a = n_glob / p.cout2;
+                            tma_store_5d(&map_out, sbuf, n_glob - a * p.cout2, tc.x0, a, tc.y0 + 2 * q, tc.img);
+                        } else {
+                            tma_store_4d(&map_out, sbuf, n_glob, tc.x0, tc.y0 + 2 * q, tc.img);
+                        }
+                    }
+                    if constexpr (MODE == EPI_STORE_POOL) {
+                        // 2x2 max over (rows 2q,2q+1) x (cols 2p,2p+1): bf16 max commutes with the rounding above.
+                        const uint32_t pbuf = my_pool + buf * 1024;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int pp = lane >> 2;
+                            const int j = (lane & 3) * 2 + i;
+                            const int r0 = 2 * pp, r1 = 2 * pp + 1, r2 = 16 + 2 * pp, r3 = 17 + 2 * pp;
+                            const uint4 m0 = ld_shared_v4(sbuf + r0 * 128 + ((j ^ (r0 & 7)) << 4));
+                            const uint4 m1 = ld_shared_v4(sbuf + r1 * 128 + ((j ^ (r1 & 7)) << 4));
+                            const uint4 m2 = ld_shared_v4(sbuf + r2 * 128 + ((j ^ (r2 & 7)) << 4));
+                            const uint4 m3 = ld_shared_v4(sbuf + r3 * 128 + ((j ^ (r3 & 7)) << 4));
+                            uint4 m;
+                            m.x = bf16x2_max(bf16x2_max(m0.x, m1.x), bf16x2_max(m2.x, m3.x));
+                            m.y = bf16x2_max(bf16x2_max(m0.y, m1.y), bf16x2_max(m2.y, m3.y));
+                            m.z = bf16x2_max(bf16x2_max(m0.z, m1.z), bf16x2_max(m2.z, m3.z));
+                            m.w = bf16x2_max(bf16x2_max(m0.w, m1.w), bf16x2_max(m2.w, m3.w));
+                            st_shared_v4(pbuf + pp * 128 + ((j ^ (pp & 7)) << 4), m.x, m.y, m.z, m.w);
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_4d(&map_pool, pbuf, n_glob, tc.x0 >> 1, (tc.y0 >> 1) + q, tc.img);
+                        }
+                    }
+                    if (lane == 0) tma_store_commit();
+                    buf ^= 1;
+                }
+            }
+            // All TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back to the MMA warp.
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+        if (MODE != EPI_HEAD && lane == 0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess) {
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        }
+    }
+    return fn;
+}
+
+// bf16 tensor map, 128B swizzle, zero OOB fill. dims/box are innermost-first; strides in elements for dims 1..rank-1.
+const char* encode_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                            const uint64_t* strides_elems, const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)";
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_elems[i] * 2;  // bytes
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return "tensor base address must be 16-byte aligned";
+    const CUresult r =
+        fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr,
+           bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        static thread_local char msg[96];
+        snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+        return msg;
+    }
+    return nullptr;
+}
+
+const char* encode_nhwc(CUtensorMap* map, const void* base, int n, int h, int w, int c, int box_w, int box_h) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(w), static_cast<uint64_t>(h),
+                              static_cast<uint64_t>(n)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(c), static_cast<uint64_t>(w) * c,
+                                 static_cast<uint64_t>(h) * w * c};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(box_w), static_cast<uint32_t>(box_h), 1};
+    return encode_bf16_map(map, base, 4, dims, strides, box);
+}
+
+template <int BLOCK_N, int MODE>
+const char* launch_inst(const ConvLaunch& l, cudaStream_t stream) {
+    auto kfn = conv_gemm_kernel<BLOCK_N, MODE>;
+    static bool configured = false;  // per instantiation; attribute is per-device-context but idempotent to set
+    constexpr int smem = smem_bytes(BLOCK_N);
+    if (!configured) {
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
+        configured = true;
+    }
+    kfn<<<l.grid, NUM_THREADS, smem, stream>>>(l.map_a0, l.map_a1, l.map_b, l.map_out, l.map_pool, l.p);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace
+
+const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
+    if (d.N <= 0 || d.H <= 0 || d.W <= 0) return "conv: empty shape";
+    if (d.taps != 9 && d.taps != 1) return "conv: taps must be 9 (3x3) or 1";
+    if (d.c0 <= 0 || d.c0 % BLOCK_K) return "conv: c0 must be a positive multiple of 64";
+    if (d.c1 < 0 || d.c1 % BLOCK_K) return "conv: c1 must be a multiple of 64";
+    if (d.c1 > 0 && !d.src1) return "conv: src1 missing";
+    if (!d.src0 || !d.wpack || !d.bias) return "conv: null operand";
+    if (d.n_total % 64) return "conv: n_total must be a multiple of 64";
+    int block_n = d.n_total % 256 == 0 ? 256 : (d.n_total % 128 == 0 ? 128 : 64);
+    if (d.mode == EPI_HEAD) {
+        if (d.n_total != 64) return "conv: head epilogue needs exactly 64 GEMM columns";
+        if (d.n_classes < 1 || !d.head_w || !d.head_b || (!d.out_f32 && !d.out_u8)) return "conv: head operands";
+        block_n = 64;
+    } else if (d.mode == EPI_CONVT) {
+        if (d.taps != 1 || d.c1 != 0) return "conv: transposed conv is a 1-tap single-source GEMM";
+        if (d.n_total % 256) return "conv: transposed conv needs 4*Cout to be a multiple of 256";
+        if (!d.dst) return "conv: dst missing";
+        block_n = 256;
+    } else if (d.mode == EPI_STORE || d.mode == EPI_STORE_POOL) {
+        if (!d.dst) return "conv: dst missing";
+        if (d.mode == EPI_STORE_POOL && (!d.dst_pool || d.H < 2 || d.W < 2)) return "conv: pooled dst missing";
+    } else {
+        return "conv: unknown epilogue mode";
+    }
+
+    ConvLaunch l;
+    memset(&l, 0, sizeof l);
+    const char* e;
+    if ((e = encode_nhwc(&l.map_a0, d.src0, d.N, d.H, d.W, d.c0, TILE_W, TILE_H))) return e;
+    if (d.c1 > 0) {
+        if ((e = encode_nhwc(&l.map_a1, d.src1, d.N, d.h1, d.w1, d.c1, TILE_W, TILE_H))) return e;
+    } else {
+        l.map_a1 = l.map_a0;
+    }
+    {
+        const uint64_t k_total = static_cast<uint64_t>(d.taps) * (d.c0 + d.c1);
+        const uint64_t dims[2] = {k_total, static_cast<uint64_t>(d.n_total)};
+        const uint64_t strides[1] = {k_total};
+        const uint32_t box[2] = {64, static_cast<uint32_t>(block_n)};
+        if ((e = encode_bf16_map(&l.map_b, d.wpack, 2, dims, strides, box))) return e;
+    }
+    l.map_out = l.map_a0;
+    l.map_pool = l.map_a0;
+    if (d.mode == EPI_STORE || d.mode == EPI_STORE_POOL) {
+        if ((e = encode_nhwc(&l.map_out, d.dst, d.N, d.H, d.W, d.n_total, TILE_W, 2))) return e;
+        if (d.mode == EPI_STORE_POOL) {
+            if ((e = encode_nhwc(&l.map_pool, d.dst_pool, d.N, d.H / 2, d.W / 2, d.n_total, TILE_W / 2, 1))) return e;
+        }
+    } else if (d.mode == EPI_CONVT) {
+        // dst [N, 2H, 2W, Cout] viewed as (b*Cout+co : 2Cout, j : W, a : 2, i : H, n : N)
+        const uint64_t cout = d.n_total / 4;
+        const uint64_t dims[5] = {2 * cout, static_cast<uint64_t>(d.W), 2, static_cast<uint64_t>(d.H),
+                                  static_cast<uint64_t>(d.N)};
+        const uint64_t strides[4] = {2 * cout, 2 * static_cast<uint64_t>(d.W) * cout,
+                                     4 * static_cast<uint64_t>(d.W) * cout,
+                                     4 * static_cast<uint64_t>(d.H) * d.W * cout};
+        const uint32_t box[5] = {64, TILE_W, 1, 2, 1};
+        if ((e = encode_bf16_map(&l.map_out, d.dst, 5, dims, strides, box))) return e;
+    }
+
+    ConvKernelParams& p = l.p;
+    p.tiles_x = (d.W + TILE_W - 1) / TILE_W;
+    p.tiles_y = (d.H + TILE_H - 1) / TILE_H;
+    p.n_img = d.N;
+    p.n_blocks = d.n_total / block_n;
+    p.taps = d.taps;
+    p.slabs0 = d.c0 / BLOCK_K;
+    p.slabs1 = d.c1 / BLOCK_K;
+    p.off_x = d.off_x;
+    p.off_y = d.off_y;
+    p.relu = d.relu;
+    p.cout2 = d.mode == EPI_CONVT ? d.n_total / 2 : 0;
+    p.H = d.H;
+    p.W = d.W;
+    p.n_classes = d.n_classes;
+    p.bias = d.bias;
+    p.head_w = d.head_w;
+    p.head_b = d.head_b;
+    p.out_f32 = d.out_f32;
+    p.out_u8 = d.out_u8;
+    l.block_n = block_n;
+    l.mode = d.mode;
+    const long long total = static_cast<long long>(p.n_blocks) * p.n_img * p.tiles_y * p.tiles_x;
+    if (total > 0x7fffffffLL) return "conv: too many tiles";
+    l.grid = static_cast<int>(total < num_sms ? total : num_sms);
+    l.flops = 2.0 * d.N * d.H * d.W * static_cast<double>(d.n_total) * d.taps * (d.c0 + d.c1);
+    if (d.mode == EPI_HEAD) l.flops += 2.0 * d.N * d.H * d.W * 64.0 * d.n_classes;
+    *out = l;
+    return nullptr;
+}
+
+const char* conv_launch(const ConvLaunch& l, cudaStream_t stream) {
+    switch (l.block_n * 4 + l.mode) {
+        case 64 * 4 + EPI_STORE: return launch_inst<64, EPI_STORE>(l, stream);
+        case 64 * 4 + EPI_STORE_POOL: return launch_inst<64, EPI_STORE_POOL>(l, stream);
+        case 64 * 4 + EPI_HEAD: return launch_inst<64, EPI_HEAD>(l, stream);
+        case 128 * 4 + EPI_STORE: return launch_inst<128, EPI_STORE>(l, stream);
+        case 128 * 4 + EPI_STORE_POOL: return launch_inst<128, EPI_STORE_POOL>(l, stream);
+        case 256 * 4 + EPI_STORE: return launch_inst<256, EPI_STORE>(l, stream);
+        case 256 * 4 + EPI_STORE_POOL: return launch_inst<256, EPI_STORE_POOL>(l, stream);
+        case 256 * 4 + EPI_CONVT: return launch_inst<256, EPI_CONVT>(l, stream);
+        default: return "conv: no kernel instantiation for this (block_n, mode)";
+    }
+}
+
+}  // namespace fi

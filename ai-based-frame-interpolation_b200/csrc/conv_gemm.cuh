@@ -1,0 +1,78 @@
+// Host-side interface of the tcgen05 implicit-GEMM convolution (conv_gemm.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace fi {
+
+// Pixel tile of one CTA: 8 rows x 16 columns of one image = 128 GEMM rows (= 128 TMEM lanes).
+constexpr int TILE_H = 8;
+constexpr int TILE_W = 16;
+constexpr int BLOCK_M = TILE_H * TILE_W;
+constexpr int BLOCK_K = 64;  // 64 bf16 channels = one 128-byte swizzle row
+
+enum EpiMode : int {
+    EPI_STORE = 0,       // bias(+ReLU) -> bf16 NHWC
+    EPI_STORE_POOL = 1,  // as above, plus the 2x2/stride-2 max-pooled tensor (floor semantics)
+    EPI_CONVT = 2,       // GEMM columns are (a,b,co) of a 2x2/stride-2 transposed conv: pixel-scatter store
+    EPI_HEAD = 3,        // 64-channel result stays in registers: 1x1 head + bias -> fp32 NCHW and/or u8
+};
+
+// One layer as the C ABI (include/fi_b200.h: fiConvDesc) describes it. Device pointers only.
+struct ConvDesc {
+    const void* src0;  // bf16 NHWC [N,H,W,c0]
+    int c0;
+    const void* src1;  // optional second K-range source, bf16 NHWC [N,h1,w1,c1] placed at (off_y,off_x) in the HxW frame
+    int c1, h1, w1, off_y, off_x;
+    const void* wpack;  // bf16 [n_total][taps*(c0+c1)], K index = tap*(c0+c1) + channel
+    const float* bias;  // fp32 [n_total]
+    int n_total;        // GEMM N: Cout, or 4*Cout for EPI_CONVT
+    int taps;           // 9 (3x3, zero pad 1) or 1
+    int mode;           // EpiMode
+    int relu;
+    void* dst;       // EPI_STORE*: [N,H,W,n_total]; EPI_CONVT: [N,2H,2W,n_total/4]
+    void* dst_pool;  // EPI_STORE_POOL: [N,H/2,W/2,n_total]
+    const float* head_w;  // EPI_HEAD: fp32 [n_classes][64]
+    const float* head_b;  // fp32 [n_classes]
+    int n_classes;
+    float* out_f32;    // EPI_HEAD: fp32 NCHW [N,n_classes,H,W] or null
+    uint8_t* out_u8;   // EPI_HEAD: u8  NCHW [N,n_classes,H,W] = trunc(clamp((y+1)/2,0,1)*255) or null
+    int N, H, W;
+};
+
+struct ConvKernelParams {
+    int tiles_x, tiles_y, n_img, n_blocks;
+    int taps, slabs0, slabs1;
+    int off_x, off_y;
+    int relu;
+    int cout2;  // EPI_CONVT: 2*Cout (columns per output-row parity a)
+    int H, W;
+    int n_classes;
+    const float* bias;
+    const float* head_w;
+    const float* head_b;
+    float* out_f32;
+    uint8_t* out_u8;
+};
+
+// A fully prepared launch: tensor maps are encoded once per (layer, shape) and reused every forward.
+struct ConvLaunch {
+    alignas(64) CUtensorMap map_a0;
+    alignas(64) CUtensorMap map_a1;
+    alignas(64) CUtensorMap map_b;
+    alignas(64) CUtensorMap map_out;
+    alignas(64) CUtensorMap map_pool;
+    ConvKernelParams p;
+    int block_n;
+    int mode;
+    int grid;
+    double flops;  // algorithmic FLOPs of this launch (2*MACs, no padding counted)
+};
+
+// Returns nullptr on success, else a static error string.
+const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out);
+const char* conv_launch(const ConvLaunch& l, cudaStream_t stream);
+
+}  // namespace fi

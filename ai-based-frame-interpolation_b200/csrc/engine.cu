@@ -1,0 +1,773 @@
+// Host side of libfi_b200.so: the C ABI (include/fi_b200.h), BatchNorm folding / weight repacking, the per-shape
+// activation arena + prepared launch list, and the forward schedule of the UNet (reference model/unet.py:84-95).
+#include "../../include/fi_b200.h"
+#include "aux_kernels.cuh"
+#include "conv_gemm.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) return fail(FI_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));        \
+    } while (0)
+#define KERNEL_TRY(expr)                                            \
+    do {                                                            \
+        const char* _m = (expr);                                    \
+        if (_m) return fail(FI_ERR_CUDA, "%s: %s", #expr, _m);      \
+    } while (0)
+
+uint16_t f32_to_bf16_rn(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);  // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return static_cast<uint16_t>(u >> 16);
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    cudaError_t upload(const void* host, size_t n) {
+        release();
+        cudaError_t e = cudaMalloc(&p, n ? n : 16);
+        if (e != cudaSuccess) return e;
+        bytes = n;
+        return cudaMemcpy(p, host, n, cudaMemcpyHostToDevice);
+    }
+};
+
+struct ConvW {     // one conv3x3+BN (or the transposed conv) after folding/packing
+    int cin = 0;   // K per tap
+    int n_total = 0;
+    DevBuf w;      // bf16 [n_total][taps*cin]
+    DevBuf b;      // fp32 [n_total]
+};
+
+struct Act {  // bf16 NHWC activation inside the arena
+    size_t off = 0;
+    int C = 0, H = 0, W = 0;
+    size_t bytes(int N) const { return static_cast<size_t>(N) * H * W * C * 2; }
+};
+
+enum StepKind { STEP_STEM, STEP_CONV, STEP_UPSAMPLE };
+struct Step {
+    StepKind kind;
+    fi::ConvLaunch conv;        // STEP_CONV
+    const void* src = nullptr;  // STEP_UPSAMPLE
+    void* dst = nullptr;        // STEP_STEM / STEP_UPSAMPLE
+    int h = 0, w = 0, C = 0;
+};
+
+struct Plan {
+    int N = 0, H = 0, W = 0;
+    DevBuf arena;
+    std::map<std::string, Act> acts;
+    std::vector<Step> steps;
+    int head_step = -1;
+    double flops = 0;
+    void reset() {
+        steps.clear();
+        acts.clear();
+        arena.release();
+        N = H = W = 0;
+        head_step = -1;
+        flops = 0;
+    }
+};
+
+}  // namespace
+
+struct fiNet {
+    int device = 0;
+    int n_channels = 2, n_classes = 1, bilinear = 0;
+    int num_sms = 148;
+    bool loaded = false;
+    DevBuf stem_w, stem_b;  // fp32 [9][cin][64], [64]
+    ConvW convs[17];        // inc.3, down{1-4}.{0,3}, up{1-4}.{0,3}
+    ConvW upT[4];           // ConvTranspose2d of up1..up4 (bilinear=False)
+    DevBuf head_w, head_b;  // fp32 [n_classes][64], [n_classes]
+    Plan plan;
+    // pinned staging for the host-buffer convenience call
+    void* pin_in = nullptr;
+    void* pin_out = nullptr;
+    size_t pin_in_bytes = 0, pin_out_bytes = 0;
+    DevBuf dev_in, dev_out;
+};
+
+namespace {
+
+// conv index helpers: 0 = inc.3; 1,2 = down1.{0,3}; ... 7,8 = down4; 9,10 = up1.{0,3}; ... 15,16 = up4
+struct ConvShape {
+    int cin, cout;
+};
+void conv_shapes(const fiNet* net, ConvShape (&cs)[17], ConvShape& stem, int (&upc)[4][2]) {
+    const int f = net->bilinear ? 2 : 1;
+    stem = {net->n_channels, 64};
+    cs[0] = {64, 64};
+    const int enc[5] = {64, 128, 256, 512, 1024 / f};
+    for (int i = 1; i <= 4; ++i) {
+        cs[2 * i - 1] = {enc[i - 1], enc[i]};
+        cs[2 * i] = {enc[i], enc[i]};
+    }
+    // Up(in, out): bilinear: DoubleConv(in, out, mid=in/2); else ConvT(in, in/2) + DoubleConv(in, out)
+    const int up_in[4] = {1024, 512, 256, 128};
+    const int up_out[4] = {512 / f, 256 / f, 128 / f, 64};
+    for (int i = 0; i < 4; ++i) {
+        const int mid = net->bilinear ? up_in[i] / 2 : up_out[i];
+        cs[9 + 2 * i] = {up_in[i], mid};
+        cs[10 + 2 * i] = {mid, up_out[i]};
+        upc[i][0] = net->bilinear ? up_in[i] / 2 : up_in[i];  // channels entering the upsample
+        upc[i][1] = up_in[i] / 2;                             // channels leaving it
+    }
+}
+
+std::string conv_prefix(int idx) {
+    char buf[64];
+    if (idx == 0) return "inc.double_conv.3";
+    if (idx <= 8) {
+        snprintf(buf, sizeof buf, "down%d.maxpool_conv.1.double_conv.%d", (idx + 1) / 2, (idx % 2) ? 0 : 3);
+        return buf;
+    }
+    const int u = (idx - 9) / 2 + 1;
+    snprintf(buf, sizeof buf, "up%d.conv.double_conv.%d", u, ((idx - 9) % 2) ? 3 : 0);
+    return buf;
+}
+std::string bn_of(const std::string& conv_key) {  // "...double_conv.0" -> "...double_conv.1"
+    std::string s = conv_key;
+    s.back() = static_cast<char>(s.back() + 1);
+    return s;
+}
+
+struct StateDict {
+    std::map<std::string, std::pair<const float*, int64_t>> m;
+    const float* get(const std::string& key, int64_t numel, std::string* err) const {
+        auto it = m.find(key);
+        if (it == m.end()) it = m.find("unet." + key);
+        if (it == m.end()) {
+            *err = "missing state-dict entry '" + key + "'";
+            return nullptr;
+        }
+        if (it->second.second != numel) {
+            char b[160];
+            snprintf(b, sizeof b, "size mismatch for '%s': got %lld elements, expected %lld", key.c_str(),
+                     static_cast<long long>(it->second.second), static_cast<long long>(numel));
+            *err = b;
+            return nullptr;
+        }
+        return it->second.first;
+    }
+};
+
+// BN(eval) fold, reference model/unet.py:13,16 (eps = 1e-5, nn.BatchNorm2d default).
+bool bn_fold(const StateDict& sd, const std::string& bn, int c, std::vector<double>* scale, std::vector<float>* shift,
+             std::string* err) {
+    const float* g = sd.get(bn + ".weight", c, err);
+    const float* b = g ? sd.get(bn + ".bias", c, err) : nullptr;
+    const float* mu = b ? sd.get(bn + ".running_mean", c, err) : nullptr;
+    const float* var = mu ? sd.get(bn + ".running_var", c, err) : nullptr;
+    if (!var) return false;
+    scale->resize(c);
+    shift->resize(c);
+    for (int i = 0; i < c; ++i) {
+        const double s = static_cast<double>(g[i]) / std::sqrt(static_cast<double>(var[i]) + 1e-5);
+        (*scale)[i] = s;
+        (*shift)[i] = static_cast<float>(static_cast<double>(b[i]) - static_cast<double>(mu[i]) * s);
+    }
+    return true;
+}
+
+int load_conv3x3(const StateDict& sd, const std::string& key, int cin, int cout, ConvW* out) {
+    std::string err;
+    const float* w = sd.get(key + ".weight", static_cast<int64_t>(cout) * cin * 9, &err);
+    std::vector<double> scale;
+    std::vector<float> shift;
+    if (!w || !bn_fold(sd, bn_of(key), cout, &scale, &shift, &err)) return fail(FI_ERR_WEIGHTS, "%s", err.c_str());
+    const size_t K = static_cast<size_t>(9) * cin;
+    std::vector<uint16_t> packed(static_cast<size_t>(cout) * K);
+    for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int t = 0; t < 9; ++t) {
+                const double v = static_cast<double>(w[(static_cast<size_t>(co) * cin + ci) * 9 + t]) * scale[co];
+                packed[co * K + static_cast<size_t>(t) * cin + ci] = f32_to_bf16_rn(static_cast<float>(v));
+            }
+    out->cin = cin;
+    out->n_total = cout;
+    CUDA_TRY(out->w.upload(packed.data(), packed.size() * 2));
+    CUDA_TRY(out->b.upload(shift.data(), shift.size() * 4));
+    return FI_OK;
+}
+
+int load_convT(const StateDict& sd, const std::string& key, int cin, int cout, ConvW* out) {
+    std::string err;
+    const float* w = sd.get(key + ".weight", static_cast<int64_t>(cin) * cout * 4, &err);  // [cin][cout][2][2]
+    const float* b = w ? sd.get(key + ".bias", cout, &err) : nullptr;
+    if (!b) return fail(FI_ERR_WEIGHTS, "%s", err.c_str());
+    std::vector<uint16_t> packed(static_cast<size_t>(4) * cout * cin);
+    std::vector<float> bias4(static_cast<size_t>(4) * cout);
+    for (int ab = 0; ab < 4; ++ab)
+        for (int co = 0; co < cout; ++co) {
+            bias4[static_cast<size_t>(ab) * cout + co] = b[co];
+            for (int ci = 0; ci < cin; ++ci)
+                packed[(static_cast<size_t>(ab) * cout + co) * cin + ci] =
+                    f32_to_bf16_rn(w[(static_cast<size_t>(ci) * cout + co) * 4 + ab]);
+        }
+    out->cin = cin;
+    out->n_total = 4 * cout;
+    CUDA_TRY(out->w.upload(packed.data(), packed.size() * 2));
+    CUDA_TRY(out->b.upload(bias4.data(), bias4.size() * 4));
+    return FI_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int build_plan(fiNet* net, int N, int H, int W) {
+    Plan& pl = net->plan;
+    if (pl.N == N && pl.H == H && pl.W == W && pl.arena.p) return FI_OK;
+    pl.reset();
+    if ((H >> 4) < 1 || (W >> 4) < 1) return fail(FI_ERR_INVALID, "input %dx%d is smaller than 16x16 (4 poolings)", H, W);
+
+    ConvShape cs[17], stem;
+    int upc[4][2];
+    conv_shapes(net, cs, stem, upc);
+
+    int hs[5], ws[5];
+    hs[0] = H;
+    ws[0] = W;
+    for (int i = 1; i < 5; ++i) {
+        hs[i] = hs[i - 1] / 2;
+        ws[i] = ws[i - 1] / 2;
+    }
+    size_t cursor = 0;
+    auto add = [&](const std::string& name, int C, int h, int w) {
+        Act a;
+        a.off = cursor;
+        a.C = C;
+        a.H = h;
+        a.W = w;
+        cursor = align_up(cursor + a.bytes(N), 1024);
+        pl.acts[name] = a;
+    };
+    const int enc_c[5] = {64, cs[2].cout, cs[4].cout, cs[6].cout, cs[8].cout};
+    add("inc.mid", 64, hs[0], ws[0]);
+    add("inc", 64, hs[0], ws[0]);
+    for (int i = 1; i <= 4; ++i) {
+        char nm[32];
+        snprintf(nm, sizeof nm, "pool%d", i);
+        add(nm, enc_c[i - 1], hs[i], ws[i]);
+        snprintf(nm, sizeof nm, "down%d.mid", i);
+        add(nm, enc_c[i], hs[i], ws[i]);
+        snprintf(nm, sizeof nm, "down%d", i);
+        add(nm, enc_c[i], hs[i], ws[i]);
+    }
+    for (int i = 0; i < 4; ++i) {
+        char nm[32];
+        const int lvl = 3 - i;  // skip level of up(i+1)
+        snprintf(nm, sizeof nm, "up%d.up", i + 1);
+        add(nm, upc[i][1], 2 * hs[lvl + 1], 2 * ws[lvl + 1]);
+        snprintf(nm, sizeof nm, "up%d.mid", i + 1);
+        add(nm, cs[9 + 2 * i].cout, hs[lvl], ws[lvl]);
+        if (i < 3) {
+            snprintf(nm, sizeof nm, "up%d", i + 1);
+            add(nm, cs[10 + 2 * i].cout, hs[lvl], ws[lvl]);
+        }
+    }
+    {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, cursor);
+        if (e != cudaSuccess)
+            return fail(FI_ERR_NOMEM, "activation arena of %zu bytes: %s", cursor, cudaGetErrorString(e));
+        pl.arena.p = p;
+        pl.arena.bytes = cursor;
+    }
+    auto ptr = [&](const std::string& name) -> void* {
+        return static_cast<char*>(pl.arena.p) + pl.acts.at(name).off;
+    };
+
+    pl.flops = 2.0 * N * H * W * 64.0 * 9 * stem.cin;
+    auto push_conv = [&](fi::ConvDesc d) -> int {
+        Step s;
+        s.kind = STEP_CONV;
+        d.N = N;
+        const char* e = fi::conv_prepare(d, net->num_sms, &s.conv);
+        if (e) return fail(FI_ERR_INVALID, "%s", e);
+        pl.flops += s.conv.flops;
+        pl.steps.push_back(s);
+        return FI_OK;
+    };
+    auto conv3 = [&](int idx, const std::string& src, const std::string& src1, const std::string& dst,
+                     const std::string& pool, int mode) -> int {
+        const Act& a = pl.acts.at(src);
+        fi::ConvDesc d;
+        memset(&d, 0, sizeof d);
+        d.src0 = ptr(src);
+        d.c0 = a.C;
+        d.H = a.H;
+        d.W = a.W;
+        if (!src1.empty()) {
+            const Act& b = pl.acts.at(src1);
+            d.src1 = ptr(src1);
+            d.c1 = b.C;
+            d.h1 = b.H;
+            d.w1 = b.W;
+            d.off_y = (a.H - b.H) / 2;  // F.pad(x1, [dX//2, dX-dX//2, dY//2, dY-dY//2]) reference model/unet.py:49-53
+            d.off_x = (a.W - b.W) / 2;
+        }
+        const ConvW& cw = net->convs[idx];
+        if (cw.cin != d.c0 + d.c1) return fail(FI_ERR_STATE, "internal: conv %d expects %d channels, got %d", idx, cw.cin, d.c0 + d.c1);
+        d.wpack = cw.w.p;
+        d.bias = static_cast<const float*>(cw.b.p);
+        d.n_total = cw.n_total;
+        d.taps = 9;
+        d.mode = mode;
+        d.relu = 1;
+        if (mode == fi::EPI_HEAD) {
+            d.head_w = static_cast<const float*>(net->head_w.p);
+            d.head_b = static_cast<const float*>(net->head_b.p);
+            d.n_classes = net->n_classes;
+            d.out_f32 = reinterpret_cast<float*>(16);  // patched per forward call
+        } else {
+            d.dst = ptr(dst);
+            if (mode == fi::EPI_STORE_POOL) d.dst_pool = ptr(pool);
+        }
+        return push_conv(d);
+    };
+
+    int rc;
+    {
+        Step s;
+        s.kind = STEP_STEM;
+        s.dst = ptr("inc.mid");
+        pl.steps.push_back(s);
+    }
+    if ((rc = conv3(0, "inc.mid", "", "inc", "pool1", fi::EPI_STORE_POOL))) return rc;
+    for (int i = 1; i <= 4; ++i) {
+        char pool[32], mid[32], out[32], nextpool[32];
+        snprintf(pool, sizeof pool, "pool%d", i);
+        snprintf(mid, sizeof mid, "down%d.mid", i);
+        snprintf(out, sizeof out, "down%d", i);
+        snprintf(nextpool, sizeof nextpool, "pool%d", i + 1);
+        if ((rc = conv3(2 * i - 1, pool, "", mid, "", fi::EPI_STORE))) return rc;
+        if ((rc = conv3(2 * i, mid, "", out, nextpool, i < 4 ? fi::EPI_STORE_POOL : fi::EPI_STORE))) return rc;
+    }
+    const char* skips[4] = {"down3", "down2", "down1", "inc"};
+    std::string below = "down4";
+    for (int i = 0; i < 4; ++i) {
+        char up[32], mid[32], out[32];
+        snprintf(up, sizeof up, "up%d.up", i + 1);
+        snprintf(mid, sizeof mid, "up%d.mid", i + 1);
+        snprintf(out, sizeof out, "up%d", i + 1);
+        const Act& lo = pl.acts.at(below);
+        if (net->bilinear) {
+            Step s;
+            s.kind = STEP_UPSAMPLE;
+            s.src = ptr(below);
+            s.dst = ptr(up);
+            s.h = lo.H;
+            s.w = lo.W;
+            s.C = lo.C;
+            pl.steps.push_back(s);
+        } else {
+            fi::ConvDesc d;
+            memset(&d, 0, sizeof d);
+            const ConvW& cw = net->upT[i];
+            d.src0 = ptr(below);
+            d.c0 = lo.C;
+            d.H = lo.H;
+            d.W = lo.W;
+            d.wpack = cw.w.p;
+            d.bias = static_cast<const float*>(cw.b.p);
+            d.n_total = cw.n_total;
+            d.taps = 1;
+            d.mode = fi::EPI_CONVT;
+            d.relu = 0;
+            d.dst = ptr(up);
+            if ((rc = push_conv(d))) return rc;
+        }
+        if ((rc = conv3(9 + 2 * i, skips[i], up, mid, "", fi::EPI_STORE))) return rc;
+        if (i < 3) {
+            if ((rc = conv3(10 + 2 * i, mid, "", out, "", fi::EPI_STORE))) return rc;
+        } else {
+            if ((rc = conv3(10 + 2 * i, mid, "", "", "", fi::EPI_HEAD))) return rc;
+            pl.head_step = static_cast<int>(pl.steps.size()) - 1;
+        }
+        below = out;
+    }
+    pl.N = N;
+    pl.H = H;
+    pl.W = W;
+    return FI_OK;
+}
+
+int check_planes(const fiNet* net, const fiPlanes* in0, const fiPlanes* in1) {
+    if (!in0 || !in0->ptr) return fail(FI_ERR_INVALID, "in0 is required");
+    const int c = in0->channels + (in1 ? in1->channels : 0);
+    if (in1 && !in1->ptr) return fail(FI_ERR_INVALID, "in1 has no data pointer");
+    if (c != net->n_channels)
+        return fail(FI_ERR_INVALID, "input planes provide %d channels, network expects %d", c, net->n_channels);
+    return FI_OK;
+}
+
+fi::PlaneSrc to_src(const fiPlanes* p) {
+    fi::PlaneSrc s;
+    memset(&s, 0, sizeof s);
+    if (p) {
+        s.ptr = p->ptr;
+        s.batch_stride = p->batch_stride;
+        s.chan_stride = p->chan_stride;
+        s.row_stride = p->row_stride;
+        s.px_stride = p->px_stride;
+        s.channels = p->channels;
+    }
+    return s;
+}
+
+int set_device(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    return FI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fiVersion(void) { return 100; }
+const char* fiLastError(void) { return g_err; }
+
+int fiNetCreate(fiNet** out, int device, int n_channels, int n_classes, int bilinear) {
+    if (!out) return fail(FI_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (n_channels < 1 || n_channels > 8) return fail(FI_ERR_INVALID, "n_channels must be in 1..8");
+    if (n_classes < 1 || n_classes > 4) return fail(FI_ERR_INVALID, "n_classes must be in 1..4");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(FI_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(FI_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+    int rc = set_device(device);
+    if (rc) return rc;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(FI_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major,
+                    prop.minor);
+    fiNet* net = new fiNet();
+    net->device = device;
+    net->n_channels = n_channels;
+    net->n_classes = n_classes;
+    net->bilinear = bilinear ? 1 : 0;
+    net->num_sms = prop.multiProcessorCount;
+    *out = net;
+    return FI_OK;
+}
+
+int fiNetDestroy(fiNet* net) {
+    if (!net) return FI_OK;
+    cudaSetDevice(net->device);
+    if (net->pin_in) cudaFreeHost(net->pin_in);
+    if (net->pin_out) cudaFreeHost(net->pin_out);
+    delete net;
+    return FI_OK;
+}
+
+int fiNetLoadWeights(fiNet* net, const char* const* names, const float* const* data_host, const int64_t* numel,
+                     int count) {
+    if (!net || !names || !data_host || !numel) return fail(FI_ERR_INVALID, "null argument");
+    int rc = set_device(net->device);
+    if (rc) return rc;
+    StateDict sd;
+    for (int i = 0; i < count; ++i) sd.m[names[i]] = {data_host[i], numel[i]};
+    net->loaded = false;
+    net->plan.reset();  // launches hold weight pointers
+
+    ConvShape cs[17], stem;
+    int upc[4][2];
+    conv_shapes(net, cs, stem, upc);
+    std::string err;
+    {   // stem: fp32 [tap][cin][64], BN folded (inc.double_conv.0 / .1)
+        const float* w = sd.get("inc.double_conv.0.weight", static_cast<int64_t>(64) * stem.cin * 9, &err);
+        std::vector<double> scale;
+        std::vector<float> shift;
+        if (!w || !bn_fold(sd, "inc.double_conv.1", 64, &scale, &shift, &err))
+            return fail(FI_ERR_WEIGHTS, "%s", err.c_str());
+        std::vector<float> ws(static_cast<size_t>(9) * stem.cin * 64);
+        for (int co = 0; co < 64; ++co)
+            for (int ci = 0; ci < stem.cin; ++ci)
+                for (int t = 0; t < 9; ++t)
+                    ws[(static_cast<size_t>(t) * stem.cin + ci) * 64 + co] = static_cast<float>(
+                        static_cast<double>(w[(static_cast<size_t>(co) * stem.cin + ci) * 9 + t]) * scale[co]);
+        CUDA_TRY(net->stem_w.upload(ws.data(), ws.size() * 4));
+        CUDA_TRY(net->stem_b.upload(shift.data(), shift.size() * 4));
+    }
+    for (int i = 0; i < 17; ++i)
+        if ((rc = load_conv3x3(sd, conv_prefix(i), cs[i].cin, cs[i].cout, &net->convs[i]))) return rc;
+    if (!net->bilinear) {
+        for (int i = 0; i < 4; ++i) {
+            char key[32];
+            snprintf(key, sizeof key, "up%d.up", i + 1);
+            if ((rc = load_convT(sd, key, upc[i][0], upc[i][1], &net->upT[i]))) return rc;
+        }
+    }
+    {
+        const float* w = sd.get("outc.conv.weight", static_cast<int64_t>(net->n_classes) * 64, &err);
+        const float* b = w ? sd.get("outc.conv.bias", net->n_classes, &err) : nullptr;
+        if (!b) return fail(FI_ERR_WEIGHTS, "%s", err.c_str());
+        CUDA_TRY(net->head_w.upload(w, static_cast<size_t>(net->n_classes) * 64 * 4));
+        CUDA_TRY(net->head_b.upload(b, static_cast<size_t>(net->n_classes) * 4));
+    }
+    net->loaded = true;
+    return FI_OK;
+}
+
+int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dtype, float* out_f32, uint8_t* out_u8,
+                 int N, int H, int W, void* stream) {
+    if (!net) return fail(FI_ERR_INVALID, "net is null");
+    if (!net->loaded) return fail(FI_ERR_STATE, "fiNetLoadWeights has not been called");
+    if (N <= 0 || H <= 0 || W <= 0) return fail(FI_ERR_INVALID, "empty batch or image");
+    if (!out_f32 && !out_u8) return fail(FI_ERR_INVALID, "no output buffer");
+    if (in_dtype != FI_IN_F32 && in_dtype != FI_IN_U8) return fail(FI_ERR_INVALID, "unknown input dtype");
+    int rc = check_planes(net, in0, in1);
+    if (rc) return rc;
+    if ((rc = set_device(net->device))) return rc;
+    if ((rc = build_plan(net, N, H, W))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Plan& pl = net->plan;
+    for (size_t i = 0; i < pl.steps.size(); ++i) {
+        Step& s = pl.steps[i];
+        if (s.kind == STEP_STEM) {
+            fi::StemDesc d;
+            memset(&d, 0, sizeof d);
+            d.src[0] = to_src(in0);
+            d.src[1] = to_src(in1);
+            d.is_u8 = in_dtype == FI_IN_U8;
+            d.cin = net->n_channels;
+            d.N = N;
+            d.H = H;
+            d.W = W;
+            d.w = static_cast<const float*>(net->stem_w.p);
+            d.bias = static_cast<const float*>(net->stem_b.p);
+            d.dst = s.dst;
+            KERNEL_TRY(fi::stem_conv_launch(d, st));
+        } else if (s.kind == STEP_UPSAMPLE) {
+            KERNEL_TRY(fi::upsample2x_launch(s.src, s.dst, N, s.h, s.w, s.C, st));
+        } else {
+            if (static_cast<int>(i) == pl.head_step) {
+                s.conv.p.out_f32 = out_f32;
+                s.conv.p.out_u8 = out_u8;
+            }
+            KERNEL_TRY(fi::conv_launch(s.conv, st));
+        }
+    }
+    return FI_OK;
+}
+
+int fiNetInterpolateHostU8(fiNet* net, const uint8_t* frame1_host, const uint8_t* frame2_host, int channels_per_frame,
+                           uint8_t* out_host, int N, int H, int W, void* stream) {
+    if (!net || !frame1_host || !frame2_host || !out_host) return fail(FI_ERR_INVALID, "null argument");
+    if (2 * channels_per_frame != net->n_channels)
+        return fail(FI_ERR_INVALID, "2 x %d channels per frame != n_channels %d", channels_per_frame, net->n_channels);
+    if (N <= 0 || H <= 0 || W <= 0) return fail(FI_ERR_INVALID, "empty batch or image");
+    int rc = set_device(net->device);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t frame_bytes = static_cast<size_t>(N) * channels_per_frame * H * W;
+    const size_t out_bytes = static_cast<size_t>(N) * net->n_classes * H * W;
+    if (net->pin_in_bytes < 2 * frame_bytes) {
+        if (net->pin_in) cudaFreeHost(net->pin_in);
+        net->pin_in = nullptr;
+        net->pin_in_bytes = 0;
+        CUDA_TRY(cudaMallocHost(&net->pin_in, 2 * frame_bytes));
+        net->pin_in_bytes = 2 * frame_bytes;
+        net->dev_in.release();
+        CUDA_TRY(cudaMalloc(&net->dev_in.p, 2 * frame_bytes));
+        net->dev_in.bytes = 2 * frame_bytes;
+    }
+    if (net->pin_out_bytes < out_bytes) {
+        if (net->pin_out) cudaFreeHost(net->pin_out);
+        net->pin_out = nullptr;
+        net->pin_out_bytes = 0;
+        CUDA_TRY(cudaMallocHost(&net->pin_out, out_bytes));
+        net->pin_out_bytes = out_bytes;
+        net->dev_out.release();
+        CUDA_TRY(cudaMalloc(&net->dev_out.p, out_bytes));
+        net->dev_out.bytes = out_bytes;
+    }
+    memcpy(net->pin_in, frame1_host, frame_bytes);
+    memcpy(static_cast<char*>(net->pin_in) + frame_bytes, frame2_host, frame_bytes);
+    CUDA_TRY(cudaMemcpyAsync(net->dev_in.p, net->pin_in, 2 * frame_bytes, cudaMemcpyHostToDevice, st));
+    fiPlanes p0, p1;
+    p0.ptr = net->dev_in.p;
+    p0.channels = channels_per_frame;
+    p0.px_stride = 1;
+    p0.row_stride = W;
+    p0.chan_stride = static_cast<int64_t>(H) * W;
+    p0.batch_stride = p0.chan_stride * channels_per_frame;
+    p1 = p0;
+    p1.ptr = static_cast<const uint8_t*>(net->dev_in.p) + frame_bytes;
+    rc = fiNetForward(net, &p0, &p1, FI_IN_U8, nullptr, static_cast<uint8_t*>(net->dev_out.p), N, H, W, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(net->pin_out, net->dev_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(out_host, net->pin_out, out_bytes);
+    return FI_OK;
+}
+
+int fiNetForwardCost(fiNet* net, int N, int H, int W, double* flops, int* launches) {
+    if (!net) return fail(FI_ERR_INVALID, "net is null");
+    if (!net->loaded) return fail(FI_ERR_STATE, "fiNetLoadWeights has not been called");
+    int rc = set_device(net->device);
+    if (rc) return rc;
+    if ((rc = build_plan(net, N, H, W))) return rc;
+    if (flops) *flops = net->plan.flops;
+    if (launches) *launches = static_cast<int>(net->plan.steps.size());
+    return FI_OK;
+}
+
+int fiNetReadActivation(fiNet* net, const char* name, float* out_host, int64_t capacity, int* C, int* H, int* W) {
+    if (!net || !name || !out_host) return fail(FI_ERR_INVALID, "null argument");
+    Plan& pl = net->plan;
+    auto it = pl.acts.find(name);
+    if (!pl.arena.p || it == pl.acts.end()) return fail(FI_ERR_INVALID, "no activation named '%s' in the current plan", name);
+    const Act& a = it->second;
+    const int64_t n = static_cast<int64_t>(pl.N) * a.C * a.H * a.W;
+    if (capacity < n) return fail(FI_ERR_INVALID, "buffer too small: need %lld floats", static_cast<long long>(n));
+    int rc = set_device(net->device);
+    if (rc) return rc;
+    std::vector<uint16_t> raw(static_cast<size_t>(n));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(raw.data(), static_cast<char*>(pl.arena.p) + a.off, raw.size() * 2, cudaMemcpyDeviceToHost));
+    for (int nn = 0; nn < pl.N; ++nn)
+        for (int y = 0; y < a.H; ++y)
+            for (int x = 0; x < a.W; ++x)
+                for (int c = 0; c < a.C; ++c) {
+                    const uint32_t bits = static_cast<uint32_t>(raw[((static_cast<size_t>(nn) * a.H + y) * a.W + x) * a.C + c]) << 16;
+                    float f;
+                    memcpy(&f, &bits, 4);
+                    out_host[((static_cast<size_t>(nn) * a.C + c) * a.H + y) * a.W + x] = f;
+                }
+    if (C) *C = a.C;
+    if (H) *H = a.H;
+    if (W) *W = a.W;
+    return FI_OK;
+}
+
+int fiConvGemm(const fiConvDesc* desc, void* stream) {
+    if (!desc) return fail(FI_ERR_INVALID, "desc is null");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    fi::ConvDesc d;
+    memset(&d, 0, sizeof d);
+    d.src0 = desc->src0;
+    d.c0 = desc->c0;
+    d.src1 = desc->src1;
+    d.c1 = desc->c1;
+    d.h1 = desc->h1;
+    d.w1 = desc->w1;
+    d.off_y = desc->off_y;
+    d.off_x = desc->off_x;
+    d.wpack = desc->wpack;
+    d.bias = desc->bias;
+    d.n_total = desc->n_total;
+    d.taps = desc->taps;
+    d.mode = desc->mode;
+    d.relu = desc->relu;
+    d.dst = desc->dst;
+    d.dst_pool = desc->dst_pool;
+    d.head_w = desc->head_w;
+    d.head_b = desc->head_b;
+    d.n_classes = desc->n_classes;
+    d.out_f32 = desc->out_f32;
+    d.out_u8 = desc->out_u8;
+    d.N = desc->N;
+    d.H = desc->H;
+    d.W = desc->W;
+    fi::ConvLaunch l;
+    const char* e = fi::conv_prepare(d, sms, &l);
+    if (e) return fail(FI_ERR_INVALID, "%s", e);
+    KERNEL_TRY(fi::conv_launch(l, static_cast<cudaStream_t>(stream)));
+    return FI_OK;
+}
+
+int fiStemConv(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const float* w, const float* bias, void* dst,
+               int N, int H, int W, void* stream) {
+    if (!in0 || !w || !bias || !dst) return fail(FI_ERR_INVALID, "null argument");
+    fi::StemDesc d;
+    memset(&d, 0, sizeof d);
+    d.src[0] = to_src(in0);
+    d.src[1] = to_src(in1);
+    d.is_u8 = in_dtype == FI_IN_U8;
+    d.cin = in0->channels + (in1 ? in1->channels : 0);
+    d.N = N;
+    d.H = H;
+    d.W = W;
+    d.w = w;
+    d.bias = bias;
+    d.dst = dst;
+    const char* e = fi::stem_conv_launch(d, static_cast<cudaStream_t>(stream));
+    if (e) return fail(FI_ERR_INVALID, "%s", e);
+    return FI_OK;
+}
+
+int fiUpsample2x(const void* src, void* dst, int N, int h, int w, int C, void* stream) {
+    if (!src || !dst) return fail(FI_ERR_INVALID, "null argument");
+    const char* e = fi::upsample2x_launch(src, dst, N, h, w, C, static_cast<cudaStream_t>(stream));
+    if (e) return fail(FI_ERR_INVALID, "%s", e);
+    return FI_OK;
+}
+
+int fiPackPairU8(const uint8_t* frame1, const uint8_t* frame2, float* out, int N, int C, int H, int W, void* stream) {
+    if (!frame1 || !frame2 || !out) return fail(FI_ERR_INVALID, "null argument");
+    const char* e = fi::pack_pair_launch(frame1, frame2, out, N, C, H, W, static_cast<cudaStream_t>(stream));
+    if (e) return fail(FI_ERR_INVALID, "%s", e);
+    return FI_OK;
+}
+
+int fiHeadPostU8(const float* logits, uint8_t* out, size_t n, void* stream) {
+    if (n && (!logits || !out)) return fail(FI_ERR_INVALID, "null argument");
+    const char* e = fi::head_post_launch(logits, out, n, static_cast<cudaStream_t>(stream));
+    if (e) return fail(FI_ERR_INVALID, "%s", e);
+    return FI_OK;
+}
+
+size_t fiSsimPsnrWorkspaceBytes(int N, int H, int W) {
+    if (N <= 0 || H <= 0 || W <= 0) return 0;
+    return fi::ssim_psnr_workspace_bytes(N, H, W);
+}
+
+int fiSsimPsnrU8(const uint8_t* pred, const uint8_t* target, int N, int H, int W, double* out, void* workspace,
+                 void* stream) {
+    const char* e = fi::ssim_psnr_launch(pred, target, N, H, W, out, workspace, static_cast<cudaStream_t>(stream));
+    if (e) return fail(FI_ERR_INVALID, "%s", e);
+    return FI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+/* fi_b200.h — C ABI of the B200-native UNet frame-synthesis path (libfi_b200.so).
+ *
+ * The reference (daultanigaurav/AI-BASED-FRAME-INTERPOLATION) has no FFI: its boundary for this path is the Python
+ * module surface of model/unet.py, model/inference.py and model/evaluation.py. Each entry point below names the
+ * reference interface it replaces (file:line, relative to the reference root). The Python drop-ins in
+ * ai-based-frame-interpolation_b200/model/ bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative fiStatus; fiLastError() gives the thread-local message;
+ *   - nothing aborts or throws across the boundary;
+ *   - all pointers are DEVICE pointers unless the parameter name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; calls are stream-ordered and never synchronise, except the
+ *     *_host convenience calls (documented below) and fiNetCreate/fiNetLoadWeights/fiNetDestroy;
+ *   - a fiNet must not be used from two threads at once (one handle per worker);
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with FI_ERR_CUDA.
+ */
+#ifndef FI_B200_H
+#define FI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum fiStatus {
+    FI_OK = 0,
+    FI_ERR_INVALID = -1, /* bad argument / unsupported shape */
+    FI_ERR_CUDA = -2,    /* CUDA runtime or driver error */
+    FI_ERR_STATE = -3,   /* e.g. forward before weights are loaded */
+    FI_ERR_WEIGHTS = -4, /* missing / mis-sized state-dict entry */
+    FI_ERR_NOMEM = -5
+} fiStatus;
+
+int fiVersion(void);
+const char* fiLastError(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Whole-network handle: replaces UNet / FrameInterpolationUNet (model/unet.py:65-112) in eval mode.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct fiNet fiNet;
+
+/* UNet(n_channels, n_classes, bilinear) — model/unet.py:66. n_channels in 1..8, n_classes in 1..4. */
+int fiNetCreate(fiNet** out, int device, int n_channels, int n_classes, int bilinear);
+int fiNetDestroy(fiNet* net);
+
+/* load_state_dict (model/inference.py:83-94, schema SURVEY.md A.5). names[i] are state-dict keys with or without the
+ * "unet." prefix; data_host[i] is the fp32 host tensor, numel[i] its element count. Eval-mode BatchNorm
+ * (model/unet.py:13,16) is folded here: W' = W*gamma/sqrt(var+eps) (rounded once to bf16), b' = beta - mean*scale. */
+int fiNetLoadWeights(fiNet* net, const char* const* names, const float* const* data_host, const int64_t* numel,
+                     int count);
+
+/* One group of input channel planes: element (n,c,y,x) at ptr[n*batch_stride + c*chan_stride + y*row_stride +
+ * x*px_stride] (strides in ELEMENTS). Covers NCHW fp32 tensors, planar u8 frames and interleaved HWC u8 frames. */
+typedef struct fiPlanes {
+    const void* ptr;
+    int64_t batch_stride, chan_stride, row_stride, px_stride;
+    int channels;
+} fiPlanes;
+
+#define FI_IN_F32 0 /* already-normalised fp32 (what preprocess_image returns, model/inference.py:11-41) */
+#define FI_IN_U8 1  /* raw uint8 pixels; u8/255*2-1 is applied in the stem kernel (model/inference.py:32-35) */
+
+/* FrameInterpolationUNet.forward(frame1, frame2) (model/unet.py:105-112) / UNet.forward(x) (model/unet.py:84-95):
+ * channels of in0 followed by channels of in1 (in1 may be NULL) form the n_channels input (the torch.cat of
+ * unet.py:109 is fused into the stem loader). Outputs, either may be NULL but not both:
+ *   out_f32: fp32 NCHW [N, n_classes, H, W] logits (what forward() returns);
+ *   out_u8 : uint8 NCHW [N, n_classes, H, W] = postprocess_image(logits) (model/inference.py:43-63). */
+int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dtype, float* out_f32, uint8_t* out_u8,
+                 int N, int H, int W, void* stream);
+
+/* interpolate_frames + postprocess_image with HOST buffers (model/inference.py:101-122, 43-63): planar u8 frames
+ * [N, C, H, W] on the host in, u8 [N, n_classes, H, W] on the host out. Copies through internal pinned staging buffers
+ * on `stream` and synchronises it before returning. */
+int fiNetInterpolateHostU8(fiNet* net, const uint8_t* frame1_host, const uint8_t* frame2_host, int channels_per_frame,
+                           uint8_t* out_host, int N, int H, int W, void* stream);
+
+/* Algorithmic FLOPs (2*MACs, no padding) of one forward at this shape, and the number of kernel launches it makes. */
+int fiNetForwardCost(fiNet* net, int N, int H, int W, double* flops, int* launches);
+/* Debug tap: copy an intermediate activation (bf16 NHWC) of the last forward to the host as fp32 NCHW.
+ * name in {inc, down1..down4, up1..up4 (block outputs), up1.up..up4.up (upsampled tensors)}. */
+int fiNetReadActivation(fiNet* net, const char* name, float* out_host, int64_t capacity, int* C, int* H, int* W);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Single layers (the same kernels the handle launches), for layer-level parity tests and reuse.
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define FI_EPI_STORE 0      /* conv3x3+BN+ReLU -> bf16 NHWC                         (DoubleConv, model/unet.py:5-21)  */
+#define FI_EPI_STORE_POOL 1 /* ... plus MaxPool2d(2) of the result                  (Down, model/unet.py:23-33)       */
+#define FI_EPI_CONVT 2      /* ConvTranspose2d(k=2,s=2)+bias as a 1-tap GEMM        (Up, model/unet.py:43)            */
+#define FI_EPI_HEAD 3       /* ... plus Conv2d(64,n_classes,1)+bias (+postprocess)  (OutConv, model/unet.py:57-63)    */
+
+typedef struct fiConvDesc {
+    const void* src0;   /* bf16 NHWC [N,H,W,c0] */
+    int c0;
+    const void* src1;   /* optional: bf16 NHWC [N,h1,w1,c1], placed at (off_y,off_x) of the HxW frame; zero elsewhere.
+                           K-range [c0, c0+c1) — the fused F.pad + torch.cat([skip, up]) of model/unet.py:49-54 */
+    int c1, h1, w1, off_y, off_x;
+    const void* wpack;  /* bf16 [n_total][taps*(c0+c1)], K index = tap*(c0+c1)+channel, tap = 3*ky+kx */
+    const float* bias;  /* fp32 [n_total] */
+    int n_total;        /* Cout, or 4*Cout ordered (ky,kx,co) for FI_EPI_CONVT */
+    int taps;           /* 9 or 1 */
+    int mode;           /* FI_EPI_* */
+    int relu;
+    void* dst;          /* STORE*: bf16 [N,H,W,n_total]; CONVT: bf16 [N,2H,2W,n_total/4] */
+    void* dst_pool;     /* STORE_POOL: bf16 [N,H/2,W/2,n_total] */
+    const float* head_w; /* HEAD: fp32 [n_classes][64] */
+    const float* head_b; /* HEAD: fp32 [n_classes] */
+    int n_classes;
+    float* out_f32;     /* HEAD: fp32 NCHW [N,n_classes,H,W] or NULL */
+    uint8_t* out_u8;    /* HEAD: u8 NCHW or NULL */
+    int N, H, W;
+} fiConvDesc;
+
+int fiConvGemm(const fiConvDesc* desc, void* stream);
+
+/* inc.double_conv.0..2 (model/unet.py:12-14) on raw planes: w fp32 [9][cin][64] (BN folded), bias fp32 [64],
+ * dst bf16 NHWC [N,H,W,64]. */
+int fiStemConv(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const float* w, const float* bias, void* dst,
+               int N, int H, int W, void* stream);
+/* nn.Upsample(scale_factor=2, bilinear, align_corners=True) (model/unet.py:40): bf16 NHWC [N,h,w,C] -> [N,2h,2w,C]. */
+int fiUpsample2x(const void* src, void* dst, int N, int h, int w, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Memory-bound kernels of the path.
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* preprocess_image normalisation (model/inference.py:32-35) + the frame-pair torch.cat (model/unet.py:109):
+ * two u8 planar batches [N,C,H,W] -> fp32 NCHW [N,2C,H,W]. */
+int fiPackPairU8(const uint8_t* frame1, const uint8_t* frame2, float* out, int N, int C, int H, int W, void* stream);
+/* postprocess_image (model/inference.py:43-63) on n fp32 values: trunc(clamp((t+1)/2,0,1)*255). */
+int fiHeadPostU8(const float* logits, uint8_t* out, size_t n, void* stream);
+/* compute_psnr / compute_ssim (model/evaluation.py:194-218 = evaluation_simple.py:103-109; scikit-image semantics,
+ * data_range=255) for N u8 image pairs [N,H,W]: out[2n] = PSNR (dB, +inf when identical), out[2n+1] = SSIM. */
+size_t fiSsimPsnrWorkspaceBytes(int N, int H, int W);
+int fiSsimPsnrU8(const uint8_t* pred, const uint8_t* target, int N, int H, int W, double* out, void* workspace,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FI_B200_H */
