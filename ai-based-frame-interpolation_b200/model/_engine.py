@@ -181,7 +181,7 @@ class Net:
             check(lib().fiNetForwardCost(self._h, n, h, w, C.byref(fl), C.byref(ln)))
         return fl.value, ln.value
 
-    def read_activation(self, name, n, max_elems=1 << 28):
+    def read_activation(self, name, n, max_elems=1 << 24):
         buf = torch.empty(max_elems, dtype=torch.float32)
         c, h, w = C.c_int(), C.c_int(), C.c_int()
         check(lib().fiNetReadActivation(self._h, name.encode(), buf.data_ptr(), max_elems, C.byref(c), C.byref(h),

@@ -1,6 +1,6 @@
 """Layer-level parity of the tcgen05 implicit-GEMM kernel (through the C ABI, fiConvGemm) against an fp64-accumulated
-CPU convolution of the same bf16-rounded operands. Tolerance: the result is rounded once to bf16 (rel 2^-9) after an
-fp32 accumulation, so |err| <= 2^-8 * |ref| + 1e-3 is a strict bound for these magnitudes."""
+CPU convolution of the same bf16-rounded operands. Tolerance: the kernel accumulates in fp32 and rounds once to bf16,
+so it may land on the bf16 neighbour of the rounded fp64 result: |err| <= 1 bf16 ulp <= 2^-7 * |ref| (+1e-3 near 0)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -15,7 +15,7 @@ def close(a, b, what):
     assert a.shape == b.shape, (what, a.shape, b.shape)
     assert not torch.isnan(a).any(), f"{what}: NaN in output (unwritten elements?)"
     err = (a - b).abs()
-    tol = 2.0 ** -8 * b.abs() + 1e-3
+    tol = 2.0 ** -7 * b.abs() + 1e-3
     bad = (err > tol)
     assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} mismatches, max err {err.max():.4g}, " \
                           f"first at {bad.nonzero()[0].tolist()}"

@@ -1,0 +1,129 @@
+"""Whole-network parity: the drop-in UNet (CUDA path through the C ABI) against the CPU oracle on identical random-init
+weights and synthetic inputs.
+
+Tolerances (BASELINE.json north_star): bf16 path max |err| <= 2e-2 in [0,1] pixel units and PSNR >= 45 dB. The reference
+output is in [-1,1] units (postprocess maps (y+1)/2), so logits are compared at half scale. The default-init fixture is
+nearly constant, hence the additional relative-error bounds per tapped layer and the stressed fixture."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+from model.unet import UNet, FrameInterpolationUNet
+
+pytestmark = pytest.mark.gpu
+
+
+def psnr_unit(a, b):
+    mse = float(((a - b) ** 2).mean())
+    return 99.0 if mse == 0 else 10 * np.log10(1.0 / mse)
+
+
+def build(sd, device, n_channels=2, n_classes=1, bilinear=False, wrapper=True):
+    m = FrameInterpolationUNet(bilinear=bilinear) if wrapper else UNet(n_channels, n_classes, bilinear)
+    m.load_state_dict(sd)
+    return m.to(device).eval()
+
+
+def frames(seed, n, c, h, w):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (n, c, h, w), generator=g, dtype=torch.uint8)
+
+
+@pytest.mark.parametrize("bilinear", [False, True])
+@pytest.mark.parametrize("n,h,w", [(1, 64, 64), (2, 48, 80), (1, 70, 54), (1, 135, 240)])
+def test_default_init_parity(cuda_device, bilinear, n, h, w):
+    sd = O.init_state_dict(0, 2, 1, bilinear)
+    m = build(sd, cuda_device, bilinear=bilinear)
+    f1, f2 = frames(1, n, 1, h, w), frames(2, n, 1, h, w)
+    x1, x2 = O.preprocess_u8(f1.numpy()), O.preprocess_u8(f2.numpy())
+    taps = {}
+    ref = O.unet_forward(sd, torch.cat([x1, x2], 1), taps)
+    got = m(x1.to(cuda_device), x2.to(cuda_device)).cpu()
+    assert got.shape == ref.shape == (n, 1, h, w)
+    err = (got - ref).abs().max().item() / 2
+    assert err <= 2e-2, f"max abs pixel error {err}"
+    assert psnr_unit(got / 2, ref / 2) >= 45.0
+    # per-layer relative error (the end-to-end bound alone is vacuous on this fixture)
+    net = m._fi_net
+    names = {"inc": "inc", "down1": "down1", "down2": "down2", "down3": "down3", "down4": "down4", "up1": "up1",
+             "up2": "up2", "up3": "up3", "up1.up": "up1.up", "up4.up": "up4.up"}
+    for ours, theirs in names.items():
+        a = net.read_activation(ours, n)
+        b = taps[theirs]
+        assert a.shape == b.shape, (ours, a.shape, b.shape)
+        rel = (a - b).norm() / (b.norm() + 1e-12)
+        assert rel < 2e-2, f"layer {ours}: relative L2 error {rel:.4f}"
+    rel_out = (got - ref).norm() / ref.norm()
+    assert rel_out < 2e-2, f"output relative L2 error {rel_out:.4f}"
+
+
+@pytest.mark.parametrize("bilinear", [False, True])
+def test_stressed_fixture(cuda_device, bilinear):
+    """Randomised BN statistics + rescaled head: output spans both clamps (SURVEY.md A.6 ii)."""
+    n, h, w = 1, 96, 128
+    f1, f2 = frames(3, n, 1, h, w), frames(4, n, 1, h, w)
+    x = torch.cat([O.preprocess_u8(f1.numpy()), O.preprocess_u8(f2.numpy())], 1)
+    sd = O.calibrate_head(O.stress_state_dict(O.init_state_dict(0, 2, 1, bilinear), seed=1), x)
+    ref = O.unet_forward(sd, x)
+    assert ref.min() < -1.2 and ref.max() > 1.2
+    m = build(sd, cuda_device, bilinear=bilinear)
+    got = m(x[:, :1].to(cuda_device), x[:, 1:].to(cuda_device)).cpu()
+    err = (got - ref).abs().max().item() / 2
+    psnr = psnr_unit(got / 2, ref / 2)
+    print(f"stressed bilinear={bilinear}: max abs {err:.4f} psnr {psnr:.1f} dB")
+    # the all-bf16 torch pipeline measures 0.025-0.038 / 39-46 dB on this fixture; we keep fp32
+    # accumulators, an fp32 stem and an fp32 head, and must meet the stated bf16 bar
+    assert err <= 2e-2, f"max abs pixel error {err}"
+    assert psnr >= 45.0, f"PSNR {psnr:.2f} dB"
+    # u8 path: same network fed raw uint8 frames, post-processing fused
+    out_u8 = m.forward_u8(f1.to(cuda_device), f2.to(cuda_device)).cpu().numpy()
+    exp_u8 = O.postprocess(ref)
+    d = np.abs(out_u8.astype(np.int32) - exp_u8.astype(np.int32))
+    assert d.max() <= 6 and (d > 1).mean() < 0.05, (d.max(), (d > 1).mean())
+
+
+def test_u8_and_f32_inputs_agree(cuda_device):
+    sd = O.init_state_dict(0, 2, 1, False)
+    m = build(sd, cuda_device)
+    f1, f2 = frames(5, 2, 1, 32, 48), frames(6, 2, 1, 32, 48)
+    a = m(O.preprocess_u8(f1.numpy()).to(cuda_device), O.preprocess_u8(f2.numpy()).to(cuda_device))
+    b = m(f1.to(cuda_device), f2.to(cuda_device))
+    assert torch.equal(a, b), "in-kernel normalisation must be bit-identical to preprocess_image's"
+
+
+def test_unet_6_in_3_out(cuda_device):
+    """UNet(6, 3): the RGB-pair variant the README describes."""
+    sd = O.init_state_dict(7, 6, 3, False, prefix="")
+    m = build(sd, cuda_device, 6, 3, False, wrapper=False)
+    x = O.preprocess_u8(frames(8, 1, 6, 40, 56).numpy())
+    ref = O.unet_forward(sd, x)
+    got = m(x.to(cuda_device)).cpu()
+    assert got.shape == (1, 3, 40, 56)
+    assert (got - ref).abs().max().item() / 2 <= 2e-2
+    assert (got - ref).norm() / ref.norm() < 2e-2
+
+
+def test_weight_update_is_picked_up(cuda_device):
+    sd = O.init_state_dict(0, 2, 1, False)
+    m = build(sd, cuda_device)
+    x1 = torch.rand(1, 1, 32, 32, device=cuda_device) * 2 - 1
+    x2 = torch.rand(1, 1, 32, 32, device=cuda_device) * 2 - 1
+    a = m(x1, x2)
+    with torch.no_grad():
+        m.unet.outc.conv.bias.add_(0.5)
+    b = m(x1, x2)
+    assert torch.allclose(b, a + 0.5, atol=1e-6)
+
+
+def test_errors_are_loud(cuda_device):
+    from model._engine import FiError
+    m = FrameInterpolationUNet().eval()
+    with pytest.raises(FiError):  # CPU tensors: no fallback
+        m(torch.zeros(1, 1, 32, 32), torch.zeros(1, 1, 32, 32))
+    m = m.to(cuda_device)
+    with pytest.raises(FiError):  # smaller than 16x16
+        m(torch.zeros(1, 1, 8, 8, device=cuda_device), torch.zeros(1, 1, 8, 8, device=cuda_device))
+    m.train()
+    with pytest.raises(FiError):
+        m(torch.zeros(1, 1, 32, 32, device=cuda_device), torch.zeros(1, 1, 32, 32, device=cuda_device))
