@@ -18,6 +18,7 @@
 #include "ptx.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace fi {
@@ -417,9 +418,20 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     ConvLaunch l;
     memset(&l, 0, sizeof l);
     const char* e;
-    if ((e = encode_nhwc(&l.map_a0, d.src0, d.N, d.H, d.W, d.c0, TILE_W, TILE_H))) return e;
+    // geometry of the CTA tile and of the TMA boxes: generic per-tap kernel, or the halo-reuse kernel
+    int tile_w = TILE_W, tile_h = TILE_H, box_w = TILE_W, box_h = TILE_H, out_w = TILE_W, out_h = 2,
+        pool_w = TILE_W / 2, pool_h = 1;
+    const char* no_halo = getenv("FI_NO_HALO");
+    l.halo = conv_halo_eligible(d) && !(no_halo && no_halo[0] == '1');
+    if (l.halo) {
+        int t;
+        conv_halo_geometry(&t, &box_w, &box_h, &out_w, &out_h, &pool_w, &pool_h);
+        tile_w = tile_h = t;
+        block_n = d.n_total;
+    }
+    if ((e = encode_nhwc(&l.map_a0, d.src0, d.N, d.H, d.W, d.c0, box_w, box_h))) return e;
     if (d.c1 > 0) {
-        if ((e = encode_nhwc(&l.map_a1, d.src1, d.N, d.h1, d.w1, d.c1, TILE_W, TILE_H))) return e;
+        if ((e = encode_nhwc(&l.map_a1, d.src1, d.N, d.h1, d.w1, d.c1, box_w, box_h))) return e;
     } else {
         l.map_a1 = l.map_a0;
     }
@@ -433,9 +445,9 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     l.map_out = l.map_a0;
     l.map_pool = l.map_a0;
     if (d.mode == EPI_STORE || d.mode == EPI_STORE_POOL) {
-        if ((e = encode_nhwc(&l.map_out, d.dst, d.N, d.H, d.W, d.n_total, TILE_W, 2))) return e;
+        if ((e = encode_nhwc(&l.map_out, d.dst, d.N, d.H, d.W, d.n_total, out_w, out_h))) return e;
         if (d.mode == EPI_STORE_POOL) {
-            if ((e = encode_nhwc(&l.map_pool, d.dst_pool, d.N, d.H / 2, d.W / 2, d.n_total, TILE_W / 2, 1))) return e;
+            if ((e = encode_nhwc(&l.map_pool, d.dst_pool, d.N, d.H / 2, d.W / 2, d.n_total, pool_w, pool_h))) return e;
         }
     } else if (d.mode == EPI_CONVT) {
         // dst [N, 2H, 2W, Cout] viewed as (b*Cout+co : 2Cout, j : W, a : 2, i : H, n : N)
@@ -450,8 +462,12 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     }
 
     ConvKernelParams& p = l.p;
-    p.tiles_x = (d.W + TILE_W - 1) / TILE_W;
-    p.tiles_y = (d.H + TILE_H - 1) / TILE_H;
+    p.tiles_x = (d.W + tile_w - 1) / tile_w;
+    p.tiles_y = (d.H + tile_h - 1) / tile_h;
+    {
+        const char* dm = getenv("FI_HALO_DESC_MODE");
+        p.desc_mode = dm ? atoi(dm) : 0;
+    }
     p.n_img = d.N;
     p.n_blocks = d.n_total / block_n;
     p.taps = d.taps;
@@ -481,6 +497,7 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
 }
 
 const char* conv_launch(const ConvLaunch& l, cudaStream_t stream) {
+    if (l.halo) return conv_halo_launch(l, stream);
     switch (l.block_n * 4 + l.mode) {
         case 64 * 4 + EPI_STORE: return launch_inst<64, EPI_STORE>(l, stream);
         case 64 * 4 + EPI_STORE_POOL: return launch_inst<64, EPI_STORE_POOL>(l, stream);

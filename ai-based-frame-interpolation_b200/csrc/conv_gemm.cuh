@@ -50,6 +50,7 @@ struct ConvKernelParams {
     int cout2;  // EPI_CONVT: 2*Cout (columns per output-row parity a)
     int H, W;
     int n_classes;
+    int desc_mode;  // halo kernel: 0 = swizzle phase from absolute smem address bits, 1 = descriptor base-offset field
     const float* bias;
     const float* head_w;
     const float* head_b;
@@ -67,6 +68,7 @@ struct ConvLaunch {
     ConvKernelParams p;
     int block_n;
     int mode;
+    int halo;  // 1: conv_halo.cu (halo-reuse kernel for Cout 64/128), 0: conv_gemm.cu
     int grid;
     double flops;  // algorithmic FLOPs of this launch (2*MACs, no padding counted)
 };
@@ -74,5 +76,10 @@ struct ConvLaunch {
 // Returns nullptr on success, else a static error string.
 const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out);
 const char* conv_launch(const ConvLaunch& l, cudaStream_t stream);
+
+// conv_halo.cu
+bool conv_halo_eligible(const ConvDesc& d);
+void conv_halo_geometry(int* tile, int* box_w, int* box_h, int* out_w, int* out_h, int* pool_w, int* pool_h);
+const char* conv_halo_launch(const ConvLaunch& l, cudaStream_t stream);
 
 }  // namespace fi

@@ -1,0 +1,393 @@
+// Halo-reuse variant of the tcgen05 implicit-GEMM conv3x3 for the high-resolution, narrow layers (Cout = 64 / 128:
+// inc.3, down1.*, up3.*, up4.* of reference model/unet.py:72-82). In conv_gemm.cu every tap re-loads its own shifted
+// 128-pixel A tile, so a narrow layer moves 9 x 16 KB of activations through L2->SMEM per 128x64 output tile and is
+// bound by that fill bandwidth (measured ~450 TFLOP/s). Here one TMA box {64ch, 24, 18, 1} (the 16x16-pixel super
+// tile plus its 1-pixel halo, row pitch padded to 24 pixels = 3 swizzle atoms) is loaded ONCE per 64-channel slab and
+// all 9 taps x 2 column halves are issued as tcgen05.mma on shifted views of it:
+//     A(tap=(dy,dx), half t)  = rows {(h+dy)*24 + (w+dx+8t)},  h in 0..15, w in 0..7   (M = 128 = 16 groups of 8 rows)
+//     -> smem descriptor start = stage + (dy*24 + dx + 8t)*128 B, stride-byte-offset = 24*128 = 3072 B.
+// The start address is no longer 1024 B aligned when dx != 0; the 128B-swizzle XOR is a function of the absolute smem
+// address bits [7,10), which is also what TMA used when it wrote the box, so the shifted view reads the right chunks
+// (validated on B200 against the oracle; p.desc_mode keeps the descriptor's base-offset alternative selectable).
+// Weights stream per (tap, slab) through their own ring. Warp roles (224 threads): 0 = A producer, 1 = TMEM owner +
+// MMA issuer, 2 = B producer, 3..6 = epilogue. TMEM: 2 accumulator sets x 2 halves x Cout columns.
+#include "conv_gemm.cuh"
+#include "ptx.cuh"
+
+#include <cstdio>
+#include <cstring>
+
+namespace fi {
+
+namespace {
+
+constexpr int HT = 16;                                 // super tile: 16 x 16 output pixels
+constexpr int HALO_W = 24, HALO_H = 18;                // TMA box (pixels): 16+2 columns padded to 24, 16+2 rows
+constexpr int HALO_BYTES = HALO_W * HALO_H * 128;      // 55296
+constexpr int HALO_THREADS = 224;
+constexpr int A_STAGES = 2;
+constexpr int B_RING_BYTES = 65536;
+constexpr int H_STAGING_PER_WARP = 2 * 4096;
+constexpr int H_POOL_PER_WARP = 2 * 1024;
+constexpr int H_BAR_BYTES = 512;
+
+__host__ __device__ constexpr int halo_b_stage_bytes(int cout) { return cout * 128; }
+__host__ __device__ constexpr int halo_b_stages(int cout) { return B_RING_BYTES / halo_b_stage_bytes(cout); }
+__host__ __device__ constexpr int halo_smem_bytes() {
+    return 1024 + A_STAGES * HALO_BYTES + B_RING_BYTES + 4 * (H_STAGING_PER_WARP + H_POOL_PER_WARP) + H_BAR_BYTES;
+}
+
+__device__ __forceinline__ uint64_t halo_desc(uint32_t smem_addr, uint32_t base_offset) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>((HALO_W * 128) >> 4) << 32;  // 3072 B between consecutive tile rows (8-row groups)
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(base_offset & 7) << 49;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+struct HTile {
+    int img, y0, x0;
+};
+__device__ __forceinline__ HTile decode_htile(int t, const ConvKernelParams& p) {
+    const int per_img = p.tiles_y * p.tiles_x;
+    HTile c;
+    c.img = t / per_img;
+    int m = t - c.img * per_img;
+    const int ty = m / p.tiles_x;
+    c.y0 = ty * HT;
+    c.x0 = (m - ty * p.tiles_x) * HT;
+    return c;
+}
+
+template <int COUT, int MODE>
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
+                 const __grid_constant__ CUtensorMap map_pool, const ConvKernelParams p) {
+    constexpr int B_STAGES = halo_b_stages(COUT);
+    constexpr int B_STAGE_BYTES = halo_b_stage_bytes(COUT);
+    constexpr int ACC_COLS = 2 * COUT;          // two column halves
+    constexpr int TMEM_COLS = 2 * ACC_COLS;     // double buffered: 256 (Cout 64) or 512 (Cout 128)
+    constexpr uint32_t IDESC = umma_idesc_bf16(128, COUT);
+    static_assert(MODE != EPI_HEAD || COUT == 64, "head epilogue consumes exactly 64 channels");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_b = smem_a + A_STAGES * HALO_BYTES;
+    const uint32_t smem_stage = smem_b + B_RING_BYTES;
+    const uint32_t smem_pool = smem_stage + 4 * H_STAGING_PER_WARP;
+    const uint32_t smem_bar = smem_pool + 4 * H_POOL_PER_WARP;
+    const uint32_t bar_afull = smem_bar;                       // A_STAGES
+    const uint32_t bar_aempty = bar_afull + 8 * A_STAGES;      // A_STAGES
+    const uint32_t bar_bfull = bar_aempty + 8 * A_STAGES;      // B_STAGES
+    const uint32_t bar_bempty = bar_bfull + 8 * B_STAGES;      // B_STAGES
+    const uint32_t bar_tfull = bar_bempty + 8 * B_STAGES;      // 2
+    const uint32_t bar_tempty = bar_tfull + 16;                // 2
+    const uint32_t tmem_slot = bar_tempty + 16;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a0);
+        tma_prefetch_desc(&map_a1);
+        tma_prefetch_desc(&map_b);
+        if (MODE != EPI_HEAD) tma_prefetch_desc(&map_out);
+        if (MODE == EPI_STORE_POOL) tma_prefetch_desc(&map_pool);
+        for (int s = 0; s < A_STAGES; ++s) {
+            mbar_init(bar_afull + 8 * s, 1);
+            mbar_init(bar_aempty + 8 * s, 1);
+        }
+        for (int s = 0; s < B_STAGES; ++s) {
+            mbar_init(bar_bfull + 8 * s, 1);
+            mbar_init(bar_bempty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int total_tiles = p.n_img * p.tiles_y * p.tiles_x;
+    const int slabs = p.slabs0 + p.slabs1;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ A producer: one halo box per (tile, slab)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const HTile tc = decode_htile(t, p);
+                for (int s = 0; s < slabs; ++s) {
+                    mbar_wait(bar_aempty + 8 * stage, phase ^ 1);
+                    const uint32_t full = bar_afull + 8 * stage;
+                    mbar_expect_tx(full, HALO_BYTES);
+                    if (s < p.slabs0) {
+                        tma_load_4d(smem_a + stage * HALO_BYTES, &map_a0, full, s * BLOCK_K, tc.x0 - 1, tc.y0 - 1,
+                                    tc.img);
+                    } else {
+                        tma_load_4d(smem_a + stage * HALO_BYTES, &map_a1, full, (s - p.slabs0) * BLOCK_K,
+                                    tc.x0 - 1 - p.off_x, tc.y0 - 1 - p.off_y, tc.img);
+                    }
+                    if (++stage == A_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ------------------------------------------------------------ B producer: one [Cout x 64] weight slab per tap
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                for (int s = 0; s < slabs; ++s) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(bar_bempty + 8 * stage, phase ^ 1);
+                        const uint32_t full = bar_bfull + 8 * stage;
+                        mbar_expect_tx(full, B_STAGE_BYTES);
+                        tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full, (tap * slabs + s) * BLOCK_K, 0);
+                        if (++stage == B_STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int a_stage = 0, b_stage = 0;
+            uint32_t a_phase = 0, b_phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                for (int s = 0; s < slabs; ++s) {
+                    mbar_wait(bar_afull + 8 * a_stage, a_phase);
+                    const uint32_t a_base = smem_a + a_stage * HALO_BYTES;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(bar_bfull + 8 * b_stage, b_phase);
+                        tc_fence_after();
+                        const int dy = tap / 3, dx = tap - 3 * dy;
+                        const uint64_t db = umma_desc_sw128(smem_b + b_stage * B_STAGE_BYTES);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const uint64_t da =
+                                halo_desc(a_base + (dy * HALO_W + dx + 8 * half) * 128, p.desc_mode ? dx : 0);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                umma_bf16_ss(d_tmem + half * COUT, da + 2 * k, db + 2 * k, IDESC, (s | tap | k) != 0);
+                            }
+                        }
+                        umma_commit(bar_bempty + 8 * b_stage);
+                        if (++b_stage == B_STAGES) {
+                            b_stage = 0;
+                            b_phase ^= 1;
+                        }
+                    }
+                    umma_commit(bar_aempty + 8 * a_stage);
+                    if (++a_stage == A_STAGES) {
+                        a_stage = 0;
+                        a_phase ^= 1;
+                    }
+                }
+                umma_commit(bar_tfull + 8 * acc);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps 3..6
+        const int q = warp & 3;  // TMEM lanes [32q, 32q+32) <-> tile rows 4q..4q+3, 8 columns of one half
+        const uint32_t my_stage = smem_stage + q * H_STAGING_PER_WARP;
+        const uint32_t my_pool = smem_pool + q * H_POOL_PER_WARP;
+        int buf = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const HTile tc = decode_htile(t, p);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS;
+#pragma unroll 1
+            for (int c = 0; c < ACC_COLS / 64; ++c) {
+                const int half = c / (COUT / 64);
+                const int n_glob = (c % (COUT / 64)) * 64;
+                const int xh = tc.x0 + 8 * half;  // first column of this half
+                const int yq = tc.y0 + 4 * q;     // first row of this warp
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32b_x32(taddr + c * 64, v0);
+                tmem_ld_32x32b_x32(taddr + c * 64 + 32, v1);
+                tmem_ld_wait();
+                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n_glob);
+                float f[64];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = __ldg(bias4 + j);
+                    f[4 * j + 0] = __uint_as_float(v0[4 * j + 0]) + b.x;
+                    f[4 * j + 1] = __uint_as_float(v0[4 * j + 1]) + b.y;
+                    f[4 * j + 2] = __uint_as_float(v0[4 * j + 2]) + b.z;
+                    f[4 * j + 3] = __uint_as_float(v0[4 * j + 3]) + b.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = __ldg(bias4 + 8 + j);
+                    f[32 + 4 * j + 0] = __uint_as_float(v1[4 * j + 0]) + b.x;
+                    f[32 + 4 * j + 1] = __uint_as_float(v1[4 * j + 1]) + b.y;
+                    f[32 + 4 * j + 2] = __uint_as_float(v1[4 * j + 2]) + b.z;
+                    f[32 + 4 * j + 3] = __uint_as_float(v1[4 * j + 3]) + b.w;
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
+                }
+
+                if constexpr (MODE == EPI_HEAD) {
+                    const int y = yq + (lane >> 3);
+                    const int x = xh + (lane & 7);
+                    const bool inside = (y < p.H) && (x < p.W);
+                    for (int k = 0; k < p.n_classes; ++k) {
+                        const float4* w4 = reinterpret_cast<const float4*>(p.head_w + k * 64);
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float4 w = __ldg(w4 + j);
+                            a0 = fmaf(f[4 * j + 0], w.x, a0);
+                            a1 = fmaf(f[4 * j + 1], w.y, a1);
+                            a2 = fmaf(f[4 * j + 2], w.z, a2);
+                            a3 = fmaf(f[4 * j + 3], w.w, a3);
+                        }
+                        const float yv = (a0 + a1) + (a2 + a3) + __ldg(p.head_b + k);
+                        if (inside) {
+                            const size_t o = ((static_cast<size_t>(tc.img) * p.n_classes + k) * p.H + y) * p.W + x;
+                            if (p.out_f32) p.out_f32[o] = yv;
+                            if (p.out_u8) {
+                                float u = __fmul_rn(__fadd_rn(yv, 1.0f), 0.5f);
+                                u = fminf(fmaxf(u, 0.0f), 1.0f);
+                                p.out_u8[o] = static_cast<uint8_t>(__fmul_rn(u, 255.0f));
+                            }
+                        }
+                    }
+                } else {
+                    uint32_t pk[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
+                    const uint32_t sbuf = my_stage + buf * 4096;
+                    const uint32_t row = sbuf + lane * 128;  // lane = (row in 0..3) * 8 + column
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        st_shared_v4(row + ((j ^ (lane & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2],
+                                     pk[4 * j + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tma_store_4d(&map_out, sbuf, n_glob, xh, yq, tc.img);  // box {64, 8, 4, 1}
+                    if constexpr (MODE == EPI_STORE_POOL) {
+                        // pooled 2 rows x 4 columns: max over lanes {2ph*8 + 2pw, +1, +8, +9}
+                        const uint32_t pbuf = my_pool + buf * 1024;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int pp = lane >> 2;  // pooled pixel 0..7 = ph*4 + pw
+                            const int j = (lane & 3) * 2 + i;
+                            const int r0 = (pp >> 2) * 16 + (pp & 3) * 2;
+                            const int r1 = r0 + 1, r2 = r0 + 8, r3 = r0 + 9;
+                            const uint4 m0 = ld_shared_v4(sbuf + r0 * 128 + ((j ^ (r0 & 7)) << 4));
+                            const uint4 m1 = ld_shared_v4(sbuf + r1 * 128 + ((j ^ (r1 & 7)) << 4));
+                            const uint4 m2 = ld_shared_v4(sbuf + r2 * 128 + ((j ^ (r2 & 7)) << 4));
+                            const uint4 m3 = ld_shared_v4(sbuf + r3 * 128 + ((j ^ (r3 & 7)) << 4));
+                            uint4 m;
+                            m.x = bf16x2_max(bf16x2_max(m0.x, m1.x), bf16x2_max(m2.x, m3.x));
+                            m.y = bf16x2_max(bf16x2_max(m0.y, m1.y), bf16x2_max(m2.y, m3.y));
+                            m.z = bf16x2_max(bf16x2_max(m0.z, m1.z), bf16x2_max(m2.z, m3.z));
+                            m.w = bf16x2_max(bf16x2_max(m0.w, m1.w), bf16x2_max(m2.w, m3.w));
+                            st_shared_v4(pbuf + pp * 128 + ((j ^ (pp & 7)) << 4), m.x, m.y, m.z, m.w);
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_4d(&map_pool, pbuf, n_glob, xh >> 1, yq >> 1, tc.img);  // box {64, 4, 2, 1}
+                        }
+                    }
+                    if (lane == 0) tma_store_commit();
+                    buf ^= 1;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+        if (MODE != EPI_HEAD && lane == 0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int COUT, int MODE>
+const char* launch_halo_inst(const ConvLaunch& l, cudaStream_t stream) {
+    auto kfn = conv_halo_kernel<COUT, MODE>;
+    static bool configured = false;
+    constexpr int smem = halo_smem_bytes();
+    if (!configured) {
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
+        configured = true;
+    }
+    kfn<<<l.grid, HALO_THREADS, smem, stream>>>(l.map_a0, l.map_a1, l.map_b, l.map_out, l.map_pool, l.p);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace
+
+bool conv_halo_eligible(const ConvDesc& d) {
+    if (d.taps != 9) return false;
+    if (d.n_total != 64 && d.n_total != 128) return false;
+    if (d.mode == EPI_HEAD) return d.n_total == 64;
+    return d.mode == EPI_STORE || d.mode == EPI_STORE_POOL;
+}
+
+void conv_halo_geometry(int* tile, int* box_w, int* box_h, int* out_w, int* out_h, int* pool_w, int* pool_h) {
+    *tile = HT;
+    *box_w = HALO_W;
+    *box_h = HALO_H;
+    *out_w = 8;
+    *out_h = 4;
+    *pool_w = 4;
+    *pool_h = 2;
+}
+
+const char* conv_halo_launch(const ConvLaunch& l, cudaStream_t stream) {
+    switch (l.block_n * 4 + l.mode) {
+        case 64 * 4 + EPI_STORE: return launch_halo_inst<64, EPI_STORE>(l, stream);
+        case 64 * 4 + EPI_STORE_POOL: return launch_halo_inst<64, EPI_STORE_POOL>(l, stream);
+        case 64 * 4 + EPI_HEAD: return launch_halo_inst<64, EPI_HEAD>(l, stream);
+        case 128 * 4 + EPI_STORE: return launch_halo_inst<128, EPI_STORE>(l, stream);
+        case 128 * 4 + EPI_STORE_POOL: return launch_halo_inst<128, EPI_STORE_POOL>(l, stream);
+        default: return "conv(halo): no kernel instantiation for this (cout, mode)";
+    }
+}
+
+}  // namespace fi

@@ -83,6 +83,9 @@ struct Step {
     const void* src = nullptr;  // STEP_UPSAMPLE
     void* dst = nullptr;        // STEP_STEM / STEP_UPSAMPLE
     int h = 0, w = 0, C = 0;
+    char name[48] = "";
+    double flops = 0;  // algorithmic FLOPs of the launch
+    double bytes = 0;  // algorithmic HBM bytes of the launch (inputs + weights + outputs, each touched once)
 };
 
 struct Plan {
@@ -114,6 +117,9 @@ struct fiNet {
     ConvW upT[4];           // ConvTranspose2d of up1..up4 (bilinear=False)
     DevBuf head_w, head_b;  // fp32 [n_classes][64], [n_classes]
     Plan plan;
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;  // [call][step][2], resolved by fiNetGetProfile
+    int prof_calls = 0;
     // pinned staging for the host-buffer convenience call
     void* pin_in = nullptr;
     void* pin_out = nullptr;
@@ -311,13 +317,20 @@ int build_plan(fiNet* net, int N, int H, int W) {
     };
 
     pl.flops = 2.0 * N * H * W * 64.0 * 9 * stem.cin;
-    auto push_conv = [&](fi::ConvDesc d) -> int {
+    auto push_conv = [&](fi::ConvDesc d, const std::string& name) -> int {
         Step s;
         s.kind = STEP_CONV;
         d.N = N;
         const char* e = fi::conv_prepare(d, net->num_sms, &s.conv);
         if (e) return fail(FI_ERR_INVALID, "%s", e);
         pl.flops += s.conv.flops;
+        snprintf(s.name, sizeof s.name, "%s", name.c_str());
+        s.flops = s.conv.flops;
+        const double px = static_cast<double>(N) * d.H * d.W;
+        s.bytes = px * d.c0 * 2 + static_cast<double>(N) * d.h1 * d.w1 * d.c1 * 2 +
+                  static_cast<double>(d.n_total) * d.taps * (d.c0 + d.c1) * 2;
+        if (d.mode == fi::EPI_HEAD) s.bytes += px * d.n_classes * 4;
+        else s.bytes += px * d.n_total * 2 * (d.mode == fi::EPI_STORE_POOL ? 1.25 : 1.0);
         pl.steps.push_back(s);
         return FI_OK;
     };
@@ -356,7 +369,7 @@ int build_plan(fiNet* net, int N, int H, int W) {
             d.dst = ptr(dst);
             if (mode == fi::EPI_STORE_POOL) d.dst_pool = ptr(pool);
         }
-        return push_conv(d);
+        return push_conv(d, conv_prefix(idx));
     };
 
     int rc;
@@ -364,6 +377,9 @@ int build_plan(fiNet* net, int N, int H, int W) {
         Step s;
         s.kind = STEP_STEM;
         s.dst = ptr("inc.mid");
+        snprintf(s.name, sizeof s.name, "inc.double_conv.0");
+        s.flops = 2.0 * N * H * W * 64.0 * 9 * stem.cin;
+        s.bytes = static_cast<double>(N) * H * W * (stem.cin * 4.0 + 128.0);
         pl.steps.push_back(s);
     }
     if ((rc = conv3(0, "inc.mid", "", "inc", "pool1", fi::EPI_STORE_POOL))) return rc;
@@ -392,6 +408,8 @@ int build_plan(fiNet* net, int N, int H, int W) {
             s.h = lo.H;
             s.w = lo.W;
             s.C = lo.C;
+            snprintf(s.name, sizeof s.name, "up%d.up", i + 1);
+            s.bytes = static_cast<double>(N) * lo.H * lo.W * lo.C * 2 * 5.0;
             pl.steps.push_back(s);
         } else {
             fi::ConvDesc d;
@@ -408,7 +426,7 @@ int build_plan(fiNet* net, int N, int H, int W) {
             d.mode = fi::EPI_CONVT;
             d.relu = 0;
             d.dst = ptr(up);
-            if ((rc = push_conv(d))) return rc;
+            if ((rc = push_conv(d, up))) return rc;
         }
         if ((rc = conv3(9 + 2 * i, skips[i], up, mid, "", fi::EPI_STORE))) return rc;
         if (i < 3) {
@@ -493,6 +511,7 @@ int fiNetDestroy(fiNet* net) {
     cudaSetDevice(net->device);
     if (net->pin_in) cudaFreeHost(net->pin_in);
     if (net->pin_out) cudaFreeHost(net->pin_out);
+    for (cudaEvent_t e : net->prof_events) cudaEventDestroy(e);
     delete net;
     return FI_OK;
 }
@@ -559,8 +578,17 @@ int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dt
     if ((rc = build_plan(net, N, H, W))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Plan& pl = net->plan;
+    cudaEvent_t* evs = nullptr;
+    if (net->profiling) {
+        const size_t base = net->prof_events.size();
+        net->prof_events.resize(base + 2 * pl.steps.size());
+        for (size_t i = base; i < net->prof_events.size(); ++i) CUDA_TRY(cudaEventCreate(&net->prof_events[i]));
+        evs = net->prof_events.data() + base;
+        ++net->prof_calls;
+    }
     for (size_t i = 0; i < pl.steps.size(); ++i) {
         Step& s = pl.steps[i];
+        if (evs) CUDA_TRY(cudaEventRecord(evs[2 * i], st));
         if (s.kind == STEP_STEM) {
             fi::StemDesc d;
             memset(&d, 0, sizeof d);
@@ -584,6 +612,48 @@ int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dt
             }
             KERNEL_TRY(fi::conv_launch(s.conv, st));
         }
+        if (evs) CUDA_TRY(cudaEventRecord(evs[2 * i + 1], st));
+    }
+    return FI_OK;
+}
+
+int fiNetSetProfiling(fiNet* net, int enable) {
+    if (!net) return fail(FI_ERR_INVALID, "net is null");
+    for (cudaEvent_t e : net->prof_events) cudaEventDestroy(e);
+    net->prof_events.clear();
+    net->prof_calls = 0;
+    net->profiling = enable != 0;
+    return FI_OK;
+}
+
+int fiNetGetProfile(fiNet* net, fiLaunchProfile* out, int capacity, int* count) {
+    if (!net || !count) return fail(FI_ERR_INVALID, "null argument");
+    const Plan& pl = net->plan;
+    const int n = static_cast<int>(pl.steps.size());
+    *count = n;
+    if (!out) return FI_OK;
+    if (capacity < n) return fail(FI_ERR_INVALID, "profile buffer too small: need %d entries", n);
+    if (net->prof_calls == 0 || net->prof_events.size() != static_cast<size_t>(2) * n * net->prof_calls)
+        return fail(FI_ERR_STATE, "no profiled forward of the current shape has run");
+    int rc = set_device(net->device);
+    if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < n; ++i) {
+        const Step& s = pl.steps[i];
+        memset(&out[i], 0, sizeof out[i]);
+        snprintf(out[i].name, sizeof out[i].name, "%s", s.name);
+        out[i].kind = s.kind == STEP_CONV ? 1 : (s.kind == STEP_STEM ? 0 : 2);
+        out[i].flops = s.flops;
+        out[i].bytes = s.bytes;
+        out[i].calls = net->prof_calls;
+        double ms = 0;
+        for (int c = 0; c < net->prof_calls; ++c) {
+            float t = 0;
+            CUDA_TRY(cudaEventElapsedTime(&t, net->prof_events[(static_cast<size_t>(c) * n + i) * 2],
+                                          net->prof_events[(static_cast<size_t>(c) * n + i) * 2 + 1]));
+            ms += t;
+        }
+        out[i].ms_total = ms;
     }
     return FI_OK;
 }

@@ -35,7 +35,14 @@ class ConvDesc(C.Structure):
                 ("out_f32", C.c_void_p), ("out_u8", C.c_void_p), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int)]
 
 
+class LaunchProfile(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("kind", C.c_int), ("calls", C.c_int), ("flops", C.c_double),
+                ("bytes", C.c_double), ("ms_total", C.c_double)]
+
+
 _SIGNATURES = {
+    "fiNetSetProfiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "fiNetGetProfile": (C.c_int, [C.c_void_p, C.POINTER(LaunchProfile), C.c_int, C.POINTER(C.c_int)]),
     "fiVersion": (C.c_int, []),
     "fiLastError": (C.c_char_p, []),
     "fiNetCreate": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -174,6 +181,19 @@ class Net:
             check(lib().fiNetInterpolateHostU8(self._h, f1.ctypes.data, f2.ctypes.data, c, out.ctypes.data, n, h, w,
                                                current_stream()))
         return out
+
+    def set_profiling(self, on):
+        check(lib().fiNetSetProfiling(self._h, int(bool(on))))
+
+    def profile(self):
+        """Per-launch device times of the profiled forwards: list of dicts (name, kind, calls, flops, bytes, ms_total)."""
+        cnt = C.c_int()
+        check(lib().fiNetGetProfile(self._h, None, 0, C.byref(cnt)))
+        arr = (LaunchProfile * cnt.value)()
+        with torch.cuda.device(self.device):
+            check(lib().fiNetGetProfile(self._h, arr, cnt.value, C.byref(cnt)))
+        return [dict(name=a.name.decode(), kind=a.kind, calls=a.calls, flops=a.flops, bytes=a.bytes,
+                     ms_total=a.ms_total) for a in arr]
 
     def cost(self, n, h, w):
         fl, ln = C.c_double(), C.c_int()

@@ -78,6 +78,20 @@ int fiNetInterpolateHostU8(fiNet* net, const uint8_t* frame1_host, const uint8_t
 
 /* Algorithmic FLOPs (2*MACs, no padding) of one forward at this shape, and the number of kernel launches it makes. */
 int fiNetForwardCost(fiNet* net, int N, int H, int W, double* flops, int* launches);
+/* Measurement hook for bench.py: when enabled, every launch of the following forwards is bracketed by a CUDA event
+ * pair on the caller's stream; fiNetGetProfile synchronises the device and returns, per launch of the schedule, the
+ * accumulated device time, its algorithmic FLOPs and bytes. kind: 0 = stem conv (CUDA cores), 1 = tcgen05 conv GEMM,
+ * 2 = bilinear upsample. Call with out == NULL to query the launch count. */
+typedef struct fiLaunchProfile {
+    char name[48];
+    int kind;
+    int calls;
+    double flops;
+    double bytes;
+    double ms_total;
+} fiLaunchProfile;
+int fiNetSetProfiling(fiNet* net, int enable);
+int fiNetGetProfile(fiNet* net, fiLaunchProfile* out, int capacity, int* count);
 /* Debug tap: copy an intermediate activation (bf16 NHWC) of the last forward to the host as fp32 NCHW.
  * name in {inc, down1..down4, up1..up4 (block outputs), up1.up..up4.up (upsampled tensors)}. */
 int fiNetReadActivation(fiNet* net, const char* name, float* out_host, int64_t capacity, int* C, int* H, int* W);

@@ -11,6 +11,13 @@ from layer_utils import bf16_round, ref_conv3x3, run_conv
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["halo", "per-tap"], autouse=True)
+def kernel_variant(request, monkeypatch):
+    """Cout 64/128 layers have two kernels (conv_halo.cu / conv_gemm.cu); run every case through both."""
+    monkeypatch.setenv("FI_NO_HALO", "0" if request.param == "halo" else "1")
+    return request.param
+
+
 def close(a, b, what):
     assert a.shape == b.shape, (what, a.shape, b.shape)
     assert not torch.isnan(a).any(), f"{what}: NaN in output (unwritten elements?)"
