@@ -1,0 +1,83 @@
+"""HTTP surface of the reference's api/app.py (routes, multipart fields, validation ranges, status codes:
+reference api/app.py:121-223), served by a resident FrameInterpolator instead of one subprocess + checkpoint load per
+request (reference api/app.py:82-101)."""
+import os
+import shutil
+import tempfile
+import threading
+import uuid
+
+import cv2
+import numpy as np
+from fastapi import FastAPI, File, Form, HTTPException, UploadFile
+from fastapi.middleware.cors import CORSMiddleware
+from fastapi.responses import FileResponse
+
+MODEL_PATH = os.environ.get("FI_MODEL_PATH", "best_model.pth")
+OUTPUT_DIR = os.environ.get("FI_OUTPUT_DIR", "temp_outputs")
+TARGET_SIZE = (256, 256)  # reference preprocess_image default (model/inference.py:11)
+
+app = FastAPI(title="Frame Interpolation API", description="B200-native UNet frame interpolation", version="1.0.0")
+app.add_middleware(CORSMiddleware, allow_origins=["*"], allow_credentials=True, allow_methods=["*"],
+                   allow_headers=["*"])
+
+_worker, _worker_lock = None, threading.Lock()
+
+
+def get_worker():
+    """One FrameInterpolator (weights + activation arena on the GPU) for the whole process; the handle is not
+    re-entrant, so requests are serialised on it."""
+    global _worker
+    if _worker is None:
+        from model.inference import FrameInterpolator
+        _worker = FrameInterpolator(MODEL_PATH, os.environ.get("FI_DEVICE", "cuda"))
+    return _worker
+
+
+def _decode(upload: UploadFile, data: bytes):
+    if not upload.content_type or not upload.content_type.startswith("image/"):
+        raise HTTPException(status_code=400, detail=f"{upload.filename} must be an image file")
+    img = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE)
+    if img is None:
+        raise HTTPException(status_code=400, detail=f"could not decode {upload.filename}")
+    return cv2.resize(img, TARGET_SIZE)
+
+
+@app.post("/interpolate")
+async def interpolate(frame1: UploadFile = File(...), frame2: UploadFile = File(...),
+                      num_intermediate: int = Form(3), fps: int = Form(30)):
+    if not 1 <= num_intermediate <= 10:
+        raise HTTPException(status_code=400, detail="num_intermediate must be between 1 and 10")
+    if not 10 <= fps <= 60:
+        raise HTTPException(status_code=400, detail="fps must be between 10 and 60")
+    a = _decode(frame1, await frame1.read())
+    b = _decode(frame2, await frame2.read())
+    try:
+        from model.inference import save_frames_as_video
+        with _worker_lock:
+            mid = get_worker().interpolate_frames(a, b)
+        os.makedirs(OUTPUT_DIR, exist_ok=True)
+        path = os.path.join(OUTPUT_DIR, f"{uuid.uuid4().hex}.mp4")
+        save_frames_as_video([a] + [mid] * num_intermediate + [b], path, fps)  # same frame list as inference.py:262-283
+        return FileResponse(path, media_type="video/mp4", filename="interpolated_video.mp4")
+    except HTTPException:
+        raise
+    except Exception as e:
+        raise HTTPException(status_code=500, detail=f"Inference failed: {e}")
+
+
+@app.get("/")
+async def root():
+    return {"message": "Frame Interpolation API", "version": "1.0.0",
+            "endpoints": {"POST /interpolate": "Upload two frames and get an interpolated video",
+                          "GET /health": "Health check"}}
+
+
+@app.get("/health")
+async def health():
+    return {"status": "healthy", "model_exists": os.path.exists(MODEL_PATH), "model_path": MODEL_PATH}
+
+
+@app.on_event("shutdown")
+async def _cleanup():
+    shutil.rmtree(OUTPUT_DIR, ignore_errors=True)

@@ -1,0 +1,97 @@
+"""CPU tier: the drop-in keeps the reference's Python surface (names, signatures, CLI flags, HTTP routes and their
+validation) — SURVEY.md §8b. Nothing here computes on a GPU."""
+import inspect
+
+import pytest
+
+
+def test_unet_module_surface_and_state_dict_schema():
+    from model import unet
+    for name in ("DoubleConv", "Down", "Up", "OutConv", "UNet", "FrameInterpolationUNet", "count_parameters"):
+        assert hasattr(unet, name)
+    assert str(inspect.signature(unet.UNet.__init__)) == "(self, n_channels=2, n_classes=1, bilinear=False)"
+    assert str(inspect.signature(unet.FrameInterpolationUNet.__init__)) == "(self, bilinear=False)"
+    assert list(inspect.signature(unet.FrameInterpolationUNet.forward).parameters) == ["self", "frame1", "frame2"]
+    assert str(inspect.signature(unet.DoubleConv.__init__)) == "(self, in_channels, out_channels, mid_channels=None)"
+    assert str(inspect.signature(unet.Up.__init__)) == "(self, in_channels, out_channels, bilinear=True)"
+    from oracle import unet_oracle as O
+    for bilinear, n_params, n_tensors in ((False, 31037057, 118), (True, 17262401, 110)):
+        m = unet.FrameInterpolationUNet(bilinear=bilinear)
+        assert unet.count_parameters(m) == n_params
+        sd = m.state_dict()
+        assert len(sd) == n_tensors
+        assert list(sd.keys()) == list(O.init_state_dict(0, 2, 1, bilinear).keys())
+        m.load_state_dict(O.init_state_dict(0, 2, 1, bilinear))  # strict
+    assert unet.count_parameters(unet.UNet(6, 3)) == 31039491
+
+
+def test_inference_module_surface():
+    from model import inference as inf
+    sigs = {
+        "preprocess_image": ["image_path", "target_size"],
+        "postprocess_image": ["tensor"],
+        "load_model": ["model_path", "device"],
+        "interpolate_frames": ["model", "frame1", "frame2", "device"],
+        "generate_multiple_intermediate_frames": ["model", "frame1", "frame2", "num_intermediate", "device"],
+        "create_smooth_transition_frames": ["frame1", "frame2", "num_intermediate"],
+        "save_frames_as_video": ["frames", "output_path", "fps"],
+    }
+    for fn, params in sigs.items():
+        assert list(inspect.signature(getattr(inf, fn)).parameters) == params, fn
+    assert inspect.signature(inf.preprocess_image).parameters["target_size"].default == (256, 256)
+    assert inspect.signature(inf.save_frames_as_video).parameters["fps"].default == 30
+    fi = inf.FrameInterpolator
+    assert list(inspect.signature(fi.interpolate_frames).parameters) == ["self", "frame1", "frame2"]
+    assert list(inspect.signature(fi.interpolate_video).parameters)[:4] == ["self", "input_path", "output_path", "factor"]
+
+
+def test_inference_cli_flags_and_error_exit_code(tmp_path, capsys):
+    from model import inference as inf
+    with pytest.raises(SystemExit):
+        inf.main([])  # --frame1/--frame2 are required, like the reference
+    rc = inf.main(["--frame1", str(tmp_path / "a.png"), "--frame2", str(tmp_path / "b.png"), "--model",
+                   str(tmp_path / "none.pth"), "--num-intermediate", "3", "--fps", "24", "--save-comparison",
+                   "--device", "auto", "--output", str(tmp_path / "o.png")])
+    assert rc == 1 and "Error during inference" in capsys.readouterr().out
+
+
+def test_linear_baseline_matches_reference_formula():
+    import torch
+    from model.inference import create_smooth_transition_frames
+    a, b = torch.zeros(1, 1, 2, 2), torch.ones(1, 1, 2, 2)
+    fr = create_smooth_transition_frames(a, b, 3)
+    assert [float(f.mean()) for f in fr] == [0.25, 0.5, 0.75]
+
+
+def test_main_cli_surface(capsys):
+    import main as cli
+    p = cli.build_parser()
+    a = p.parse_args(["video", "--model", "m.pth", "--input", "i.mp4", "--output", "o.mp4", "--factor", "4"])
+    assert (a.command, a.factor, a.device) == ("video", 4, "auto")
+    a = p.parse_args(["infer", "--model", "m.pth", "--frame1", "a", "--frame2", "b"])
+    assert a.output == "interpolated.png"
+    assert p.parse_args(["serve"]).port == 8000
+    assert cli.main(["info"]) == 0  # the reference raises AttributeError here (no --device on `info`)
+    assert "31,037,057" in capsys.readouterr().out
+
+
+def test_http_routes_and_validation():
+    from fastapi.testclient import TestClient
+    from api.app import app
+    c = TestClient(app)
+    assert c.get("/health").json()["status"] == "healthy"
+    assert "POST /interpolate" in c.get("/").json()["endpoints"]
+    png = b"\x89PNG\r\n\x1a\n" + b"0" * 16
+    files = {"frame1": ("a.png", png, "image/png"), "frame2": ("b.png", png, "image/png")}
+    assert c.post("/interpolate", files=files, data={"num_intermediate": "11", "fps": "30"}).status_code == 400
+    assert c.post("/interpolate", files=files, data={"num_intermediate": "3", "fps": "5"}).status_code == 400
+    bad = {"frame1": ("a.txt", b"x", "text/plain"), "frame2": ("b.png", png, "image/png")}
+    assert c.post("/interpolate", files=bad, data={"num_intermediate": "3", "fps": "30"}).status_code == 400
+    assert c.post("/interpolate", data={"num_intermediate": "3"}).status_code == 422  # missing files
+
+
+def test_metric_functions_exist_with_reference_argument_order():
+    from model import evaluation, evaluation_simple
+    for mod in (evaluation, evaluation_simple):
+        assert list(inspect.signature(mod.compute_psnr).parameters) == ["pred", "target"]
+        assert list(inspect.signature(mod.compute_ssim).parameters) == ["pred", "target"]

@@ -1,0 +1,141 @@
+"""GPU tier: the reference-facing Python API end to end (files in, files out) against the oracle."""
+import numpy as np
+import pytest
+import torch
+import cv2
+
+from oracle import metrics_oracle as M
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def moving_disc(i, h=96, w=128, color=False):
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = (40 + 60 * (xx / w)).astype(np.float32)
+    img += 150 * (((xx - (30 + 6 * i)) ** 2 + (yy - h // 2) ** 2) < 18 ** 2)
+    img = np.clip(img, 0, 255).astype(np.uint8)
+    return np.stack([img, np.roll(img, 3, 0), np.roll(img, 5, 1)], -1) if color else img
+
+
+@pytest.fixture(scope="module")
+def checkpoints(tmp_path_factory):
+    d = tmp_path_factory.mktemp("ckpt")
+    paths = {}
+    for bilinear in (True, False):
+        x = torch.cat([O.preprocess_u8(moving_disc(0)[None, None]), O.preprocess_u8(moving_disc(2)[None, None])], 1)
+        sd = O.calibrate_head(O.stress_state_dict(O.init_state_dict(0, 2, 1, bilinear), seed=1), x, out_std=0.4)
+        p = d / f"model_bilinear{int(bilinear)}.pth"
+        if bilinear:  # the dict form train.py writes (reference model/train.py:234-242)
+            torch.save({"epoch": 3, "model_state_dict": sd, "val_loss": 0.125}, p)
+        else:         # bare state dict
+            torch.save(sd, p)
+        paths[bilinear] = (str(p), sd)
+    return paths
+
+
+def test_inference_cli_single_frame(cuda_device, checkpoints, tmp_path, monkeypatch):
+    from model import inference as inf
+    path, sd = checkpoints[True]  # load_model builds bilinear=True, like the reference
+    cv2.imwrite(str(tmp_path / "a.png"), moving_disc(0, 300, 280))
+    cv2.imwrite(str(tmp_path / "b.png"), moving_disc(2, 300, 280))
+    out = tmp_path / "out.png"
+    rc = inf.main(["--frame1", str(tmp_path / "a.png"), "--frame2", str(tmp_path / "b.png"), "--model", path,
+                   "--output", str(out), "--device", "cuda"])
+    assert rc == 0 and out.exists()
+    got = cv2.imread(str(out), cv2.IMREAD_GRAYSCALE)
+    assert got.shape == (256, 256)
+    # oracle: the reference's own pipeline (resize 256x256, normalise, forward, postprocess)
+    a = cv2.resize(cv2.imread(str(tmp_path / "a.png"), cv2.IMREAD_GRAYSCALE), (256, 256))
+    b = cv2.resize(cv2.imread(str(tmp_path / "b.png"), cv2.IMREAD_GRAYSCALE), (256, 256))
+    ref = O.postprocess(O.frame_interp_forward(sd, O.preprocess_u8(a[None, None]), O.preprocess_u8(b[None, None])))[0, 0]
+    assert np.abs(got.astype(int) - ref.astype(int)).max() <= 6
+
+
+def test_inference_cli_multi_frame_outputs(cuda_device, checkpoints, tmp_path, monkeypatch):
+    from model import inference as inf
+    path, _ = checkpoints[True]
+    cv2.imwrite(str(tmp_path / "a.png"), moving_disc(0))
+    cv2.imwrite(str(tmp_path / "b.png"), moving_disc(2))
+    monkeypatch.chdir(tmp_path)  # api/app.py relies on these file names in the cwd (reference api/app.py:82-114)
+    rc = inf.main(["--frame1", "a.png", "--frame2", "b.png", "--model", path, "--num-intermediate", "3", "--fps", "24",
+                   "--save-comparison", "--device", "cuda"])
+    assert rc == 0
+    for name in ("intermediate_01.png", "intermediate_03.png", "linear_intermediate_02.png", "output.mp4",
+                 "output_comparison.mp4"):
+        assert (tmp_path / name).exists(), name
+    cap = cv2.VideoCapture(str(tmp_path / "output.mp4"))
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 5
+
+
+def test_frame_interpolator_bgr_and_grey(cuda_device, checkpoints):
+    from model.inference import FrameInterpolator
+    for bilinear in (False, True):
+        path, sd = checkpoints[bilinear]
+        fi = FrameInterpolator(path, "cuda")
+        a, b = moving_disc(0, 72, 88, color=True), moving_disc(2, 72, 88, color=True)
+        out = fi.interpolate_frames(a, b)
+        assert out.shape == a.shape and out.dtype == np.uint8
+        for ch in range(3):  # grey model applied per colour channel
+            ref = O.postprocess(O.frame_interp_forward(sd, O.preprocess_u8(a[None, None, :, :, ch]),
+                                                       O.preprocess_u8(b[None, None, :, :, ch])))[0, 0]
+            assert np.abs(out[..., ch].astype(int) - ref.astype(int)).max() <= 6
+        g = fi.interpolate_frames(a[..., 0], b[..., 0])
+        assert g.shape == a.shape[:2] and np.array_equal(g, out[..., 0])
+
+
+def test_interpolate_sequence_and_video(cuda_device, checkpoints, tmp_path):
+    from model.inference import FrameInterpolator
+    path, _ = checkpoints[False]
+    fi = FrameInterpolator(path, "cuda", pairs_per_batch=3)
+    frames = [moving_disc(i, 64, 80) for i in range(6)]
+    seq2 = fi.interpolate_sequence(frames, 2)
+    assert len(seq2) == 11 and all(np.array_equal(seq2[2 * i], frames[i]) for i in range(6))
+    assert np.array_equal(seq2[1], fi.interpolate_frames(frames[0], frames[1]))  # batching does not change results
+    seq4 = fi.interpolate_sequence(frames, 4)
+    assert len(seq4) == 21 and np.array_equal(seq4[2], seq2[1])
+    assert len(fi.interpolate_sequence(frames, 3)) == 16
+    src = tmp_path / "in.mp4"
+    wr = cv2.VideoWriter(str(src), cv2.VideoWriter_fourcc(*"mp4v"), 10.0, (80, 64), True)
+    for f in frames:
+        wr.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+    wr.release()
+    n = fi.interpolate_video(str(src), str(tmp_path / "out.mp4"), 2, chunk=4)
+    assert n == 11
+    cap = cv2.VideoCapture(str(tmp_path / "out.mp4"))
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 11 and abs(cap.get(cv2.CAP_PROP_FPS) - 20.0) < 0.5
+
+
+def test_compute_psnr_ssim_drop_in(cuda_device):
+    from model.evaluation import compute_psnr, compute_ssim, evaluate_triplets
+    a, b = moving_disc(0, 256, 256), moving_disc(1, 256, 256)
+    assert abs(compute_psnr(a, b) - M.psnr_u8(a, b)) <= 1e-4
+    assert abs(compute_ssim(a, b) - M.ssim_u8(a, b)) <= 1e-4
+    assert compute_psnr(a, a) == float("inf") and abs(compute_ssim(a, a) - 1.0) < 1e-6
+
+
+def test_evaluate_triplets_schema(cuda_device, checkpoints):
+    from model.evaluation import evaluate_triplets
+    from model.inference import FrameInterpolator
+    fi = FrameInterpolator(checkpoints[False][0], "cuda")
+    trip = [(moving_disc(i), moving_disc(i + 1), moving_disc(i + 2)) for i in range(5)]
+    res = evaluate_triplets(fi, trip, batch=2)
+    assert res["num_triplets"] == 5 and set(res["methods"]) == {"unet", "linear"}
+    lin = res["methods"]["linear"]
+    exp = [M.psnr_u8(((t[0].astype(np.float32) + t[2]) / 2).astype(np.uint8), t[1]) for t in trip]
+    assert np.allclose(lin["psnr_values"], exp, atol=1e-4) and len(lin["ssim_values"]) == 5
+
+
+def test_http_interpolate_end_to_end(cuda_device, checkpoints, tmp_path, monkeypatch):
+    import api.app as appmod
+    from fastapi.testclient import TestClient
+    monkeypatch.setattr(appmod, "MODEL_PATH", checkpoints[True][0])
+    monkeypatch.setattr(appmod, "OUTPUT_DIR", str(tmp_path / "out"))
+    monkeypatch.setattr(appmod, "_worker", None)
+    ok, pa = cv2.imencode(".png", moving_disc(0))
+    ok, pb = cv2.imencode(".png", moving_disc(2))
+    c = TestClient(appmod.app)
+    r = c.post("/interpolate", files={"frame1": ("a.png", pa.tobytes(), "image/png"),
+                                      "frame2": ("b.png", pb.tobytes(), "image/png")},
+               data={"num_intermediate": "2", "fps": "12"})
+    assert r.status_code == 200 and r.headers["content-type"] == "video/mp4" and len(r.content) > 1000
