@@ -117,8 +117,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     const int k_iters = p.taps * slabs;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer (one lane)
-        if (lane == 0) {
+        // ------------------------------------------------------------ TMA producer (warp converged, one lane issues)
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -129,16 +129,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     for (int s = 0; s < slabs; ++s) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t full = bar_full + 8 * stage;
-                        mbar_expect_tx(full, STAGE_TX);
-                        if (s < p.slabs0) {
-                            tma_load_4d(smem_a + stage * A_STAGE_BYTES, &map_a0, full, s * BLOCK_K, tc.x0 + dx,
-                                        tc.y0 + dy, tc.img);
-                        } else {
-                            tma_load_4d(smem_a + stage * A_STAGE_BYTES, &map_a1, full, (s - p.slabs0) * BLOCK_K,
-                                        tc.x0 + dx - p.off_x, tc.y0 + dy - p.off_y, tc.img);
+                        if (elect_one()) {
+                            mbar_expect_tx(full, STAGE_TX);
+                            if (s < p.slabs0) {
+                                tma_load_4d(smem_a + stage * A_STAGE_BYTES, &map_a0, full, s * BLOCK_K, tc.x0 + dx,
+                                            tc.y0 + dy, tc.img);
+                            } else {
+                                tma_load_4d(smem_a + stage * A_STAGE_BYTES, &map_a1, full, (s - p.slabs0) * BLOCK_K,
+                                            tc.x0 + dx - p.off_x, tc.y0 + dy - p.off_y, tc.img);
+                            }
+                            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full, (tap * slabs + s) * BLOCK_K,
+                                        tc.nb * BLOCK_N);
                         }
-                        tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full, (tap * slabs + s) * BLOCK_K,
-                                    tc.nb * BLOCK_N);
+                        __syncwarp();
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -148,8 +151,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (one lane)
-        if (lane == 0) {
+        // ------------------------------------------------------------ MMA issuer (warp converged, one lane issues)
+        {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -164,18 +167,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     tc_fence_after();
                     const uint64_t da = umma_desc_sw128(smem_a + stage * A_STAGE_BYTES);
                     const uint64_t db = umma_desc_sw128(smem_b + stage * B_STAGE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k) {
-                        // +32 bytes along K inside the 128B swizzle row = +2 in the (addr >> 4) field
-                        umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
+                        for (int k = 0; k < BLOCK_K / 16; ++k) {
+                            // +32 bytes along K inside the 128B swizzle row = +2 in the (addr >> 4) field
+                            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
+                        }
+                        umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs retire
+                        if (kb == k_iters - 1) umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
                     }
-                    umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs retire
+                    __syncwarp();
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
             }
         }
     } else {
@@ -255,7 +261,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
                     // The staging buffer used two chunks ago must have been read by its TMA store.
-                    if (lane == 0) tma_store_wait_read<1>();
+                    if (elect_one()) tma_store_wait_read<1>();
                     __syncwarp();
                     const uint32_t sbuf = my_stage + buf * 4096;
                     const uint32_t row = sbuf + lane * 128;
@@ -266,7 +272,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         if constexpr (MODE == EPI_CONVT) {
                             const int a = n_glob / p.cout2;
                             tma_store_5d(&map_out, sbuf, n_glob - a * p.cout2, tc.x0, a, tc.y0 + 2 * q, tc.img);
@@ -295,20 +301,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
+                        if (elect_one()) {
                             tma_store_4d(&map_pool, pbuf, n_glob, tc.x0 >> 1, (tc.y0 >> 1) + q, tc.img);
                         }
                     }
-                    if (lane == 0) tma_store_commit();
+                    if (elect_one()) tma_store_commit();
                     buf ^= 1;
                 }
             }
             // All TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back to the MMA warp.
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            if (elect_one()) mbar_arrive(bar_tempty + 8 * acc);
         }
-        if (MODE != EPI_HEAD && lane == 0) tma_store_wait_all();
+        __syncwarp();
+        if (MODE != EPI_HEAD && elect_one()) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -467,6 +474,8 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     {
         const char* dm = getenv("FI_HALO_DESC_MODE");
         p.desc_mode = dm ? atoi(dm) : 0;
+        const char* pf = getenv("FI_HALO_PREFETCH");
+        p.prefetch_dist = pf ? atoi(pf) : 2;
     }
     p.n_img = d.N;
     p.n_blocks = d.n_total / block_n;

@@ -50,6 +50,7 @@ struct ConvKernelParams {
     int cout2;  // EPI_CONVT: 2*Cout (columns per output-row parity a)
     int H, W;
     int n_classes;
+    int prefetch_dist;  // halo kernel: L2-prefetch the halo boxes of the tile this many grid strides ahead (0 = off)
     int desc_mode;  // halo kernel: 0 = swizzle phase from absolute smem address bits, 1 = descriptor base-offset field
     const float* bias;
     const float* head_w;

@@ -33,8 +33,13 @@ constexpr int H_BAR_BYTES = 512;
 
 __host__ __device__ constexpr int halo_b_stage_bytes(int cout) { return cout * 128; }
 __host__ __device__ constexpr int halo_b_stages(int cout) { return B_RING_BYTES / halo_b_stage_bytes(cout); }
-__host__ __device__ constexpr int halo_smem_bytes() {
-    return 1024 + A_STAGES * HALO_BYTES + B_RING_BYTES + 4 * (H_STAGING_PER_WARP + H_POOL_PER_WARP) + H_BAR_BYTES;
+// RESIDENT: a single-slab layer (Cin = 64) keeps all nine [Cout x 64] weight slabs in smem for the CTA's lifetime.
+__host__ __device__ constexpr int halo_b_bytes(int cout, bool resident) {
+    return resident ? 9 * halo_b_stage_bytes(cout) : B_RING_BYTES;
+}
+__host__ __device__ constexpr int halo_smem_bytes(int cout, bool resident) {
+    return 1024 + A_STAGES * HALO_BYTES + halo_b_bytes(cout, resident) +
+           4 * (H_STAGING_PER_WARP + H_POOL_PER_WARP) + H_BAR_BYTES;
 }
 
 __device__ __forceinline__ uint64_t halo_desc(uint32_t smem_addr, uint32_t base_offset) {
@@ -62,7 +67,7 @@ __device__ __forceinline__ HTile decode_htile(int t, const ConvKernelParams& p) 
     return c;
 }
 
-template <int COUT, int MODE>
+template <int COUT, int MODE, bool RESIDENT>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
@@ -78,7 +83,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_a + A_STAGES * HALO_BYTES;
-    const uint32_t smem_stage = smem_b + B_RING_BYTES;
+    const uint32_t smem_stage = smem_b + halo_b_bytes(COUT, RESIDENT);
     const uint32_t smem_pool = smem_stage + 4 * H_STAGING_PER_WARP;
     const uint32_t smem_bar = smem_pool + 4 * H_POOL_PER_WARP;
     const uint32_t bar_afull = smem_bar;                       // A_STAGES
@@ -87,7 +92,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     const uint32_t bar_bempty = bar_bfull + 8 * B_STAGES;      // B_STAGES
     const uint32_t bar_tfull = bar_bempty + 8 * B_STAGES;      // 2
     const uint32_t bar_tempty = bar_tfull + 16;                // 2
-    const uint32_t tmem_slot = bar_tempty + 16;
+    const uint32_t bar_bres = bar_tempty + 16;                 // 1 (RESIDENT: all weights landed)
+    const uint32_t tmem_slot = bar_bres + 8;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
@@ -111,6 +117,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             mbar_init(bar_tfull + 8 * a, 1);
             mbar_init(bar_tempty + 8 * a, 4);
         }
+        mbar_init(bar_bres, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -124,22 +131,38 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
 
     if (warp == 0) {
         // ------------------------------------------------------------ A producer: one halo box per (tile, slab)
-        if (lane == 0) {
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const HTile tc = decode_htile(t, p);
+                // Only A_STAGES-1 halo boxes can be in flight towards smem, which does not cover HBM latency:
+                // pull the boxes of this CTA's tile after next into L2 now (no smem needed for that).
+                const int tp = t + p.prefetch_dist * static_cast<int>(gridDim.x);
+                if (p.prefetch_dist > 0 && tp < total_tiles && lane == 0) {
+                    const HTile pc = decode_htile(tp, p);
+                    for (int s = 0; s < slabs; ++s) {
+                        if (s < p.slabs0)
+                            tma_prefetch_l2_4d(&map_a0, s * BLOCK_K, pc.x0 - 1, pc.y0 - 1, pc.img);
+                        else
+                            tma_prefetch_l2_4d(&map_a1, (s - p.slabs0) * BLOCK_K, pc.x0 - 1 - p.off_x,
+                                               pc.y0 - 1 - p.off_y, pc.img);
+                    }
+                }
                 for (int s = 0; s < slabs; ++s) {
                     mbar_wait(bar_aempty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_afull + 8 * stage;
-                    mbar_expect_tx(full, HALO_BYTES);
-                    if (s < p.slabs0) {
-                        tma_load_4d(smem_a + stage * HALO_BYTES, &map_a0, full, s * BLOCK_K, tc.x0 - 1, tc.y0 - 1,
-                                    tc.img);
-                    } else {
-                        tma_load_4d(smem_a + stage * HALO_BYTES, &map_a1, full, (s - p.slabs0) * BLOCK_K,
-                                    tc.x0 - 1 - p.off_x, tc.y0 - 1 - p.off_y, tc.img);
+                    if (elect_one()) {
+                        mbar_expect_tx(full, HALO_BYTES);
+                        if (s < p.slabs0) {
+                            tma_load_4d(smem_a + stage * HALO_BYTES, &map_a0, full, s * BLOCK_K, tc.x0 - 1,
+                                        tc.y0 - 1, tc.img);
+                        } else {
+                            tma_load_4d(smem_a + stage * HALO_BYTES, &map_a1, full, (s - p.slabs0) * BLOCK_K,
+                                        tc.x0 - 1 - p.off_x, tc.y0 - 1 - p.off_y, tc.img);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == A_STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -149,7 +172,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         }
     } else if (warp == 2) {
         // ------------------------------------------------------------ B producer: one [Cout x 64] weight slab per tap
-        if (lane == 0) {
+        if (RESIDENT) {
+            if (lane == 0) {
+                mbar_expect_tx(bar_bres, 9 * B_STAGE_BYTES);
+                for (int tap = 0; tap < 9; ++tap)
+                    tma_load_2d(smem_b + tap * B_STAGE_BYTES, &map_b, bar_bres, tap * BLOCK_K, 0);
+            }
+        } else {
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -157,8 +186,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     for (int tap = 0; tap < 9; ++tap) {
                         mbar_wait(bar_bempty + 8 * stage, phase ^ 1);
                         const uint32_t full = bar_bfull + 8 * stage;
-                        mbar_expect_tx(full, B_STAGE_BYTES);
-                        tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full, (tap * slabs + s) * BLOCK_K, 0);
+                        if (elect_one()) {
+                            mbar_expect_tx(full, B_STAGE_BYTES);
+                            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full, (tap * slabs + s) * BLOCK_K, 0);
+                        }
+                        __syncwarp();
                         if (++stage == B_STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -168,11 +200,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------ MMA issuer (warp converged, one elected lane issues)
+        {
             int a_stage = 0, b_stage = 0;
             uint32_t a_phase = 0, b_phase = 0;
             int it = 0;
+            if (RESIDENT) mbar_wait(bar_bres, 0);
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
@@ -183,32 +216,41 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     mbar_wait(bar_afull + 8 * a_stage, a_phase);
                     const uint32_t a_base = smem_a + a_stage * HALO_BYTES;
                     for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(bar_bfull + 8 * b_stage, b_phase);
+                        if (!RESIDENT) mbar_wait(bar_bfull + 8 * b_stage, b_phase);
                         tc_fence_after();
                         const int dy = tap / 3, dx = tap - 3 * dy;
-                        const uint64_t db = umma_desc_sw128(smem_b + b_stage * B_STAGE_BYTES);
+                        const uint64_t db =
+                            umma_desc_sw128(smem_b + (RESIDENT ? tap : b_stage) * B_STAGE_BYTES);
+                        const uint64_t da0 = halo_desc(a_base + (dy * HALO_W + dx) * 128, p.desc_mode ? dx : 0);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            const uint64_t da =
-                                halo_desc(a_base + (dy * HALO_W + dx + 8 * half) * 128, p.desc_mode ? dx : 0);
+                            for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                            for (int k = 0; k < BLOCK_K / 16; ++k) {
-                                umma_bf16_ss(d_tmem + half * COUT, da + 2 * k, db + 2 * k, IDESC, (s | tap | k) != 0);
+                                for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                    // +8 pixels (1024 B) per column half, +32 B per K step, in 16-byte units
+                                    umma_bf16_ss(d_tmem + half * COUT, da0 + 64 * half + 2 * k, db + 2 * k, IDESC,
+                                                 (s | tap | k) != 0);
+                                }
+                            }
+                            if (!RESIDENT) umma_commit(bar_bempty + 8 * b_stage);
+                            if (tap == 8) {
+                                umma_commit(bar_aempty + 8 * a_stage);
+                                if (s == slabs - 1) umma_commit(bar_tfull + 8 * acc);
                             }
                         }
-                        umma_commit(bar_bempty + 8 * b_stage);
-                        if (++b_stage == B_STAGES) {
-                            b_stage = 0;
-                            b_phase ^= 1;
+                        __syncwarp();
+                        if (!RESIDENT) {
+                            if (++b_stage == B_STAGES) {
+                                b_stage = 0;
+                                b_phase ^= 1;
+                            }
                         }
                     }
-                    umma_commit(bar_aempty + 8 * a_stage);
                     if (++a_stage == A_STAGES) {
                         a_stage = 0;
                         a_phase ^= 1;
                     }
                 }
-                umma_commit(bar_tfull + 8 * acc);
             }
         }
     } else {
@@ -288,7 +330,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     uint32_t pk[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                    if (lane == 0) tma_store_wait_read<1>();
+                    if (elect_one()) tma_store_wait_read<1>();
                     __syncwarp();
                     const uint32_t sbuf = my_stage + buf * 4096;
                     const uint32_t row = sbuf + lane * 128;  // lane = (row in 0..3) * 8 + column
@@ -299,7 +341,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) tma_store_4d(&map_out, sbuf, n_glob, xh, yq, tc.img);  // box {64, 8, 4, 1}
+                    if (elect_one()) tma_store_4d(&map_out, sbuf, n_glob, xh, yq, tc.img);  // box {64, 8, 4, 1}
                     if constexpr (MODE == EPI_STORE_POOL) {
                         // pooled 2 rows x 4 columns: max over lanes {2ph*8 + 2pw, +1, +8, +9}
                         const uint32_t pbuf = my_pool + buf * 1024;
@@ -322,19 +364,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
+                        if (elect_one()) {
                             tma_store_4d(&map_pool, pbuf, n_glob, xh >> 1, yq >> 1, tc.img);  // box {64, 4, 2, 1}
                         }
                     }
-                    if (lane == 0) tma_store_commit();
+                    if (elect_one()) tma_store_commit();
                     buf ^= 1;
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            if (elect_one()) mbar_arrive(bar_tempty + 8 * acc);
         }
-        if (MODE != EPI_HEAD && lane == 0) tma_store_wait_all();
+        __syncwarp();
+        if (MODE != EPI_HEAD && elect_one()) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -345,11 +388,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     }
 }
 
-template <int COUT, int MODE>
+template <int COUT, int MODE, bool RESIDENT = false>
 const char* launch_halo_inst(const ConvLaunch& l, cudaStream_t stream) {
-    auto kfn = conv_halo_kernel<COUT, MODE>;
+    if constexpr (COUT == 64 && !RESIDENT) {
+        if (l.p.slabs0 + l.p.slabs1 == 1) return launch_halo_inst<COUT, MODE, true>(l, stream);
+    }
+    auto kfn = conv_halo_kernel<COUT, MODE, RESIDENT>;
     static bool configured = false;
-    constexpr int smem = halo_smem_bytes();
+    constexpr int smem = halo_smem_bytes(COUT, RESIDENT);
+    static_assert(smem <= 232448, "halo kernel exceeds the 227 KB shared memory limit");
     if (!configured) {
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
             return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";

@@ -120,6 +120,16 @@ struct fiNet {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;  // [call][step][2], resolved by fiNetGetProfile
     int prof_calls = 0;
+    // clip pipeline (fiNetInterpolateClipHostU8): double-buffered pinned + device staging, copy streams, events
+    struct ClipSlot {
+        void* pin_in = nullptr;
+        void* pin_out = nullptr;
+        void* dev_in = nullptr;
+        void* dev_out = nullptr;
+        cudaEvent_t in_ready = nullptr, done = nullptr, out_ready = nullptr;
+    } clip[2];
+    size_t clip_in_bytes = 0, clip_out_bytes = 0;
+    cudaStream_t clip_h2d = nullptr, clip_d2h = nullptr;
     // pinned staging for the host-buffer convenience call
     void* pin_in = nullptr;
     void* pin_out = nullptr;
@@ -512,6 +522,17 @@ int fiNetDestroy(fiNet* net) {
     if (net->pin_in) cudaFreeHost(net->pin_in);
     if (net->pin_out) cudaFreeHost(net->pin_out);
     for (cudaEvent_t e : net->prof_events) cudaEventDestroy(e);
+    for (auto& c : net->clip) {
+        if (c.pin_in) cudaFreeHost(c.pin_in);
+        if (c.pin_out) cudaFreeHost(c.pin_out);
+        if (c.dev_in) cudaFree(c.dev_in);
+        if (c.dev_out) cudaFree(c.dev_out);
+        if (c.in_ready) cudaEventDestroy(c.in_ready);
+        if (c.done) cudaEventDestroy(c.done);
+        if (c.out_ready) cudaEventDestroy(c.out_ready);
+    }
+    if (net->clip_h2d) cudaStreamDestroy(net->clip_h2d);
+    if (net->clip_d2h) cudaStreamDestroy(net->clip_d2h);
     delete net;
     return FI_OK;
 }
@@ -707,6 +728,86 @@ int fiNetInterpolateHostU8(fiNet* net, const uint8_t* frame1_host, const uint8_t
     CUDA_TRY(cudaStreamSynchronize(st));
     memcpy(out_host, net->pin_out, out_bytes);
     return FI_OK;
+}
+
+int fiNetInterpolateClipHostU8(fiNet* net, const uint8_t* frames_host, int n_frames, int channels_per_frame,
+                               uint8_t* out_host, int H, int W, int pairs_per_batch, void* stream) {
+    if (!net || !frames_host || !out_host) return fail(FI_ERR_INVALID, "null argument");
+    if (2 * channels_per_frame != net->n_channels)
+        return fail(FI_ERR_INVALID, "2 x %d channels per frame != n_channels %d", channels_per_frame, net->n_channels);
+    if (n_frames < 2 || H <= 0 || W <= 0 || pairs_per_batch < 1) return fail(FI_ERR_INVALID, "empty clip or batch");
+    int rc = set_device(net->device);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int B = pairs_per_batch;
+    const size_t frame_bytes = static_cast<size_t>(channels_per_frame) * H * W;
+    const size_t outf_bytes = static_cast<size_t>(net->n_classes) * H * W;
+    const size_t in_bytes = (B + 1) * frame_bytes, out_bytes = B * outf_bytes;
+    if (!net->clip_h2d) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&net->clip_h2d, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&net->clip_d2h, cudaStreamNonBlocking));
+        for (auto& c : net->clip) {
+            CUDA_TRY(cudaEventCreateWithFlags(&c.in_ready, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c.out_ready, cudaEventDisableTiming));
+        }
+    }
+    if (net->clip_in_bytes < in_bytes || net->clip_out_bytes < out_bytes) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        for (auto& c : net->clip) {
+            if (c.pin_in) cudaFreeHost(c.pin_in);
+            if (c.pin_out) cudaFreeHost(c.pin_out);
+            if (c.dev_in) cudaFree(c.dev_in);
+            if (c.dev_out) cudaFree(c.dev_out);
+            c.pin_in = c.pin_out = c.dev_in = c.dev_out = nullptr;
+        }
+        net->clip_in_bytes = net->clip_out_bytes = 0;
+        for (auto& c : net->clip) {
+            CUDA_TRY(cudaMallocHost(&c.pin_in, in_bytes));
+            CUDA_TRY(cudaMallocHost(&c.pin_out, out_bytes));
+            CUDA_TRY(cudaMalloc(&c.dev_in, in_bytes));
+            CUDA_TRY(cudaMalloc(&c.dev_out, out_bytes));
+        }
+        net->clip_in_bytes = in_bytes;
+        net->clip_out_bytes = out_bytes;
+    }
+    const int n_pairs = n_frames - 1;
+    const int n_batches = (n_pairs + B - 1) / B;
+    auto collect = [&](int b) -> int {  // wait for batch b's D2H and hand its frames to the caller
+        fiNet::ClipSlot& c = net->clip[b & 1];
+        CUDA_TRY(cudaEventSynchronize(c.out_ready));
+        const int first = b * B;
+        const int cnt = n_pairs - first < B ? n_pairs - first : B;
+        memcpy(out_host + static_cast<size_t>(first) * outf_bytes, c.pin_out, cnt * outf_bytes);
+        return FI_OK;
+    };
+    for (int b = 0; b < n_batches; ++b) {
+        fiNet::ClipSlot& c = net->clip[b & 1];
+        const int first = b * B;
+        const int cnt = n_pairs - first < B ? n_pairs - first : B;
+        // slot reuse is safe: batch b-2 was collected (host-synchronised) in iteration b-1
+        memcpy(c.pin_in, frames_host + static_cast<size_t>(first) * frame_bytes, (cnt + 1) * frame_bytes);
+        CUDA_TRY(cudaMemcpyAsync(c.dev_in, c.pin_in, (cnt + 1) * frame_bytes, cudaMemcpyHostToDevice, net->clip_h2d));
+        CUDA_TRY(cudaEventRecord(c.in_ready, net->clip_h2d));
+        CUDA_TRY(cudaStreamWaitEvent(st, c.in_ready, 0));
+        fiPlanes p0, p1;
+        p0.ptr = c.dev_in;
+        p0.channels = channels_per_frame;
+        p0.px_stride = 1;
+        p0.row_stride = W;
+        p0.chan_stride = static_cast<int64_t>(H) * W;
+        p0.batch_stride = p0.chan_stride * channels_per_frame;
+        p1 = p0;
+        p1.ptr = static_cast<const uint8_t*>(c.dev_in) + frame_bytes;
+        rc = fiNetForward(net, &p0, &p1, FI_IN_U8, nullptr, static_cast<uint8_t*>(c.dev_out), cnt, H, W, stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(c.done, st));
+        CUDA_TRY(cudaStreamWaitEvent(net->clip_d2h, c.done, 0));
+        CUDA_TRY(cudaMemcpyAsync(c.pin_out, c.dev_out, cnt * outf_bytes, cudaMemcpyDeviceToHost, net->clip_d2h));
+        CUDA_TRY(cudaEventRecord(c.out_ready, net->clip_d2h));
+        if (b > 0 && (rc = collect(b - 1))) return rc;
+    }
+    return collect(n_batches - 1);
 }
 
 int fiNetForwardCost(fiNet* net, int N, int H, int W, double* flops, int* launches) {

@@ -53,6 +53,8 @@ _SIGNATURES = {
                                C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fiNetInterpolateHostU8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                          C.c_int, C.c_void_p]),
+    "fiNetInterpolateClipHostU8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_int, C.c_void_p]),
     "fiNetForwardCost": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "fiNetReadActivation": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int),
                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -180,6 +182,18 @@ class Net:
         with torch.cuda.device(self.device):
             check(lib().fiNetInterpolateHostU8(self._h, f1.ctypes.data, f2.ctypes.data, c, out.ctypes.data, n, h, w,
                                                current_stream()))
+        return out
+
+    def interpolate_clip_host_u8(self, frames, pairs_per_batch=4):
+        """numpy uint8 [F,C,H,W] host clip in, numpy uint8 [F-1,n_classes,H,W] midpoints out; copies and compute are
+        pipelined inside the library."""
+        import numpy as np
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        f, c, h, w = frames.shape
+        out = np.empty((f - 1, self.n_classes, h, w), dtype=np.uint8)
+        with torch.cuda.device(self.device):
+            check(lib().fiNetInterpolateClipHostU8(self._h, frames.ctypes.data, f, c, out.ctypes.data, h, w,
+                                                   pairs_per_batch, current_stream()))
         return out
 
     def set_profiling(self, on):

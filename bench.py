@@ -9,7 +9,7 @@ configs[2]: 600 synthetic 1920x1080 frames, frame pairs sharded across the GPUs 
 
 A step = one forward of `--pairs` consecutive frame pairs (u8 frames resident in HBM -> u8 interpolated frames in HBM).
 `value` is device-timed (CUDA events, max over ranks); `e2e` goes through the C-ABI host-buffer entry point
-(fiNetInterpolateHostU8: pinned H2D of both frames, forward, D2H of the result, all inside the timed region).
+(fiNetInterpolateClipHostU8: pinned H2D of every frame, forward, D2H of every result, all inside the timed region).
 """
 import argparse
 import json
@@ -82,18 +82,19 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synthetic_frames(n, seed):
-    """Moving bright disc over a gradient + noise (the reference's only data generator is of this kind,
-    demo_simple.py:17-40), seeded."""
+def synthetic_frames(n, first=0):
+    """Frames [first, first+n) of the synthetic clip: a moving bright disc over a gradient + noise (the reference's
+    only data generator is of this kind, demo_simple.py:17-40), seeded per frame index."""
     import numpy as np
-    rs = np.random.RandomState(seed)
     yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
     base = (xx / W * 96 + yy / H * 64).astype(np.float32)
     out = np.empty((n, 1, H, W), dtype=np.uint8)
-    for i in range(n):
-        cx, cy = 200 + 9.0 * i, 540 + 120 * np.sin(i / 7.0)
+    for k in range(n):
+        i = first + k
+        rs = np.random.RandomState(1000 + i)
+        cx, cy = 200 + 2.5 * i, 540 + 120 * np.sin(i / 7.0)
         disc = ((xx - cx) ** 2 + (yy - cy) ** 2 < 90 ** 2) * 120.0
-        out[i, 0] = np.clip(base + disc + rs.randint(0, 24, size=(H, W)), 0, 255).astype(np.uint8)
+        out[k, 0] = np.clip(base + disc + rs.randint(0, 24, size=(H, W)), 0, 255).astype(np.uint8)
     return out
 
 
@@ -103,7 +104,7 @@ def cpu_forward_seconds(pairs, threads):
     from oracle import unet_oracle as O
     torch.set_num_threads(threads)
     sd = O.init_state_dict(0, 2, 1, False)
-    fr = synthetic_frames(pairs + 1, 0)
+    fr = synthetic_frames(pairs + 1)
     x = torch.cat([O.preprocess_u8(fr[:-1]), O.preprocess_u8(fr[1:])], 1)
     O.unet_forward(sd, x[:1, :, :64, :64])  # thread-pool / allocator warm-up on a tiny crop
     t0 = time.perf_counter()
@@ -121,7 +122,7 @@ def run_reference(args):
     from oracle import unet_oracle as O
     torch.set_num_threads(threads)
     sd = O.init_state_dict(0, 2, 1, False)
-    fr = synthetic_frames(2, 0)
+    fr = synthetic_frames(2)
     x = torch.cat([O.preprocess_u8(fr[:1]), O.preprocess_u8(fr[1:])], 1)
     O.unet_forward(sd, x[:, :, :64, :64])
     budget_s, times = 200.0, []
@@ -203,11 +204,12 @@ def main():
     net = E.Net(dev, 2, 1, args.bilinear)
     net.load_state_dict(O.init_state_dict(0, 2, 1, args.bilinear))
 
-    # this rank's contiguous shard of the 599 frame pairs (1-frame overlap at the boundaries), synthetic
-    pairs_total = N_FRAMES - 1
-    per_rank = (pairs_total + world - 1) // world
-    n_local = min(B * 4 + 1, per_rank + 1)  # a rotating window of the shard is enough to defeat reuse
-    host = synthetic_frames(n_local, seed=rank)
+    # this rank's contiguous shard of the 599 frame pairs (neighbouring ranks share one boundary frame); the timed
+    # steps rotate over a window of the shard (generating all 600 1080p frames on the host would only slow start-up)
+    from model.sharding import shard_pairs
+    first_pair, n_pairs = shard_pairs(N_FRAMES, world, rank)
+    n_local = max(B + 1, min(B * 4 + 1, n_pairs + 1))
+    host = synthetic_frames(n_local, first=first_pair)
     frames = torch.from_numpy(host).to(dev)
 
     def step(i):
@@ -235,16 +237,15 @@ def main():
     net.set_profiling(False)
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- end to end through the host-buffer C-ABI call
+    # ---- end to end through the host-buffer C-ABI call: one clip of steps*B frame pairs on the HOST in, the
+    # interpolated frames on the HOST out (pinned H2D of every frame, forward, D2H of every result inside the region)
     e2e_steps = args.steps
-    host_a = [np.ascontiguousarray(host[(i * B) % (n_local - B):][:B]) for i in range(4)]
-    host_b = [np.ascontiguousarray(host[(i * B) % (n_local - B) + 1:][:B]) for i in range(4)]
-    for i in range(2):
-        net.interpolate_host_u8(host_a[i % 4], host_b[i % 4])
+    idx = np.arange(e2e_steps * B + 1) % n_local
+    clip = np.ascontiguousarray(host[idx])
+    net.interpolate_clip_host_u8(clip[:2 * B + 1], B)  # staging buffers + streams allocated outside the timed region
     barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        res = net.interpolate_host_u8(host_a[i % 4], host_b[i % 4])
+    res = net.interpolate_clip_host_u8(clip, B)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * B * e2e_steps / e2e_s
@@ -291,9 +292,10 @@ def main():
                    "l2": "inputs larger than L2: %.1f GB of activations written and re-read per step vs 126 MB L2; "
                          "frame window rotates every step" % (2.3 * B)},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": 2 * B * H * W,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": (B + 1) * H * W,
                 "d2h_bytes_per_step": B * H * W, "steps": e2e_steps,
-                "api": "fiNetInterpolateHostU8 (host u8 frames -> host u8 frames, synchronous)"},
+                "api": "fiNetInterpolateClipHostU8: host u8 clip -> host u8 interpolated frames, one synchronous "
+                       "call over steps*pairs_per_step pairs; copies overlap compute inside the library"},
         "gpu_launches": launches_step * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,

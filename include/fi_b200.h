@@ -76,6 +76,14 @@ int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dt
 int fiNetInterpolateHostU8(fiNet* net, const uint8_t* frame1_host, const uint8_t* frame2_host, int channels_per_frame,
                            uint8_t* out_host, int N, int H, int W, void* stream);
 
+/* The video loop FrameInterpolator.interpolate_video needs (reference main.py:118-129; the reference never wrote it,
+ * SURVEY.md D3): a clip of n_frames planar u8 frames [n_frames, C, H, W] on the host -> the n_frames-1 midpoint
+ * frames [n_frames-1, n_classes, H, W] on the host. Frames are uploaded once per batch of `pairs_per_batch` pairs;
+ * H2D of batch i+1, the forward of batch i and D2H of batch i-1 overlap (two copy streams + `stream`, double-buffered
+ * pinned staging). Synchronous: returns when out_host is complete. */
+int fiNetInterpolateClipHostU8(fiNet* net, const uint8_t* frames_host, int n_frames, int channels_per_frame,
+                               uint8_t* out_host, int H, int W, int pairs_per_batch, void* stream);
+
 /* Algorithmic FLOPs (2*MACs, no padding) of one forward at this shape, and the number of kernel launches it makes. */
 int fiNetForwardCost(fiNet* net, int N, int H, int W, double* flops, int* launches);
 /* Measurement hook for bench.py: when enabled, every launch of the following forwards is bracketed by a CUDA event

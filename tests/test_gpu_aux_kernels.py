@@ -120,3 +120,17 @@ def test_host_buffer_entry_point(cuda_device):
     assert np.array_equal(out, dev.cpu().numpy())
     ref = O.postprocess(O.unet_forward(sd, torch.cat([O.preprocess_u8(f1), O.preprocess_u8(f2)], 1)))
     assert np.abs(out.astype(int) - ref.astype(int)).max() <= 2
+
+
+def test_clip_pipeline_matches_pairwise_calls(cuda_device):
+    """fiNetInterpolateClipHostU8 (pipelined video loop) == the synchronous per-batch entry point, bit for bit,
+    including a ragged last batch."""
+    sd = O.init_state_dict(0, 2, 1, False)
+    net = E.Net(cuda_device, 2, 1, False)
+    net.load_state_dict(sd)
+    rs = np.random.RandomState(3)
+    clip = rs.randint(0, 256, size=(12, 1, 40, 56)).astype(np.uint8)
+    ref = net.interpolate_host_u8(clip[:-1], clip[1:])
+    for b in (1, 3, 4, 16):
+        out = net.interpolate_clip_host_u8(clip, pairs_per_batch=b)
+        assert out.shape == (11, 1, 40, 56) and np.array_equal(out, ref), b
