@@ -1,4 +1,4 @@
-// CUDA-core kernels of the frame-synthesis path: the stem convolution (tiny K, HBM-write bound), the bilinear
+// CUDA-core kernels of the frame-synthesis path (the stem convolution lives in stem_mma.cu): the bilinear
 // decoder upsample, frame-pair packing, output post-processing and the fused SSIM+PSNR metric kernel.
 #include "aux_kernels.cuh"
 #include "ptx.cuh"
@@ -10,103 +10,6 @@ namespace {
 __device__ __forceinline__ float norm_u8(uint8_t u) {
     // image.astype(float32)/255.0 then 2.0*image-1.0, each rounded to fp32 (reference model/inference.py:32-35)
     return __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(static_cast<float>(u), 255.0f)), 1.0f);
-}
-
-// ------------------------------------------------------------------------------------------------ stem conv
-// inc.double_conv.0 (reference model/unet.py:12-14 with C_in = n_channels): conv3x3 + folded BN + ReLU, K = 9*C_in <= 72.
-// Arithmetic intensity ~17 FLOP/B -> bound by the 128 B/pixel bf16 NHWC write; fp32 CUDA-core math on exact inputs.
-constexpr int ST_TH = 8;
-constexpr int ST_TW = 32;
-constexpr int ST_MAXC = 8;
-
-template <bool U8>
-__global__ void __launch_bounds__(256) stem_conv_kernel(const StemDesc d) {
-    __shared__ float in_s[ST_MAXC][ST_TH + 2][ST_TW + 2];
-    __shared__ __align__(16) float w_s[9 * ST_MAXC * 64];
-    __shared__ __align__(16) float b_s[64];
-
-    const int tid = threadIdx.x;
-    const int tiles_x = (d.W + ST_TW - 1) / ST_TW;
-    const int tiles_y = (d.H + ST_TH - 1) / ST_TH;
-    int t = blockIdx.x;
-    const int n = t / (tiles_x * tiles_y);
-    t -= n * tiles_x * tiles_y;
-    const int y0 = (t / tiles_x) * ST_TH;
-    const int x0 = (t % tiles_x) * ST_TW;
-
-    for (int i = tid; i < 9 * d.cin * 64; i += 256) w_s[i] = d.w[i];
-    if (tid < 64) b_s[tid] = d.bias[tid];
-
-    const int halo = (ST_TH + 2) * (ST_TW + 2);
-    for (int i = tid; i < d.cin * halo; i += 256) {
-        const int c = i / halo;
-        const int r = (i - c * halo) / (ST_TW + 2);
-        const int col = i - c * halo - r * (ST_TW + 2);
-        const int y = y0 + r - 1, x = x0 + col - 1;
-        float v = 0.0f;  // zero padding of the (already normalised) input
-        if (y >= 0 && y < d.H && x >= 0 && x < d.W) {
-            const bool first = c < d.src[0].channels;
-            const PlaneSrc& s = first ? d.src[0] : d.src[1];
-            const int cc = first ? c : c - d.src[0].channels;
-            const long long off = n * s.batch_stride + cc * s.chan_stride + y * s.row_stride + x * s.px_stride;
-            if (U8) v = norm_u8(static_cast<const uint8_t*>(s.ptr)[off]);
-            else v = static_cast<const float*>(s.ptr)[off];
-        }
-        in_s[c][r][col] = v;
-    }
-    __syncthreads();
-
-    const int cg = tid & 7;   // output channels [8cg, 8cg+8)
-    const int pl = tid >> 3;  // tile column
-    float acc[ST_TH][8];
-#pragma unroll
-    for (int r = 0; r < ST_TH; ++r)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[r][j] = b_s[cg * 8 + j];
-
-    const float4* w4 = reinterpret_cast<const float4*>(w_s);
-    for (int c = 0; c < d.cin; ++c) {
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            float col[ST_TH + 2];
-#pragma unroll
-            for (int r = 0; r < ST_TH + 2; ++r) col[r] = in_s[c][r][pl + dx];
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-                const int wi = (((dy * 3 + dx) * d.cin + c) * 64 + cg * 8) >> 2;
-                const float4 wa = w4[wi], wb = w4[wi + 1];
-#pragma unroll
-                for (int r = 0; r < ST_TH; ++r) {
-                    const float v = col[r + dy];
-                    acc[r][0] = fmaf(v, wa.x, acc[r][0]);
-                    acc[r][1] = fmaf(v, wa.y, acc[r][1]);
-                    acc[r][2] = fmaf(v, wa.z, acc[r][2]);
-                    acc[r][3] = fmaf(v, wa.w, acc[r][3]);
-                    acc[r][4] = fmaf(v, wb.x, acc[r][4]);
-                    acc[r][5] = fmaf(v, wb.y, acc[r][5]);
-                    acc[r][6] = fmaf(v, wb.z, acc[r][6]);
-                    acc[r][7] = fmaf(v, wb.w, acc[r][7]);
-                }
-            }
-        }
-    }
-
-    const int x = x0 + pl;
-    if (x < d.W) {
-        uint4* dst = static_cast<uint4*>(d.dst);
-#pragma unroll
-        for (int r = 0; r < ST_TH; ++r) {
-            const int y = y0 + r;
-            if (y < d.H) {
-                uint4 o;
-                o.x = pack_bf16x2(fmaxf(acc[r][0], 0.f), fmaxf(acc[r][1], 0.f));
-                o.y = pack_bf16x2(fmaxf(acc[r][2], 0.f), fmaxf(acc[r][3], 0.f));
-                o.z = pack_bf16x2(fmaxf(acc[r][4], 0.f), fmaxf(acc[r][5], 0.f));
-                o.w = pack_bf16x2(fmaxf(acc[r][6], 0.f), fmaxf(acc[r][7], 0.f));
-                dst[((static_cast<size_t>(n) * d.H + y) * d.W + x) * 8 + cg] = o;  // 8 x 16 B per pixel
-            }
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------ bilinear x2
@@ -408,17 +311,6 @@ const char* last_launch_error() {
 }
 
 }  // namespace
-
-const char* stem_conv_launch(const StemDesc& d, cudaStream_t stream) {
-    if (d.cin < 1 || d.cin > ST_MAXC) return "stem: 1..8 input channels supported";
-    if (d.src[0].channels + d.src[1].channels != d.cin) return "stem: plane sources do not add up to cin";
-    if (d.N <= 0 || d.H <= 0 || d.W <= 0) return "stem: empty shape";
-    const long long tiles = static_cast<long long>(d.N) * ((d.H + ST_TH - 1) / ST_TH) * ((d.W + ST_TW - 1) / ST_TW);
-    if (tiles > 0x7fffffffLL) return "stem: too many tiles";
-    if (d.is_u8) stem_conv_kernel<true><<<static_cast<int>(tiles), 256, 0, stream>>>(d);
-    else stem_conv_kernel<false><<<static_cast<int>(tiles), 256, 0, stream>>>(d);
-    return last_launch_error();
-}
 
 const char* upsample2x_launch(const void* src, void* dst, int N, int h, int w, int C, cudaStream_t stream) {
     if (C % 8) return "upsample: channels must be a multiple of 8";

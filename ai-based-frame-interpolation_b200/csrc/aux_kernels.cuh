@@ -19,11 +19,13 @@ struct StemDesc {
     int is_u8;           // 1: uint8 pixels, normalised in-kernel as u8/255*2-1 (reference inference.py:32-35); 0: fp32
     int cin;             // total input channels (<= 8)
     int N, H, W;
-    const float* w;      // fp32 [9][cin][64], BN folded
+    const void* wpack;   // bf16 [64][stem_packed_k(cin)], hi/lo split rows (stem_pack_weights), BN folded
     const float* bias;   // fp32 [64]
     void* dst;           // bf16 NHWC [N,H,W,64]
 };
-const char* stem_conv_launch(const StemDesc& d, cudaStream_t stream);
+const char* stem_conv_launch(const StemDesc& d, cudaStream_t stream);  // stem_mma.cu
+int stem_packed_k(int cin);                                               // packed K length (multiple of 64)
+void stem_pack_weights(const float* w /*[64][cin][3][3]*/, int cin, uint16_t* out /*[64][stem_packed_k]*/);
 
 // nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) on bf16 NHWC (reference unet.py:40).
 const char* upsample2x_launch(const void* src, void* dst, int N, int h, int w, int C, cudaStream_t stream);

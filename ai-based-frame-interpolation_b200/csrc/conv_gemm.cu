@@ -397,6 +397,11 @@ const char* launch_inst(const ConvLaunch& l, cudaStream_t stream) {
 
 }  // namespace
 
+const char* encode_bf16_map_public(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                                   const uint64_t* strides_elems, const uint32_t* box) {
+    return encode_bf16_map(map, base, rank, dims, strides_elems, box);
+}
+
 const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     if (d.N <= 0 || d.H <= 0 || d.W <= 0) return "conv: empty shape";
     if (d.taps != 9 && d.taps != 1) return "conv: taps must be 9 (3x3) or 1";

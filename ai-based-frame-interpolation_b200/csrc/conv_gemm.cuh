@@ -78,6 +78,10 @@ struct ConvLaunch {
 const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out);
 const char* conv_launch(const ConvLaunch& l, cudaStream_t stream);
 
+// bf16 tensor map (128B swizzle, zero OOB fill); dims/box innermost first, strides in elements for dims 1..rank-1.
+const char* encode_bf16_map_public(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                                   const uint64_t* strides_elems, const uint32_t* box);
+
 // conv_halo.cu
 bool conv_halo_eligible(const ConvDesc& d);
 void conv_halo_geometry(int* tile, int* box_w, int* box_h, int* out_w, int* out_h, int* pool_w, int* pool_h);

@@ -112,7 +112,7 @@ struct fiNet {
     int n_channels = 2, n_classes = 1, bilinear = 0;
     int num_sms = 148;
     bool loaded = false;
-    DevBuf stem_w, stem_b;  // fp32 [9][cin][64], [64]
+    DevBuf stem_w, stem_b;  // bf16 [64][stem_packed_k] hi/lo split, fp32 [64]
     ConvW convs[17];        // inc.3, down{1-4}.{0,3}, up{1-4}.{0,3}
     ConvW upT[4];           // ConvTranspose2d of up1..up4 (bilinear=False)
     DevBuf head_w, head_b;  // fp32 [n_classes][64], [n_classes]
@@ -551,19 +551,20 @@ int fiNetLoadWeights(fiNet* net, const char* const* names, const float* const* d
     int upc[4][2];
     conv_shapes(net, cs, stem, upc);
     std::string err;
-    {   // stem: fp32 [tap][cin][64], BN folded (inc.double_conv.0 / .1)
+    {   // stem: BN folded in fp64 (inc.double_conv.0 / .1), then split into bf16 hi/lo rows for the tensor-core stem
         const float* w = sd.get("inc.double_conv.0.weight", static_cast<int64_t>(64) * stem.cin * 9, &err);
         std::vector<double> scale;
         std::vector<float> shift;
         if (!w || !bn_fold(sd, "inc.double_conv.1", 64, &scale, &shift, &err))
             return fail(FI_ERR_WEIGHTS, "%s", err.c_str());
-        std::vector<float> ws(static_cast<size_t>(9) * stem.cin * 64);
+        std::vector<float> ws(static_cast<size_t>(64) * stem.cin * 9);
         for (int co = 0; co < 64; ++co)
-            for (int ci = 0; ci < stem.cin; ++ci)
-                for (int t = 0; t < 9; ++t)
-                    ws[(static_cast<size_t>(t) * stem.cin + ci) * 64 + co] = static_cast<float>(
-                        static_cast<double>(w[(static_cast<size_t>(co) * stem.cin + ci) * 9 + t]) * scale[co]);
-        CUDA_TRY(net->stem_w.upload(ws.data(), ws.size() * 4));
+            for (size_t i = 0; i < static_cast<size_t>(stem.cin) * 9; ++i)
+                ws[co * static_cast<size_t>(stem.cin) * 9 + i] = static_cast<float>(
+                    static_cast<double>(w[co * static_cast<size_t>(stem.cin) * 9 + i]) * scale[co]);
+        std::vector<uint16_t> packed(static_cast<size_t>(64) * fi::stem_packed_k(stem.cin));
+        fi::stem_pack_weights(ws.data(), stem.cin, packed.data());
+        CUDA_TRY(net->stem_w.upload(packed.data(), packed.size() * 2));
         CUDA_TRY(net->stem_b.upload(shift.data(), shift.size() * 4));
     }
     for (int i = 0; i < 17; ++i)
@@ -620,7 +621,7 @@ int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dt
             d.N = N;
             d.H = H;
             d.W = W;
-            d.w = static_cast<const float*>(net->stem_w.p);
+            d.wpack = net->stem_w.p;
             d.bias = static_cast<const float*>(net->stem_b.p);
             d.dst = s.dst;
             KERNEL_TRY(fi::stem_conv_launch(d, st));
@@ -888,9 +889,18 @@ int fiConvGemm(const fiConvDesc* desc, void* stream) {
     return FI_OK;
 }
 
-int fiStemConv(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const float* w, const float* bias, void* dst,
+int fiStemPackedK(int cin) { return cin >= 1 && cin <= 8 ? fi::stem_packed_k(cin) : 0; }
+
+int fiStemPackWeights(const float* w_host, int cin, uint16_t* out_host) {
+    if (!w_host || !out_host) return fail(FI_ERR_INVALID, "null argument");
+    if (cin < 1 || cin > 8) return fail(FI_ERR_INVALID, "stem: 1..8 input channels supported");
+    fi::stem_pack_weights(w_host, cin, out_host);
+    return FI_OK;
+}
+
+int fiStemConv(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const void* wpack, const float* bias, void* dst,
                int N, int H, int W, void* stream) {
-    if (!in0 || !w || !bias || !dst) return fail(FI_ERR_INVALID, "null argument");
+    if (!in0 || !wpack || !bias || !dst) return fail(FI_ERR_INVALID, "null argument");
     fi::StemDesc d;
     memset(&d, 0, sizeof d);
     d.src[0] = to_src(in0);
@@ -900,7 +910,7 @@ int fiStemConv(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const flo
     d.N = N;
     d.H = H;
     d.W = W;
-    d.w = w;
+    d.wpack = wpack;
     d.bias = bias;
     d.dst = dst;
     const char* e = fi::stem_conv_launch(d, static_cast<cudaStream_t>(stream));

@@ -1,0 +1,418 @@
+// Stem convolution (inc.double_conv.0, reference model/unet.py:12-14 with C_in = n_channels <= 8) on the tensor cores.
+//
+// K = 9*C_in is tiny (18 for the grey frame pair), so the layer is bound by writing 128 B/pixel of bf16 NHWC output;
+// the fp32 CUDA-core version spent 1152 FMA lane-ops per pixel and ran at ~20 % of that bound. Here producer threads
+// build the im2col row of their pixel directly in a 128B-swizzled smem tile and one tcgen05.mma slab does the math.
+// To keep fp32-grade accuracy on the un-rounded input (the whole point of an exact stem, SURVEY.md "hard parts"), both
+// operands are split into bf16 hi + lo parts and three of the four cross products are accumulated:
+//     A row  = [ x_hi (KT) | x_hi (KT) | x_lo (KT) | 0 ... ]        KT = 9*C_in, padded to a multiple of 64
+//     B row  = [ w_hi (KT) | w_lo (KT) | w_hi (KT) | 0 ... ]        -> sum = x_hi*w_hi + x_hi*w_lo + x_lo*w_hi
+// (the dropped x_lo*w_lo term is O(2^-18) relative). Input normalisation u8/255*2-1 (reference inference.py:32-35),
+// the frame-pair torch.cat (unet.py:109) and the conv zero padding are all done by the gather.
+// Warp roles (288 threads): 0..3 = im2col producers (thread = pixel of the 8x16 tile), 4 = MMA issuer + TMEM owner,
+// 5..8 = epilogue (bias + ReLU -> bf16 -> swizzled staging -> TMA store). Two CTAs fit per SM.
+#include "aux_kernels.cuh"
+#include "conv_gemm.cuh"
+#include "ptx.cuh"
+
+#include <cstring>
+
+namespace fi {
+
+namespace {
+
+constexpr int SM_THREADS = 288;
+constexpr int SM_A_STAGES = 3;
+constexpr int SM_A_BYTES = 128 * 128;  // 128 pixels x 64 bf16
+
+struct StemParams {
+    PlaneSrc src[2];
+    int N, H, W, tiles_x, tiles_y;
+    const float* bias;
+};
+
+__host__ __device__ constexpr int stem_slabs(int cin) { return (27 * cin + 63) / 64; }
+constexpr int SM_IN_ROWS = TILE_H + 2, SM_IN_COLS = TILE_W + 2, SM_IN_PITCH = 20;  // input tile + halo, padded pitch
+__host__ __device__ constexpr int stem_in_bytes(int cin) { return 2 * cin * SM_IN_ROWS * SM_IN_PITCH * 4; }
+__host__ __device__ constexpr int stem_smem_bytes(int cin) {
+    return 1024 + SM_A_STAGES * SM_A_BYTES + stem_slabs(cin) * 8192 + 4 * 2 * 4096 + 256 + 1040 + stem_in_bytes(cin);
+}
+
+__device__ __forceinline__ float norm_u8_stem(uint8_t u) {
+    return __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(static_cast<float>(u), 255.0f)), 1.0f);
+}
+__device__ __forceinline__ uint32_t bf16_bits(float v) {  // round-to-nearest-even bf16, as the upper 16 bits
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v), "f"(0.0f));
+    return r & 0xffff0000u;
+}
+
+template <int CIN, bool U8>
+__global__ void __launch_bounds__(SM_THREADS, CIN <= 3 ? 2 : 1)
+stem_mma_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
+                const StemParams p) {
+    constexpr int KT = 9 * CIN;
+    constexpr int SLABS = stem_slabs(CIN);
+    constexpr uint32_t IDESC = umma_idesc_bf16(128, 64);
+    constexpr int TMEM_COLS = 128;  // 2 accumulators x 64 columns
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_b = smem_a + SM_A_STAGES * SM_A_BYTES;
+    const uint32_t smem_stage = smem_b + SLABS * 8192;
+    const uint32_t smem_bar = smem_stage + 4 * 2 * 4096;
+    const uint32_t bar_full = smem_bar;                       // SM_A_STAGES
+    const uint32_t bar_empty = bar_full + 8 * SM_A_STAGES;    // SM_A_STAGES
+    const uint32_t bar_tfull = bar_empty + 8 * SM_A_STAGES;   // 2
+    const uint32_t bar_tempty = bar_tfull + 16;               // 2
+    const uint32_t bar_bres = bar_tempty + 16;                // 1
+    const uint32_t tmem_slot = bar_bres + 8;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    // u8 -> (bf16 hi | bf16 lo << 16) of the normalised value, and the double-buffered split input tile
+    uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + (smem_bar + 256 - smem_u32(smem_raw)));
+    uint32_t* in_tile = lut + 260;  // 257 LUT slots (slot 256 = zero padding), padded
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (U8 && threadIdx.x < 256) {
+        const float v = norm_u8_stem(static_cast<uint8_t>(threadIdx.x));
+        const uint32_t h = bf16_bits(v);
+        lut[threadIdx.x] = (h >> 16) | bf16_bits(v - __uint_as_float(h));
+        if (threadIdx.x == 0) lut[256] = 0u;
+    }
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
+        for (int s = 0; s < SM_A_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 4);   // one arrive per producer warp
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4);
+        }
+        mbar_init(bar_bres, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int per_img = p.tiles_y * p.tiles_x;
+    const int total_tiles = p.N * per_img;
+
+    if (warp < 4) {
+        // ------------------------------------------------------------ im2col producers: thread = pixel
+        // Phase A (cooperative): the (8+2)x(16+2) input tile of every channel is loaded once, normalised and split into
+        // bf16 hi/lo, and parked in smem. Phase B: each thread assembles the im2col row of its pixel from 9*CIN LDS.
+        const int m = threadIdx.x;  // 0..127, tile row = m / 16, tile column = m % 16
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        constexpr int PLANE = SM_IN_ROWS * SM_IN_PITCH;
+        constexpr int IN_ELEMS = CIN * SM_IN_ROWS * SM_IN_COLS;
+        constexpr int NLOAD = (IN_ELEMS + 127) / 128;
+        // raw input values of the NEXT tile travel in registers while the current tile is assembled: the global-load
+        // latency (the stall that dominated the first version of this kernel) overlaps phase B.
+        uint32_t raw[NLOAD];
+        auto fetch = [&](int tile_idx) {
+            const int img = tile_idx / per_img;
+            const int r = tile_idx - img * per_img;
+            const int y0 = (r / p.tiles_x) * TILE_H, x0 = (r % p.tiles_x) * TILE_W;
+#pragma unroll
+            for (int k = 0; k < NLOAD; ++k) {
+                const int i = m + 128 * k;
+                uint32_t v = U8 ? 256u : 0u;  // out of bounds -> zero padding (LUT slot 256 / +0.0f)
+                if (i < IN_ELEMS) {
+                    const int c = i / (SM_IN_ROWS * SM_IN_COLS);
+                    const int rr = (i - c * SM_IN_ROWS * SM_IN_COLS) / SM_IN_COLS;
+                    const int col = i - c * SM_IN_ROWS * SM_IN_COLS - rr * SM_IN_COLS;
+                    const int yy = y0 + rr - 1, xx = x0 + col - 1;
+                    if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+                        const bool first = c < p.src[0].channels;
+                        const PlaneSrc& sp = first ? p.src[0] : p.src[1];
+                        const int cc = first ? c : c - p.src[0].channels;
+                        const long long off = img * sp.batch_stride + cc * sp.chan_stride + yy * sp.row_stride +
+                                              xx * sp.px_stride;
+                        if (U8) v = __ldg(static_cast<const uint8_t*>(sp.ptr) + off);
+                        else v = __float_as_uint(__ldg(static_cast<const float*>(sp.ptr) + off));
+                    }
+                }
+                raw[k] = v;
+            }
+        };
+        if (static_cast<int>(blockIdx.x) < total_tiles) fetch(blockIdx.x);
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            uint32_t* tile = in_tile + (it & 1) * CIN * PLANE;
+#pragma unroll
+            for (int k = 0; k < NLOAD; ++k) {
+                const int i = m + 128 * k;
+                if (i < IN_ELEMS) {
+                    const int c = i / (SM_IN_ROWS * SM_IN_COLS);
+                    const int rr = (i - c * SM_IN_ROWS * SM_IN_COLS) / SM_IN_COLS;
+                    const int col = i - c * SM_IN_ROWS * SM_IN_COLS - rr * SM_IN_COLS;
+                    uint32_t packed;
+                    if (U8) {
+                        packed = lut[raw[k]];
+                    } else {
+                        const float v = __uint_as_float(raw[k]);
+                        const uint32_t h = bf16_bits(v);
+                        packed = (h >> 16) | bf16_bits(v - __uint_as_float(h));
+                    }
+                    tile[c * PLANE + rr * SM_IN_PITCH + col] = packed;
+                }
+            }
+            if (t + static_cast<int>(gridDim.x) < total_tiles) fetch(t + gridDim.x);
+            // one barrier per tile is enough with two buffers: a thread re-writes buffer b only after every producer
+            // passed the barrier of the tile in between, i.e. after they all finished reading b
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            uint32_t hl[KT];  // low half = bf16 hi part, high half = bf16 lo part
+            const uint32_t* px = tile + (m >> 4) * SM_IN_PITCH + (m & 15);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+                for (int c = 0; c < CIN; ++c)
+                    hl[tap * CIN + c] = px[c * PLANE + (tap / 3) * SM_IN_PITCH + (tap % 3)];
+            auto elem = [&](int e) -> uint32_t {  // 16-bit K element e of the row [x_hi | x_hi | x_lo | 0]
+                return e < KT ? (hl[e] & 0xffffu)
+                              : (e < 2 * KT ? (hl[e - KT] & 0xffffu) : (e < 3 * KT ? (hl[e - 2 * KT] >> 16) : 0u));
+            };
+#pragma unroll
+            for (int s = 0; s < SLABS; ++s) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                const uint32_t row = smem_a + stage * SM_A_BYTES + m * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t wv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int e = s * 64 + j * 8 + q * 2;
+                        wv[q] = elem(e) | (elem(e + 1) << 16);
+                    }
+                    st_shared_v4(row + ((j ^ (m & 7)) << 4), wv[0], wv[1], wv[2], wv[3]);
+                }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+                if (++stage == SM_A_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ------------------------------------------------------------ weights (once) + MMA issue
+        if (elect_one()) {
+            mbar_expect_tx(bar_bres, SLABS * 8192);
+            for (int s = 0; s < SLABS; ++s) tma_load_2d(smem_b + s * 8192, &map_b, bar_bres, s * 64, 0);
+        }
+        __syncwarp();
+        mbar_wait(bar_bres, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int acc = it & 1;
+            mbar_wait(bar_tempty + 8 * acc, ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 64;
+            for (int s = 0; s < SLABS; ++s) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                const uint64_t da = umma_desc_sw128(smem_a + stage * SM_A_BYTES);
+                const uint64_t db = umma_desc_sw128(smem_b + s * 8192);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, IDESC, (s | k) != 0);
+                    umma_commit(bar_empty + 8 * stage);
+                    if (s == SLABS - 1) umma_commit(bar_tfull + 8 * acc);
+                }
+                __syncwarp();
+                if (++stage == SM_A_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps 5..8
+        const int q = warp & 3;
+        const uint32_t my_stage = smem_stage + q * 8192;
+        int buf = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int img = t / per_img;
+            const int r = t - img * per_img;
+            const int y0 = (r / p.tiles_x) * TILE_H, x0 = (r % p.tiles_x) * TILE_W;
+            const int acc = it & 1;
+            mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 64;
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32b_x32(taddr, v0);
+            tmem_ld_32x32b_x32(taddr + 32, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) mbar_arrive(bar_tempty + 8 * acc);  // accumulator is in registers: release it early
+            const float4* bias4 = reinterpret_cast<const float4*>(p.bias);
+            uint32_t pk[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(bias4 + j);
+                pk[2 * j] = pack_bf16x2(fmaxf(__uint_as_float(v0[4 * j]) + b.x, 0.f),
+                                        fmaxf(__uint_as_float(v0[4 * j + 1]) + b.y, 0.f));
+                pk[2 * j + 1] = pack_bf16x2(fmaxf(__uint_as_float(v0[4 * j + 2]) + b.z, 0.f),
+                                            fmaxf(__uint_as_float(v0[4 * j + 3]) + b.w, 0.f));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(bias4 + 8 + j);
+                pk[16 + 2 * j] = pack_bf16x2(fmaxf(__uint_as_float(v1[4 * j]) + b.x, 0.f),
+                                             fmaxf(__uint_as_float(v1[4 * j + 1]) + b.y, 0.f));
+                pk[16 + 2 * j + 1] = pack_bf16x2(fmaxf(__uint_as_float(v1[4 * j + 2]) + b.z, 0.f),
+                                                 fmaxf(__uint_as_float(v1[4 * j + 3]) + b.w, 0.f));
+            }
+            if (elect_one()) tma_store_wait_read<1>();
+            __syncwarp();
+            const uint32_t sbuf = my_stage + buf * 4096;
+            const uint32_t row = sbuf + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                st_shared_v4(row + ((j ^ (lane & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one()) {
+                tma_store_4d(&map_out, sbuf, 0, x0, y0 + 2 * q, img);  // box {64, 16, 2, 1}
+                tma_store_commit();
+            }
+            buf ^= 1;
+        }
+        __syncwarp();
+        if (elect_one()) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int CIN>
+const char* launch_stem(const StemDesc& d, const CUtensorMap& map_b, const CUtensorMap& map_out, const StemParams& p,
+                        int grid, cudaStream_t stream) {
+    constexpr int smem = stem_smem_bytes(CIN);
+    static bool configured[2] = {false, false};
+    if (d.is_u8) {
+        auto k = stem_mma_kernel<CIN, true>;
+        if (!configured[1]) {
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+                return "stem: cudaFuncSetAttribute failed";
+            configured[1] = true;
+        }
+        k<<<grid, SM_THREADS, smem, stream>>>(map_b, map_out, p);
+    } else {
+        auto k = stem_mma_kernel<CIN, false>;
+        if (!configured[0]) {
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+                return "stem: cudaFuncSetAttribute failed";
+            configured[0] = true;
+        }
+        k<<<grid, SM_THREADS, smem, stream>>>(map_b, map_out, p);
+    }
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+uint16_t host_bf16(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return static_cast<uint16_t>(u >> 16);
+}
+float host_bf16_to_f32(uint16_t h) {
+    const uint32_t u = static_cast<uint32_t>(h) << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+}  // namespace
+
+int stem_packed_k(int cin) { return stem_slabs(cin) * 64; }
+
+void stem_pack_weights(const float* w, int cin, uint16_t* out) {
+    // w: fp32 [64][cin][3][3] (BN already folded); out: bf16 [64][stem_packed_k(cin)] = [w_hi | w_lo | w_hi | 0]
+    const int kt = 9 * cin, kp = stem_packed_k(cin);
+    for (int co = 0; co < 64; ++co) {
+        uint16_t* row = out + static_cast<size_t>(co) * kp;
+        for (int k = 0; k < kp; ++k) row[k] = 0;
+        for (int tap = 0; tap < 9; ++tap)
+            for (int c = 0; c < cin; ++c) {
+                const float v = w[(static_cast<size_t>(co) * cin + c) * 9 + tap];
+                const uint16_t h = host_bf16(v);
+                const uint16_t l = host_bf16(v - host_bf16_to_f32(h));
+                const int k = tap * cin + c;
+                row[k] = h;
+                row[kt + k] = l;
+                row[2 * kt + k] = h;
+            }
+    }
+}
+
+const char* stem_conv_launch(const StemDesc& d, cudaStream_t stream) {
+    if (d.cin < 1 || d.cin > 8) return "stem: 1..8 input channels supported";
+    if (d.src[0].channels + d.src[1].channels != d.cin) return "stem: plane sources do not add up to cin";
+    if (d.N <= 0 || d.H <= 0 || d.W <= 0) return "stem: empty shape";
+    if (!d.wpack || !d.bias || !d.dst || !d.src[0].ptr) return "stem: null operand";
+    StemParams p;
+    memset(&p, 0, sizeof p);
+    p.src[0] = d.src[0];
+    p.src[1] = d.src[1];
+    p.N = d.N;
+    p.H = d.H;
+    p.W = d.W;
+    p.tiles_x = (d.W + TILE_W - 1) / TILE_W;
+    p.tiles_y = (d.H + TILE_H - 1) / TILE_H;
+    p.bias = d.bias;
+    const long long tiles = static_cast<long long>(d.N) * p.tiles_x * p.tiles_y;
+    if (tiles > 0x7fffffffLL) return "stem: too many tiles";
+    alignas(64) CUtensorMap map_b, map_out;
+    const char* e;
+    {
+        const uint64_t kp = stem_packed_k(d.cin);
+        const uint64_t dims[2] = {kp, 64};
+        const uint64_t strides[1] = {kp};
+        const uint32_t box[2] = {64, 64};
+        if ((e = encode_bf16_map_public(&map_b, d.wpack, 2, dims, strides, box))) return e;
+    }
+    {
+        const uint64_t dims[4] = {64, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H),
+                                  static_cast<uint64_t>(d.N)};
+        const uint64_t strides[3] = {64, static_cast<uint64_t>(d.W) * 64, static_cast<uint64_t>(d.H) * d.W * 64};
+        const uint32_t box[4] = {64, TILE_W, 2, 1};
+        if ((e = encode_bf16_map_public(&map_out, d.dst, 4, dims, strides, box))) return e;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = static_cast<int>(tiles < 2LL * sms ? tiles : 2LL * sms);
+    switch (d.cin) {
+        case 1: return launch_stem<1>(d, map_b, map_out, p, grid, stream);
+        case 2: return launch_stem<2>(d, map_b, map_out, p, grid, stream);
+        case 3: return launch_stem<3>(d, map_b, map_out, p, grid, stream);
+        case 4: return launch_stem<4>(d, map_b, map_out, p, grid, stream);
+        case 5: return launch_stem<5>(d, map_b, map_out, p, grid, stream);
+        case 6: return launch_stem<6>(d, map_b, map_out, p, grid, stream);
+        case 7: return launch_stem<7>(d, map_b, map_out, p, grid, stream);
+        default: return launch_stem<8>(d, map_b, map_out, p, grid, stream);
+    }
+}
+
+}  // namespace fi

@@ -59,6 +59,8 @@ _SIGNATURES = {
     "fiNetReadActivation": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int),
                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fiConvGemm": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "fiStemPackedK": (C.c_int, [C.c_int]),
+    "fiStemPackWeights": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "fiStemConv": (C.c_int, [C.POINTER(Planes), C.POINTER(Planes), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fiUpsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

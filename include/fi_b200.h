@@ -136,9 +136,12 @@ typedef struct fiConvDesc {
 
 int fiConvGemm(const fiConvDesc* desc, void* stream);
 
-/* inc.double_conv.0..2 (model/unet.py:12-14) on raw planes: w fp32 [9][cin][64] (BN folded), bias fp32 [64],
- * dst bf16 NHWC [N,H,W,64]. */
-int fiStemConv(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const float* w, const float* bias, void* dst,
+/* inc.double_conv.0..2 (model/unet.py:12-14) on raw planes, computed on the tensor cores with bf16 hi/lo operand
+ * splitting (fp32-grade result). wpack: DEVICE bf16 [64][fiStemPackedK(cin)] produced on the host by
+ * fiStemPackWeights from the BN-folded fp32 weight [64][cin][3][3]; bias fp32 [64]; dst bf16 NHWC [N,H,W,64]. */
+int fiStemPackedK(int cin);
+int fiStemPackWeights(const float* w_host, int cin, uint16_t* out_host);
+int fiStemConv(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const void* wpack, const float* bias, void* dst,
                int N, int H, int W, void* stream);
 /* nn.Upsample(scale_factor=2, bilinear, align_corners=True) (model/unet.py:40): bf16 NHWC [N,h,w,C] -> [N,2h,2w,C]. */
 int fiUpsample2x(const void* src, void* dst, int N, int h, int w, int C, void* stream);
