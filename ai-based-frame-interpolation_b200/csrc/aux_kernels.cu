@@ -7,39 +7,48 @@ namespace fi {
 
 namespace {
 
-__device__ __forceinline__ float norm_u8(uint8_t u) {
-    // image.astype(float32)/255.0 then 2.0*image-1.0, each rounded to fp32 (reference model/inference.py:32-35)
-    return __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(static_cast<float>(u), 255.0f)), 1.0f);
+__device__ __forceinline__ float norm_u8(uint32_t u) {
+    // image.astype(float32)/255.0 then 2.0*image-1.0, each rounded to fp32 (reference model/inference.py:32-35).
+    // u/255 is formed as u*(1/255) plus one FMA residual correction, which is the correctly rounded quotient for all
+    // 256 inputs (checked exhaustively by tests/test_gpu_aux_kernels.py::test_pack_pair_bit_exact) at a third of the
+    // instruction count of an IEEE division.
+    const float x = static_cast<float>(u);
+    const float r = 1.0f / 255.0f;
+    const float q = __fmul_rn(x, r);
+    const float q2 = __fmaf_rn(__fmaf_rn(-q, 255.0f, x), r, q);
+    return __fmaf_rn(2.0f, q2, -1.0f);  // 2*q2 is exact, so this is fl(2*q2 - 1)
 }
 
 // ------------------------------------------------------------------------------------------------ bilinear x2
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// One block row = one output row (blockIdx.y = n*2h + oy): the vertical taps/weights are block-uniform, index math is
+// 32-bit, and consecutive threads walk (ox, channel-group) so both the 16-byte gathers and the store are coalesced.
 __global__ void __launch_bounds__(256)
-upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int h, int w, int c8) {
+upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int h, int w, int c8) {
     const int oh = 2 * h, ow = 2 * w;
-    const size_t total = static_cast<size_t>(N) * oh * ow * c8;
+    const int n = blockIdx.y / oh, oy = blockIdx.y - n * oh;
     const float rh = oh > 1 ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.f;
     const float rw = ow > 1 ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) : 0.f;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int cg = static_cast<int>(i % c8);
-        size_t r = i / c8;
-        const int ox = static_cast<int>(r % ow);
-        r /= ow;
-        const int oy = static_cast<int>(r % oh);
-        const int n = static_cast<int>(r / oh);
-        const float fy = rh * oy, fx = rw * ox;
-        const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-        const float ly = fy - y0, lx = fx - x0;
-        const float hy = 1.f - ly, hx = 1.f - lx;
-        const size_t base = static_cast<size_t>(n) * h * w;
-        const uint4 p00 = __ldg(src + (base + static_cast<size_t>(y0) * w + x0) * c8 + cg);
-        const uint4 p01 = __ldg(src + (base + static_cast<size_t>(y0) * w + x1) * c8 + cg);
-        const uint4 p10 = __ldg(src + (base + static_cast<size_t>(y1) * w + x0) * c8 + cg);
-        const uint4 p11 = __ldg(src + (base + static_cast<size_t>(y1) * w + x1) * c8 + cg);
+    const float fy = rh * oy;
+    const int y0 = static_cast<int>(fy);
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+    const float ly = fy - y0, hy = 1.f - ly;
+    const uint4* row0 = src + (static_cast<size_t>(n) * h + y0) * w * c8;
+    const uint4* row1 = src + (static_cast<size_t>(n) * h + y1) * w * c8;
+    uint4* out = dst + (static_cast<size_t>(n) * oh + oy) * ow * c8;
+    const int items = ow * c8;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < items; i += gridDim.x * 256) {
+        const int ox = i / c8, cg = i - ox * c8;
+        const float fx = rw * ox;
+        const int x0 = static_cast<int>(fx);
+        const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float lx = fx - x0, hx = 1.f - lx;
+        const uint4 p00 = __ldg(row0 + x0 * c8 + cg);
+        const uint4 p01 = __ldg(row0 + x1 * c8 + cg);
+        const uint4 p10 = __ldg(row1 + x0 * c8 + cg);
+        const uint4 p11 = __ldg(row1 + x1 * c8 + cg);
         const uint32_t a[4] = {p00.x, p00.y, p00.z, p00.w}, b[4] = {p01.x, p01.y, p01.z, p01.w};
         const uint32_t c[4] = {p10.x, p10.y, p10.z, p10.w}, e[4] = {p11.x, p11.y, p11.z, p11.w};
         uint32_t o[4];
@@ -49,7 +58,7 @@ upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N,
             const float hi = hy * (hx * bf_hi(a[k]) + lx * bf_hi(b[k])) + ly * (hx * bf_hi(c[k]) + lx * bf_hi(e[k]));
             o[k] = pack_bf16x2(lo, hi);
         }
-        dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        out[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -143,7 +152,7 @@ __device__ __forceinline__ uint32_t load_word_guarded(const uint8_t* rowp, int c
     return v;
 }
 
-__global__ void __launch_bounds__(SS_THREADS)
+__global__ void __launch_bounds__(SS_THREADS, 4)
 ssim_psnr_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int H, int W, int aligned,
                  double* __restrict__ part_ssim, unsigned long long* __restrict__ part_ssd) {
     const int tid = threadIdx.x;
@@ -165,49 +174,50 @@ ssim_psnr_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, i
     const float K1 = 6.5025f * 2401.0f;   // C1 * 49^2
     const float K2 = 58.5225f * 2352.0f;  // C2 * 48 * 49
 
+    // The six words of row i+1 are requested before row i is reduced, so their latency overlaps the arithmetic.
+    uint32_t na[3], nb[3];
+    auto fetch_row = [&](int yin) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) na[k] = nb[k] = 0;
+        if (yin >= 0 && yin < H && xb - 4 < W) {
+            const uint8_t* ra = ia + static_cast<size_t>(yin) * W;
+            const uint8_t* rbp = ib + static_cast<size_t>(yin) * W;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                na[k] = load_word_guarded(ra, xb - 4 + 4 * k, W, aligned);
+                nb[k] = load_word_guarded(rbp, xb - 4 + 4 * k, W, aligned);
+            }
+        }
+    };
+    fetch_row(ty0 - 3);
     for (int rb = 0; rb < SS_ROWS + 6; rb += 7) {
 #pragma unroll
         for (int s = 0; s < 7; ++s) {
             const int i = rb + s;
             if (i < SS_ROWS + 6) {
                 const int yin = ty0 - 3 + i;
-                uint32_t wa[3] = {0, 0, 0}, wb[3] = {0, 0, 0};
-                if (yin >= 0 && yin < H && xb - 4 < W) {
-                    const uint8_t* ra = ia + static_cast<size_t>(yin) * W;
-                    const uint8_t* rbp = ib + static_cast<size_t>(yin) * W;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        wa[k] = load_word_guarded(ra, xb - 4 + 4 * k, W, aligned);
-                        wb[k] = load_word_guarded(rbp, xb - 4 + 4 * k, W, aligned);
-                    }
-                }
-                // pixels xb-3 .. xb+6 = bytes 1..10 of the 12-byte span
-                uint32_t p1[10], pq[10], pp[10];
-#pragma unroll
-                for (int k = 0; k < 10; ++k) {
-                    const int byte = k + 1;
-                    const uint32_t pa = (wa[byte >> 2] >> (8 * (byte & 3))) & 0xff;
-                    const uint32_t pb = (wb[byte >> 2] >> (8 * (byte & 3))) & 0xff;
-                    p1[k] = pa | (pb << 16);
-                    pq[k] = pa * pa + pb * pb;
-                    pp[k] = pa * pb;
-                }
-                if (yin >= ty0 && yin < ty0 + SS_ROWS) {  // squared error of the owned pixels (zero outside the image)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int dlt = static_cast<int>(p1[3 + j] & 0xffff) - static_cast<int>(p1[3 + j] >> 16);
-                        ssd += static_cast<uint32_t>(dlt * dlt);
-                    }
-                }
+                const uint32_t wa[3] = {na[0], na[1], na[2]}, wb[3] = {nb[0], nb[1], nb[2]};
+                if (i + 1 < SS_ROWS + 6) fetch_row(yin + 1);
+                // Pixels xb-3 .. xb+6 are bytes 1..10 of the 12-byte span {w0,w1,w2}; the 7-pixel window of owned column j
+                // is bytes j+1 .. j+7. Two funnel shifts align it into (4 bytes, 3 bytes) and __dp4a forms the five
+                // window sums directly on packed bytes (no per-pixel unpack / multiply):
                 uint32_t h1[4], hq[4], hp[4];
-                h1[0] = p1[0] + p1[1] + p1[2] + p1[3] + p1[4] + p1[5] + p1[6];
-                hq[0] = pq[0] + pq[1] + pq[2] + pq[3] + pq[4] + pq[5] + pq[6];
-                hp[0] = pp[0] + pp[1] + pp[2] + pp[3] + pp[4] + pp[5] + pp[6];
 #pragma unroll
-                for (int j = 1; j < 4; ++j) {
-                    h1[j] = h1[j - 1] + p1[j + 6] - p1[j - 1];
-                    hq[j] = hq[j - 1] + pq[j + 6] - pq[j - 1];
-                    hp[j] = hp[j - 1] + pp[j + 6] - pp[j - 1];
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t sh = 8 * (j + 1);
+                    const uint32_t xa = j < 3 ? __funnelshift_r(wa[0], wa[1], sh) : wa[1];
+                    const uint32_t xb2 = (j < 3 ? __funnelshift_r(wa[1], wa[2], sh) : wa[2]) & 0x00ffffffu;
+                    const uint32_t ya = j < 3 ? __funnelshift_r(wb[0], wb[1], sh) : wb[1];
+                    const uint32_t yb2 = (j < 3 ? __funnelshift_r(wb[1], wb[2], sh) : wb[2]) & 0x00ffffffu;
+                    const uint32_t sx = __dp4a(xa, 0x01010101u, __dp4a(xb2, 0x01010101u, 0u));
+                    const uint32_t sy = __dp4a(ya, 0x01010101u, __dp4a(yb2, 0x01010101u, 0u));
+                    h1[j] = sx | (sy << 16);  // each <= 7*255: the two 16-bit halves never interact
+                    hq[j] = __dp4a(xa, xa, __dp4a(xb2, xb2, __dp4a(ya, ya, __dp4a(yb2, yb2, 0u))));
+                    hp[j] = __dp4a(xa, ya, __dp4a(xb2, yb2, 0u));
+                }
+                if (yin >= ty0 && yin < ty0 + SS_ROWS) {
+                    // squared error of the 4 owned pixels (= bytes of w1): sum (x-y)^2 = x.x + y.y - 2 x.y
+                    ssd += __dp4a(wa[1], wa[1], __dp4a(wb[1], wb[1], 0u)) - 2u * __dp4a(wa[1], wb[1], 0u);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -231,7 +241,7 @@ ssim_psnr_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, i
                             const float b1 = static_cast<float>(sq2) + K1;
                             const float a2 = static_cast<float>(2 * (49 * static_cast<int>(vp[j]) - sxsy)) + K2;
                             const float b2 = static_cast<float>(49 * static_cast<int>(vq[j]) - sq2) + K2;
-                            ssim_acc += (a1 * a2) / (b1 * b2);
+                            ssim_acc += __fdividef(a1 * a2, b1 * b2);  // |S| <= 1, operands ~1e17: well inside range
                         }
                     }
                 }
@@ -315,9 +325,11 @@ const char* last_launch_error() {
 const char* upsample2x_launch(const void* src, void* dst, int N, int h, int w, int C, cudaStream_t stream) {
     if (C % 8) return "upsample: channels must be a multiple of 8";
     if (N <= 0 || h <= 0 || w <= 0) return "upsample: empty shape";
-    const size_t total = static_cast<size_t>(N) * 4 * h * w * (C / 8);
-    upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(src),
-                                                                 static_cast<uint4*>(dst), N, h, w, C / 8);
+    if (static_cast<long long>(N) * 2 * h > 65535) return "upsample: N*2h must be <= 65535 (grid.y)";
+    const int items = 2 * w * (C / 8);
+    const int gx = (items + 1023) / 1024;  // 4 items per thread
+    upsample2x_kernel<<<dim3(gx, N * 2 * h), 256, 0, stream>>>(static_cast<const uint4*>(src),
+                                                                static_cast<uint4*>(dst), h, w, C / 8);
     return last_launch_error();
 }
 

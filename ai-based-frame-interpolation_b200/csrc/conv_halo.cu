@@ -223,10 +223,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                             umma_desc_sw128(smem_b + (RESIDENT ? tap : b_stage) * B_STAGE_BYTES);
                         const uint64_t da0 = halo_desc(a_base + (dy * HALO_W + dx) * 128, p.desc_mode ? dx : 0);
                         if (elect_one()) {
+                            // The two column halves are independent accumulators: alternating them keeps back-to-back
+                            // tcgen05.mma from serialising on the same TMEM tile.
 #pragma unroll
-                            for (int half = 0; half < 2; ++half) {
+                            for (int k = 0; k < BLOCK_K / 16; ++k) {
 #pragma unroll
-                                for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                for (int half = 0; half < 2; ++half) {
                                     // +8 pixels (1024 B) per column half, +32 B per K step, in 16-byte units
                                     umma_bf16_ss(d_tmem + half * COUT, da0 + 64 * half + 2 * k, db + 2 * k, IDESC,
                                                  (s | tap | k) != 0);

@@ -16,6 +16,9 @@ pytestmark = pytest.mark.gpu
 
 def test_pack_pair_bit_exact(cuda_device):
     g = torch.Generator().manual_seed(0)
+    allv = torch.arange(256, dtype=torch.uint8).view(1, 1, 16, 16)  # every input value, exhaustively
+    got = E.pack_pair_u8(allv.to(cuda_device), allv.flip(3).to(cuda_device)).cpu()
+    assert torch.equal(got, torch.cat([O.preprocess_u8(allv.numpy()), O.preprocess_u8(allv.flip(3).numpy())], 1))
     for shape in [(2, 1, 32, 48), (1, 3, 17, 19), (1, 1, 1080, 1920)]:
         f1 = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8)
         f2 = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8)
