@@ -263,8 +263,16 @@ def main():
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])  # kernels are timed inside a long step
     all_ms = sum(p["ms_total"] for p in prof)
+    traffic = None  # DRAM bytes per conv launch from the committed ncu --set full capture, scaled to this batch
+    tf = ROOT / "profiles" / "ncu_traffic.json"
+    if tf.exists() and not args.bilinear:
+        t = json.loads(tf.read_text())
+        traffic = t["dram_bytes"] / t["pairs"] * B / t["conv_launches"]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak else None, "traffic": None,
+                "frac": achieved / peak if peak else None, "traffic": traffic,
+                "traffic_note": "avg DRAM read+write bytes per tcgen05 conv launch: profiles/ncu_traffic.json "
+                                "(ncu --set full at 1 pair) x pairs_per_step; algorithmic bytes per launch avg = %.3e"
+                                % (sum(p["bytes"] for p in conv) / max(1, len(conv))),
                 "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM), all instantiations",
                 "peak_source": pk_src + ", sustained bf16 cuBLAS figure",
                 "avg_launch_ms": conv_ms / max(1, conv_launches), "launches": conv_launches,
