@@ -2,6 +2,7 @@
 """Builds profiles/README.md and profiles/ncu_traffic.json from the measurement files gathered on the B200 box."""
 import csv
 import json
+import re
 from pathlib import Path
 
 P = Path(__file__).resolve().parent.parent / "profiles"
@@ -52,7 +53,8 @@ def main():
     dram = 0.0
     n_conv = 0
     for i, r in enumerate(ncu[1:]):
-        name = r[ik].split("::")[-1].split("(CUtensorMap")[0]
+        m = re.search(r"(\w+_kernel<[^>]*>)", r[ik])
+        name = m.group(1) if m else r[ik][:60]
         w(f"| {i} | `{name}` | {float(r[it]):.1f} | {float(r[ir]):.1f} | {float(r[iw]):.1f} | {float(r[itn]):.1f} | {float(r[il2]):.1f} |")
         if "stem" not in name:
             dram += (float(r[ir]) + float(r[iw])) * 1e6
