@@ -26,7 +26,8 @@ __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 
 // One block row = one output row (blockIdx.y = n*2h + oy): the vertical taps/weights are block-uniform, index math is
 // 32-bit, and consecutive threads walk (ox, channel-group) so both the 16-byte gathers and the store are coalesced.
 __global__ void __launch_bounds__(256)
-upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int h, int w, int c8) {
+upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int h, int w, int c8,
+                  const uint4* __restrict__ src_lo, uint4* __restrict__ dst_lo) {
     const int oh = 2 * h, ow = 2 * w;
     const int n = blockIdx.y / oh, oy = blockIdx.y - n * oh;
     const float rh = oh > 1 ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.f;
@@ -52,13 +53,36 @@ upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int h,
         const uint32_t a[4] = {p00.x, p00.y, p00.z, p00.w}, b[4] = {p01.x, p01.y, p01.z, p01.w};
         const uint32_t c[4] = {p10.x, p10.y, p10.z, p10.w}, e[4] = {p11.x, p11.y, p11.z, p11.w};
         uint32_t o[4];
+        if (src_lo == nullptr) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float lo = hy * (hx * bf_lo(a[k]) + lx * bf_lo(b[k])) + ly * (hx * bf_lo(c[k]) + lx * bf_lo(e[k]));
-            const float hi = hy * (hx * bf_hi(a[k]) + lx * bf_hi(b[k])) + ly * (hx * bf_hi(c[k]) + lx * bf_hi(e[k]));
-            o[k] = pack_bf16x2(lo, hi);
+            for (int k = 0; k < 4; ++k) {
+                const float lo =
+                    hy * (hx * bf_lo(a[k]) + lx * bf_lo(b[k])) + ly * (hx * bf_lo(c[k]) + lx * bf_lo(e[k]));
+                const float hi =
+                    hy * (hx * bf_hi(a[k]) + lx * bf_hi(b[k])) + ly * (hx * bf_hi(c[k]) + lx * bf_hi(e[k]));
+                o[k] = pack_bf16x2(lo, hi);
+            }
+            out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+            // precise mode: every value is hi + lo (exact in fp32); the result is split again
+            const size_t d0 = (static_cast<size_t>(n) * h + y0) * w * c8, d1 = (static_cast<size_t>(n) * h + y1) * w * c8;
+            const uint4 q00 = __ldg(src_lo + d0 + x0 * c8 + cg), q01 = __ldg(src_lo + d0 + x1 * c8 + cg);
+            const uint4 q10 = __ldg(src_lo + d1 + x0 * c8 + cg), q11 = __ldg(src_lo + d1 + x1 * c8 + cg);
+            const uint32_t al[4] = {q00.x, q00.y, q00.z, q00.w}, bl[4] = {q01.x, q01.y, q01.z, q01.w};
+            const uint32_t cl[4] = {q10.x, q10.y, q10.z, q10.w}, el[4] = {q11.x, q11.y, q11.z, q11.w};
+            uint32_t ol[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float lo = hy * (hx * (bf_lo(a[k]) + bf_lo(al[k])) + lx * (bf_lo(b[k]) + bf_lo(bl[k]))) +
+                                 ly * (hx * (bf_lo(c[k]) + bf_lo(cl[k])) + lx * (bf_lo(e[k]) + bf_lo(el[k])));
+                const float hi = hy * (hx * (bf_hi(a[k]) + bf_hi(al[k])) + lx * (bf_hi(b[k]) + bf_hi(bl[k]))) +
+                                 ly * (hx * (bf_hi(c[k]) + bf_hi(cl[k])) + lx * (bf_hi(e[k]) + bf_hi(el[k])));
+                o[k] = pack_bf16x2(lo, hi);
+                ol[k] = pack_bf16x2(lo - bf_lo(o[k]), hi - bf_hi(o[k]));
+            }
+            out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+            (dst_lo + (static_cast<size_t>(n) * oh + oy) * ow * c8)[i] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
         }
-        out[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -322,14 +346,18 @@ const char* last_launch_error() {
 
 }  // namespace
 
-const char* upsample2x_launch(const void* src, void* dst, int N, int h, int w, int C, cudaStream_t stream) {
+const char* upsample2x_launch(const void* src, void* dst, int N, int h, int w, int C, cudaStream_t stream,
+                              const void* src_lo, void* dst_lo) {
+    if ((src_lo == nullptr) != (dst_lo == nullptr)) return "upsample: src_lo and dst_lo go together";
     if (C % 8) return "upsample: channels must be a multiple of 8";
     if (N <= 0 || h <= 0 || w <= 0) return "upsample: empty shape";
     if (static_cast<long long>(N) * 2 * h > 65535) return "upsample: N*2h must be <= 65535 (grid.y)";
     const int items = 2 * w * (C / 8);
     const int gx = (items + 1023) / 1024;  // 4 items per thread
     upsample2x_kernel<<<dim3(gx, N * 2 * h), 256, 0, stream>>>(static_cast<const uint4*>(src),
-                                                                static_cast<uint4*>(dst), h, w, C / 8);
+                                                                static_cast<uint4*>(dst), h, w, C / 8,
+                                                                static_cast<const uint4*>(src_lo),
+                                                                static_cast<uint4*>(dst_lo));
     return last_launch_error();
 }
 

@@ -22,13 +22,15 @@ struct StemDesc {
     const void* wpack;   // bf16 [64][stem_packed_k(cin)], hi/lo split rows (stem_pack_weights), BN folded
     const float* bias;   // fp32 [64]
     void* dst;           // bf16 NHWC [N,H,W,64]
+    void* dst_lo;        // precise mode: lo halves (value = dst + dst_lo), else null
 };
 const char* stem_conv_launch(const StemDesc& d, cudaStream_t stream);  // stem_mma.cu
 int stem_packed_k(int cin);                                               // packed K length (multiple of 64)
 void stem_pack_weights(const float* w /*[64][cin][3][3]*/, int cin, uint16_t* out /*[64][stem_packed_k]*/);
 
 // nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) on bf16 NHWC (reference unet.py:40).
-const char* upsample2x_launch(const void* src, void* dst, int N, int h, int w, int C, cudaStream_t stream);
+const char* upsample2x_launch(const void* src, void* dst, int N, int h, int w, int C, cudaStream_t stream,
+                              const void* src_lo = nullptr, void* dst_lo = nullptr);  // lo halves: precise mode
 
 // Frame-pair packing + normalisation: two u8 planar frame batches [N,C,H,W] -> fp32 NCHW [N,2C,H,W] = cat(2*f/255-1).
 const char* pack_pair_launch(const uint8_t* f0, const uint8_t* f1, float* out, int N, int C, int H, int W,

@@ -61,11 +61,9 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const ConvKernelParams& 
     return c;
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
-                 const __grid_constant__ CUtensorMap map_pool, const ConvKernelParams p) {
+conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p) {
     constexpr int STAGES = num_stages(BLOCK_N);
     constexpr int B_STAGE_BYTES = b_stage_bytes(BLOCK_N);
     constexpr uint32_t STAGE_TX = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -91,11 +89,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&map_a0);
-        tma_prefetch_desc(&map_a1);
-        tma_prefetch_desc(&map_b);
-        if (MODE != EPI_HEAD) tma_prefetch_desc(&map_out);
-        if (MODE == EPI_STORE_POOL) tma_prefetch_desc(&map_pool);
+        tma_prefetch_desc(&maps.a[0]);
+        tma_prefetch_desc(&maps.a[2]);
+        tma_prefetch_desc(&maps.b);
+        if (MODE != EPI_HEAD) tma_prefetch_desc(&maps.out[0]);
+        if (MODE == EPI_STORE_POOL) tma_prefetch_desc(&maps.pool[0]);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
@@ -113,7 +111,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     const int total_tiles = p.n_blocks * p.n_img * p.tiles_y * p.tiles_x;
-    const int slabs = p.slabs0 + p.slabs1;
+    const int slabs = p.slabs;
     const int k_iters = p.taps * slabs;
 
     if (warp == 0) {
@@ -126,19 +124,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                 for (int tap = 0; tap < p.taps; ++tap) {
                     const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
                     const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+                    int seg = 0, left = p.seg_slabs[0];
                     for (int s = 0; s < slabs; ++s) {
+                        while (left == 0) left = p.seg_slabs[++seg];  // K segment (source tensor) of this slab
+                        const int local = p.seg_slabs[seg] - left;
+                        --left;
+                        const int mid = p.seg_map[seg];
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t full = bar_full + 8 * stage;
                         if (elect_one()) {
                             mbar_expect_tx(full, STAGE_TX);
-                            if (s < p.slabs0) {
-                                tma_load_4d(smem_a + stage * A_STAGE_BYTES, &map_a0, full, s * BLOCK_K, tc.x0 + dx,
-                                            tc.y0 + dy, tc.img);
-                            } else {
-                                tma_load_4d(smem_a + stage * A_STAGE_BYTES, &map_a1, full, (s - p.slabs0) * BLOCK_K,
-                                            tc.x0 + dx - p.off_x, tc.y0 + dy - p.off_y, tc.img);
-                            }
-                            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full, (tap * slabs + s) * BLOCK_K,
+                            const int ox = mid >= 2 ? p.off_x : 0, oy = mid >= 2 ? p.off_y : 0;  // F.pad of src1
+                            tma_load_4d(smem_a + stage * A_STAGE_BYTES, &maps.a[mid], full, local * BLOCK_K,
+                                        tc.x0 + dx - ox, tc.y0 + dy - oy, tc.img);
+                            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &maps.b, full, (tap * slabs + s) * BLOCK_K,
                                         tc.nb * BLOCK_N);
                         }
                         __syncwarp();
@@ -256,7 +255,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                             }
                         }
                     }
-                } else {
+                } else if constexpr (!SPLIT) {
                     uint32_t pk[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
@@ -275,9 +274,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     if (elect_one()) {
                         if constexpr (MODE == EPI_CONVT) {
                             const int a = n_glob / p.cout2;
-                            tma_store_5d(&map_out, sbuf, n_glob - a * p.cout2, tc.x0, a, tc.y0 + 2 * q, tc.img);
+                            tma_store_5d(&maps.out[0], sbuf, n_glob - a * p.cout2, tc.x0, a, tc.y0 + 2 * q, tc.img);
                         } else {
-                            tma_store_4d(&map_out, sbuf, n_glob, tc.x0, tc.y0 + 2 * q, tc.img);
+                            tma_store_4d(&maps.out[0], sbuf, n_glob, tc.x0, tc.y0 + 2 * q, tc.img);
                         }
                     }
                     if constexpr (MODE == EPI_STORE_POOL) {
@@ -302,11 +301,57 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (elect_one()) {
-                            tma_store_4d(&map_pool, pbuf, n_glob, tc.x0 >> 1, (tc.y0 >> 1) + q, tc.img);
+                            tma_store_4d(&maps.pool[0], pbuf, n_glob, tc.x0 >> 1, (tc.y0 >> 1) + q, tc.img);
                         }
                     }
                     if (elect_one()) tma_store_commit();
                     buf ^= 1;
+                } else {
+                    // precise mode: value = hi + lo, both bf16; the two staging buffers hold the hi and the lo tile
+                    uint32_t pk[32], pl[32];
+                    split_hi_lo(f, pk, pl);
+                    if (elect_one()) tma_store_wait_read<0>();
+                    __syncwarp();
+                    const uint32_t shi = my_stage, slo = my_stage + 4096;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t o = lane * 128 + ((j ^ (lane & 7)) << 4);
+                        st_shared_v4(shi + o, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        st_shared_v4(slo + o, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (elect_one()) {
+                        if constexpr (MODE == EPI_CONVT) {
+                            const int a = n_glob / p.cout2;
+                            tma_store_5d(&maps.out[0], shi, n_glob - a * p.cout2, tc.x0, a, tc.y0 + 2 * q, tc.img);
+                            tma_store_5d(&maps.out[1], slo, n_glob - a * p.cout2, tc.x0, a, tc.y0 + 2 * q, tc.img);
+                        } else {
+                            tma_store_4d(&maps.out[0], shi, n_glob, tc.x0, tc.y0 + 2 * q, tc.img);
+                            tma_store_4d(&maps.out[1], slo, n_glob, tc.x0, tc.y0 + 2 * q, tc.img);
+                        }
+                    }
+                    if constexpr (MODE == EPI_STORE_POOL) {
+                        const uint32_t phi = my_pool, plo = my_pool + 1024;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int pp = lane >> 2;
+                            const int j = (lane & 3) * 2 + i;
+                            const int rows[4] = {2 * pp, 2 * pp + 1, 16 + 2 * pp, 17 + 2 * pp};
+                            uint4 mh, ml;
+                            pool4_hi_lo(shi, slo, rows, j, mh, ml);
+                            const uint32_t o = pp * 128 + ((j ^ (pp & 7)) << 4);
+                            st_shared_v4(phi + o, mh.x, mh.y, mh.z, mh.w);
+                            st_shared_v4(plo + o, ml.x, ml.y, ml.z, ml.w);
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (elect_one()) {
+                            tma_store_4d(&maps.pool[0], phi, n_glob, tc.x0 >> 1, (tc.y0 >> 1) + q, tc.img);
+                            tma_store_4d(&maps.pool[1], plo, n_glob, tc.x0 >> 1, (tc.y0 >> 1) + q, tc.img);
+                        }
+                    }
+                    if (elect_one()) tma_store_commit();
                 }
             }
             // All TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back to the MMA warp.
@@ -380,9 +425,12 @@ const char* encode_nhwc(CUtensorMap* map, const void* base, int n, int h, int w,
     return encode_bf16_map(map, base, 4, dims, strides, box);
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool SPLIT = false>
 const char* launch_inst(const ConvLaunch& l, cudaStream_t stream) {
-    auto kfn = conv_gemm_kernel<BLOCK_N, MODE>;
+    if constexpr (!SPLIT && MODE != EPI_HEAD) {
+        if (l.split) return launch_inst<BLOCK_N, MODE, true>(l, stream);
+    }
+    auto kfn = conv_gemm_kernel<BLOCK_N, MODE, SPLIT>;
     static bool configured = false;  // per instantiation; attribute is per-device-context but idempotent to set
     constexpr int smem = smem_bytes(BLOCK_N);
     if (!configured) {
@@ -390,7 +438,7 @@ const char* launch_inst(const ConvLaunch& l, cudaStream_t stream) {
             return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
         configured = true;
     }
-    kfn<<<l.grid, NUM_THREADS, smem, stream>>>(l.map_a0, l.map_a1, l.map_b, l.map_out, l.map_pool, l.p);
+    kfn<<<l.grid, NUM_THREADS, smem, stream>>>(l.maps, l.p);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -410,6 +458,8 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     if (d.c1 > 0 && !d.src1) return "conv: src1 missing";
     if (!d.src0 || !d.wpack || !d.bias) return "conv: null operand";
     if (d.n_total % 64) return "conv: n_total must be a multiple of 64";
+    const bool precise = d.precise != 0;
+    if (precise && (!d.src0_lo || (d.c1 > 0 && !d.src1_lo))) return "conv: precise mode needs the lo source tensors";
     int block_n = d.n_total % 256 == 0 ? 256 : (d.n_total % 128 == 0 ? 128 : 64);
     if (d.mode == EPI_HEAD) {
         if (d.n_total != 64) return "conv: head epilogue needs exactly 64 GEMM columns";
@@ -426,6 +476,8 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     } else {
         return "conv: unknown epilogue mode";
     }
+    if (precise && d.mode != EPI_HEAD && (!d.dst_lo || (d.mode == EPI_STORE_POOL && !d.dst_pool_lo)))
+        return "conv: precise mode needs the lo destination tensors";
 
     ConvLaunch l;
     memset(&l, 0, sizeof l);
@@ -441,25 +493,32 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
         tile_w = tile_h = t;
         block_n = d.n_total;
     }
-    if ((e = encode_nhwc(&l.map_a0, d.src0, d.N, d.H, d.W, d.c0, box_w, box_h))) return e;
+    ConvMaps& m = l.maps;
+    if ((e = encode_nhwc(&m.a[0], d.src0, d.N, d.H, d.W, d.c0, box_w, box_h))) return e;
+    m.a[1] = m.a[2] = m.a[3] = m.a[0];
+    if (precise && (e = encode_nhwc(&m.a[1], d.src0_lo, d.N, d.H, d.W, d.c0, box_w, box_h))) return e;
     if (d.c1 > 0) {
-        if ((e = encode_nhwc(&l.map_a1, d.src1, d.N, d.h1, d.w1, d.c1, box_w, box_h))) return e;
-    } else {
-        l.map_a1 = l.map_a0;
+        if ((e = encode_nhwc(&m.a[2], d.src1, d.N, d.h1, d.w1, d.c1, box_w, box_h))) return e;
+        m.a[3] = m.a[2];
+        if (precise && (e = encode_nhwc(&m.a[3], d.src1_lo, d.N, d.h1, d.w1, d.c1, box_w, box_h))) return e;
     }
+    const int kmul = precise ? 3 : 1;
     {
-        const uint64_t k_total = static_cast<uint64_t>(d.taps) * (d.c0 + d.c1);
+        const uint64_t k_total = static_cast<uint64_t>(d.taps) * kmul * (d.c0 + d.c1);
         const uint64_t dims[2] = {k_total, static_cast<uint64_t>(d.n_total)};
         const uint64_t strides[1] = {k_total};
         const uint32_t box[2] = {64, static_cast<uint32_t>(block_n)};
-        if ((e = encode_bf16_map(&l.map_b, d.wpack, 2, dims, strides, box))) return e;
+        if ((e = encode_bf16_map(&m.b, d.wpack, 2, dims, strides, box))) return e;
     }
-    l.map_out = l.map_a0;
-    l.map_pool = l.map_a0;
+    m.out[0] = m.out[1] = m.pool[0] = m.pool[1] = m.a[0];
     if (d.mode == EPI_STORE || d.mode == EPI_STORE_POOL) {
-        if ((e = encode_nhwc(&l.map_out, d.dst, d.N, d.H, d.W, d.n_total, out_w, out_h))) return e;
+        if ((e = encode_nhwc(&m.out[0], d.dst, d.N, d.H, d.W, d.n_total, out_w, out_h))) return e;
+        if (precise && (e = encode_nhwc(&m.out[1], d.dst_lo, d.N, d.H, d.W, d.n_total, out_w, out_h))) return e;
         if (d.mode == EPI_STORE_POOL) {
-            if ((e = encode_nhwc(&l.map_pool, d.dst_pool, d.N, d.H / 2, d.W / 2, d.n_total, pool_w, pool_h))) return e;
+            if ((e = encode_nhwc(&m.pool[0], d.dst_pool, d.N, d.H / 2, d.W / 2, d.n_total, pool_w, pool_h))) return e;
+            if (precise &&
+                (e = encode_nhwc(&m.pool[1], d.dst_pool_lo, d.N, d.H / 2, d.W / 2, d.n_total, pool_w, pool_h)))
+                return e;
         }
     } else if (d.mode == EPI_CONVT) {
         // dst [N, 2H, 2W, Cout] viewed as (b*Cout+co : 2Cout, j : W, a : 2, i : H, n : N)
@@ -470,7 +529,8 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
                                      4 * static_cast<uint64_t>(d.W) * cout,
                                      4 * static_cast<uint64_t>(d.H) * d.W * cout};
         const uint32_t box[5] = {64, TILE_W, 1, 2, 1};
-        if ((e = encode_bf16_map(&l.map_out, d.dst, 5, dims, strides, box))) return e;
+        if ((e = encode_bf16_map(&m.out[0], d.dst, 5, dims, strides, box))) return e;
+        if (precise && (e = encode_bf16_map(&m.out[1], d.dst_lo, 5, dims, strides, box))) return e;
     }
 
     ConvKernelParams& p = l.p;
@@ -485,8 +545,18 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     p.n_img = d.N;
     p.n_blocks = d.n_total / block_n;
     p.taps = d.taps;
-    p.slabs0 = d.c0 / BLOCK_K;
-    p.slabs1 = d.c1 / BLOCK_K;
+    // K segments of one tap: [src0] (+[src1]); precise: [src0_hi, src0_hi, src0_lo] (+ the same for src1)
+    p.nseg = 0;
+    for (int src = 0; src < (d.c1 > 0 ? 2 : 1); ++src) {
+        const int sl = (src == 0 ? d.c0 : d.c1) / BLOCK_K;
+        const int ids[3] = {2 * src, 2 * src, 2 * src + 1};
+        for (int k = 0; k < kmul; ++k) {
+            p.seg_slabs[p.nseg] = sl;
+            p.seg_map[p.nseg] = ids[k];
+            ++p.nseg;
+        }
+    }
+    p.slabs = kmul * (d.c0 + d.c1) / BLOCK_K;
     p.off_x = d.off_x;
     p.off_y = d.off_y;
     p.relu = d.relu;
@@ -501,6 +571,7 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     p.out_u8 = d.out_u8;
     l.block_n = block_n;
     l.mode = d.mode;
+    l.split = precise ? 1 : 0;
     const long long total = static_cast<long long>(p.n_blocks) * p.n_img * p.tiles_y * p.tiles_x;
     if (total > 0x7fffffffLL) return "conv: too many tiles";
     l.grid = static_cast<int>(total < num_sms ? total : num_sms);

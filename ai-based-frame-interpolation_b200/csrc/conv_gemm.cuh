@@ -40,11 +40,25 @@ struct ConvDesc {
     float* out_f32;    // EPI_HEAD: fp32 NCHW [N,n_classes,H,W] or null
     uint8_t* out_u8;   // EPI_HEAD: u8  NCHW [N,n_classes,H,W] = trunc(clamp((y+1)/2,0,1)*255) or null
     int N, H, W;
+    // precise mode ("fp32x3"): every activation is a bf16 hi + bf16 lo pair (value = hi + lo, ~16 mantissa bits) and
+    // the GEMM accumulates x_hi*w_hi + x_hi*w_lo + x_lo*w_hi. K per tap = 3*(c0+c1), ordered
+    // [src0_hi | src0_hi | src0_lo | src1_hi | src1_hi | src1_lo] against wpack rows [w0_hi | w0_lo | w0_hi | w1_hi | ...].
+    int precise;
+    const void* src0_lo;
+    const void* src1_lo;
+    void* dst_lo;       // lo halves of dst / dst_pool (EPI_STORE*, EPI_CONVT)
+    void* dst_pool_lo;
 };
+
+constexpr int MAX_SEGS = 6;
 
 struct ConvKernelParams {
     int tiles_x, tiles_y, n_img, n_blocks;
-    int taps, slabs0, slabs1;
+    int taps;
+    int slabs;                 // 64-channel K slabs per tap = sum of seg_slabs
+    int nseg;                  // K segments per tap, each read from one source tensor map
+    int seg_slabs[MAX_SEGS];
+    int seg_map[MAX_SEGS];     // index into ConvMaps::a: 0 = src0 (hi), 1 = src0 lo, 2 = src1 (hi), 3 = src1 lo
     int off_x, off_y;
     int relu;
     int cout2;  // EPI_CONVT: 2*Cout (columns per output-row parity a)
@@ -60,15 +74,19 @@ struct ConvKernelParams {
 };
 
 // A fully prepared launch: tensor maps are encoded once per (layer, shape) and reused every forward.
+struct alignas(64) ConvMaps {
+    CUtensorMap a[4];     // src0, src0 lo, src1, src1 lo
+    CUtensorMap b;        // packed weights
+    CUtensorMap out[2];   // dst (hi), dst lo
+    CUtensorMap pool[2];  // pooled dst (hi), lo
+};
+
 struct ConvLaunch {
-    alignas(64) CUtensorMap map_a0;
-    alignas(64) CUtensorMap map_a1;
-    alignas(64) CUtensorMap map_b;
-    alignas(64) CUtensorMap map_out;
-    alignas(64) CUtensorMap map_pool;
+    ConvMaps maps;
     ConvKernelParams p;
     int block_n;
     int mode;
+    int split;  // 1: precise mode, epilogue writes hi + lo tensors
     int halo;  // 1: conv_halo.cu (halo-reuse kernel for Cout 64/128), 0: conv_gemm.cu
     int grid;
     double flops;  // algorithmic FLOPs of this launch (2*MACs, no padding counted)

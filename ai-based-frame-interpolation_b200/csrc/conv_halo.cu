@@ -67,11 +67,9 @@ __device__ __forceinline__ HTile decode_htile(int t, const ConvKernelParams& p) 
     return c;
 }
 
-template <int COUT, int MODE, bool RESIDENT>
+template <int COUT, int MODE, bool RESIDENT, bool SPLIT>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
-                 const __grid_constant__ CUtensorMap map_pool, const ConvKernelParams p) {
+conv_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p) {
     constexpr int B_STAGES = halo_b_stages(COUT);
     constexpr int B_STAGE_BYTES = halo_b_stage_bytes(COUT);
     constexpr int ACC_COLS = 2 * COUT;          // two column halves
@@ -100,11 +98,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&map_a0);
-        tma_prefetch_desc(&map_a1);
-        tma_prefetch_desc(&map_b);
-        if (MODE != EPI_HEAD) tma_prefetch_desc(&map_out);
-        if (MODE == EPI_STORE_POOL) tma_prefetch_desc(&map_pool);
+        tma_prefetch_desc(&maps.a[0]);
+        tma_prefetch_desc(&maps.a[2]);
+        tma_prefetch_desc(&maps.b);
+        if (MODE != EPI_HEAD) tma_prefetch_desc(&maps.out[0]);
+        if (MODE == EPI_STORE_POOL) tma_prefetch_desc(&maps.pool[0]);
         for (int s = 0; s < A_STAGES; ++s) {
             mbar_init(bar_afull + 8 * s, 1);
             mbar_init(bar_aempty + 8 * s, 1);
@@ -127,7 +125,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     const int total_tiles = p.n_img * p.tiles_y * p.tiles_x;
-    const int slabs = p.slabs0 + p.slabs1;
+    const int slabs = p.slabs;
 
     if (warp == 0) {
         // ------------------------------------------------------------ A producer: one halo box per (tile, slab)
@@ -141,26 +139,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                 const int tp = t + p.prefetch_dist * static_cast<int>(gridDim.x);
                 if (p.prefetch_dist > 0 && tp < total_tiles && lane == 0) {
                     const HTile pc = decode_htile(tp, p);
-                    for (int s = 0; s < slabs; ++s) {
-                        if (s < p.slabs0)
-                            tma_prefetch_l2_4d(&map_a0, s * BLOCK_K, pc.x0 - 1, pc.y0 - 1, pc.img);
-                        else
-                            tma_prefetch_l2_4d(&map_a1, (s - p.slabs0) * BLOCK_K, pc.x0 - 1 - p.off_x,
-                                               pc.y0 - 1 - p.off_y, pc.img);
+                    for (int g = 0; g < p.nseg; ++g) {
+                        const int mid = p.seg_map[g];
+                        if (g > 0 && p.seg_map[g - 1] == mid) continue;  // same tensor as the previous segment
+                        const int ox = mid >= 2 ? p.off_x : 0, oy = mid >= 2 ? p.off_y : 0;
+                        for (int c = 0; c < p.seg_slabs[g]; ++c)
+                            tma_prefetch_l2_4d(&maps.a[mid], c * BLOCK_K, pc.x0 - 1 - ox, pc.y0 - 1 - oy, pc.img);
                     }
                 }
+                int seg = 0, left = p.seg_slabs[0];
                 for (int s = 0; s < slabs; ++s) {
+                    while (left == 0) left = p.seg_slabs[++seg];
+                    const int local = p.seg_slabs[seg] - left;
+                    --left;
+                    const int mid = p.seg_map[seg];
                     mbar_wait(bar_aempty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_afull + 8 * stage;
                     if (elect_one()) {
                         mbar_expect_tx(full, HALO_BYTES);
-                        if (s < p.slabs0) {
-                            tma_load_4d(smem_a + stage * HALO_BYTES, &map_a0, full, s * BLOCK_K, tc.x0 - 1,
-                                        tc.y0 - 1, tc.img);
-                        } else {
-                            tma_load_4d(smem_a + stage * HALO_BYTES, &map_a1, full, (s - p.slabs0) * BLOCK_K,
-                                        tc.x0 - 1 - p.off_x, tc.y0 - 1 - p.off_y, tc.img);
-                        }
+                        const int ox = mid >= 2 ? p.off_x : 0, oy = mid >= 2 ? p.off_y : 0;  // F.pad of src1
+                        tma_load_4d(smem_a + stage * HALO_BYTES, &maps.a[mid], full, local * BLOCK_K, tc.x0 - 1 - ox,
+                                    tc.y0 - 1 - oy, tc.img);
                     }
                     __syncwarp();
                     if (++stage == A_STAGES) {
@@ -176,7 +175,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             if (lane == 0) {
                 mbar_expect_tx(bar_bres, 9 * B_STAGE_BYTES);
                 for (int tap = 0; tap < 9; ++tap)
-                    tma_load_2d(smem_b + tap * B_STAGE_BYTES, &map_b, bar_bres, tap * BLOCK_K, 0);
+                    tma_load_2d(smem_b + tap * B_STAGE_BYTES, &maps.b, bar_bres, tap * BLOCK_K, 0);
             }
         } else {
             int stage = 0;
@@ -188,7 +187,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                         const uint32_t full = bar_bfull + 8 * stage;
                         if (elect_one()) {
                             mbar_expect_tx(full, B_STAGE_BYTES);
-                            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full, (tap * slabs + s) * BLOCK_K, 0);
+                            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &maps.b, full, (tap * slabs + s) * BLOCK_K, 0);
                         }
                         __syncwarp();
                         if (++stage == B_STAGES) {
@@ -328,7 +327,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                             }
                         }
                     }
-                } else {
+                } else if constexpr (!SPLIT) {
                     uint32_t pk[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
@@ -343,7 +342,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (elect_one()) tma_store_4d(&map_out, sbuf, n_glob, xh, yq, tc.img);  // box {64, 8, 4, 1}
+                    if (elect_one()) tma_store_4d(&maps.out[0], sbuf, n_glob, xh, yq, tc.img);  // box {64, 8, 4, 1}
                     if constexpr (MODE == EPI_STORE_POOL) {
                         // pooled 2 rows x 4 columns: max over lanes {2ph*8 + 2pw, +1, +8, +9}
                         const uint32_t pbuf = my_pool + buf * 1024;
@@ -367,11 +366,52 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (elect_one()) {
-                            tma_store_4d(&map_pool, pbuf, n_glob, xh >> 1, yq >> 1, tc.img);  // box {64, 4, 2, 1}
+                            tma_store_4d(&maps.pool[0], pbuf, n_glob, xh >> 1, yq >> 1, tc.img);  // box {64, 4, 2, 1}
                         }
                     }
                     if (elect_one()) tma_store_commit();
                     buf ^= 1;
+                } else {
+                    // precise mode: hi tile in staging buffer 0, lo tile in buffer 1
+                    uint32_t pk[32], pl[32];
+                    split_hi_lo(f, pk, pl);
+                    if (elect_one()) tma_store_wait_read<0>();
+                    __syncwarp();
+                    const uint32_t shi = my_stage, slo = my_stage + 4096;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t o = lane * 128 + ((j ^ (lane & 7)) << 4);
+                        st_shared_v4(shi + o, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        st_shared_v4(slo + o, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (elect_one()) {
+                        tma_store_4d(&maps.out[0], shi, n_glob, xh, yq, tc.img);
+                        tma_store_4d(&maps.out[1], slo, n_glob, xh, yq, tc.img);
+                    }
+                    if constexpr (MODE == EPI_STORE_POOL) {
+                        const uint32_t phi = my_pool, plo = my_pool + 1024;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int pp = lane >> 2;
+                            const int j = (lane & 3) * 2 + i;
+                            const int r0 = (pp >> 2) * 16 + (pp & 3) * 2;
+                            const int rows[4] = {r0, r0 + 1, r0 + 8, r0 + 9};
+                            uint4 mh, ml;
+                            pool4_hi_lo(shi, slo, rows, j, mh, ml);
+                            const uint32_t o = pp * 128 + ((j ^ (pp & 7)) << 4);
+                            st_shared_v4(phi + o, mh.x, mh.y, mh.z, mh.w);
+                            st_shared_v4(plo + o, ml.x, ml.y, ml.z, ml.w);
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (elect_one()) {
+                            tma_store_4d(&maps.pool[0], phi, n_glob, xh >> 1, yq >> 1, tc.img);
+                            tma_store_4d(&maps.pool[1], plo, n_glob, xh >> 1, yq >> 1, tc.img);
+                        }
+                    }
+                    if (elect_one()) tma_store_commit();
                 }
             }
             tc_fence_before();
@@ -390,12 +430,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     }
 }
 
-template <int COUT, int MODE, bool RESIDENT = false>
+template <int COUT, int MODE, bool RESIDENT = false, bool SPLIT = false>
 const char* launch_halo_inst(const ConvLaunch& l, cudaStream_t stream) {
-    if constexpr (COUT == 64 && !RESIDENT) {
-        if (l.p.slabs0 + l.p.slabs1 == 1) return launch_halo_inst<COUT, MODE, true>(l, stream);
+    if constexpr (COUT == 64 && !RESIDENT && !SPLIT) {
+        if (l.p.slabs == 1 && !l.split) return launch_halo_inst<COUT, MODE, true, false>(l, stream);
     }
-    auto kfn = conv_halo_kernel<COUT, MODE, RESIDENT>;
+    if constexpr (!SPLIT && !RESIDENT && MODE != EPI_HEAD) {
+        if (l.split) return launch_halo_inst<COUT, MODE, false, true>(l, stream);
+    }
+    auto kfn = conv_halo_kernel<COUT, MODE, RESIDENT, SPLIT>;
     static bool configured = false;
     constexpr int smem = halo_smem_bytes(COUT, RESIDENT);
     static_assert(smem <= 232448, "halo kernel exceeds the 227 KB shared memory limit");
@@ -404,7 +447,7 @@ const char* launch_halo_inst(const ConvLaunch& l, cudaStream_t stream) {
             return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
         configured = true;
     }
-    kfn<<<l.grid, HALO_THREADS, smem, stream>>>(l.map_a0, l.map_a1, l.map_b, l.map_out, l.map_pool, l.p);
+    kfn<<<l.grid, HALO_THREADS, smem, stream>>>(l.maps, l.p);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

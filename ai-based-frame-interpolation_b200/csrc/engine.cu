@@ -70,8 +70,9 @@ struct ConvW {     // one conv3x3+BN (or the transposed conv) after folding/pack
     DevBuf b;      // fp32 [n_total]
 };
 
-struct Act {  // bf16 NHWC activation inside the arena
+struct Act {  // bf16 NHWC activation inside the arena (precise mode: a second, lo tensor at off_lo)
     size_t off = 0;
+    size_t off_lo = 0;
     int C = 0, H = 0, W = 0;
     size_t bytes(int N) const { return static_cast<size_t>(N) * H * W * C * 2; }
 };
@@ -82,6 +83,8 @@ struct Step {
     fi::ConvLaunch conv;        // STEP_CONV
     const void* src = nullptr;  // STEP_UPSAMPLE
     void* dst = nullptr;        // STEP_STEM / STEP_UPSAMPLE
+    const void* src_lo = nullptr;
+    void* dst_lo = nullptr;
     int h = 0, w = 0, C = 0;
     char name[48] = "";
     double flops = 0;  // algorithmic FLOPs of the launch
@@ -110,6 +113,7 @@ struct Plan {
 struct fiNet {
     int device = 0;
     int n_channels = 2, n_classes = 1, bilinear = 0;
+    int precise = 0;  // FI_PRECISION_FP32X3: hi/lo-split activations and weights, three products per MAC
     int num_sms = 148;
     bool loaded = false;
     DevBuf stem_w, stem_b;  // bf16 [64][stem_packed_k] hi/lo split, fp32 [64]
@@ -219,20 +223,50 @@ bool bn_fold(const StateDict& sd, const std::string& bn, int c, std::vector<doub
     return true;
 }
 
-int load_conv3x3(const StateDict& sd, const std::string& key, int cin, int cout, ConvW* out) {
+// One packed weight row: per tap, per source block [c_begin, c_end): bf16 [w] or, in precise mode, [w_hi | w_lo | w_hi].
+void pack_row(const std::vector<double>& w_tap_ci /*[taps][cin]*/, int taps, int cin, const int* blocks, int nblocks,
+              bool precise, uint16_t* row) {
+    size_t o = 0;
+    for (int t = 0; t < taps; ++t) {
+        int c0 = 0;
+        for (int b = 0; b < nblocks; ++b) {
+            const int c1 = c0 + blocks[b];
+            if (!precise) {
+                for (int c = c0; c < c1; ++c) row[o++] = f32_to_bf16_rn(static_cast<float>(w_tap_ci[static_cast<size_t>(t) * cin + c]));
+            } else {
+                for (int pass = 0; pass < 3; ++pass)
+                    for (int c = c0; c < c1; ++c) {
+                        const float v = static_cast<float>(w_tap_ci[static_cast<size_t>(t) * cin + c]);
+                        const uint16_t h = f32_to_bf16_rn(v);
+                        uint32_t hb = static_cast<uint32_t>(h) << 16;
+                        float hf;
+                        memcpy(&hf, &hb, 4);
+                        row[o++] = pass == 1 ? f32_to_bf16_rn(v - hf) : h;
+                    }
+            }
+            c0 = c1;
+        }
+    }
+}
+
+int load_conv3x3(const StateDict& sd, const std::string& key, int cin, int cout, ConvW* out, bool precise = false,
+                 int split_at = 0) {
     std::string err;
     const float* w = sd.get(key + ".weight", static_cast<int64_t>(cout) * cin * 9, &err);
     std::vector<double> scale;
     std::vector<float> shift;
     if (!w || !bn_fold(sd, bn_of(key), cout, &scale, &shift, &err)) return fail(FI_ERR_WEIGHTS, "%s", err.c_str());
-    const size_t K = static_cast<size_t>(9) * cin;
+    const size_t K = static_cast<size_t>(9) * cin * (precise ? 3 : 1);
     std::vector<uint16_t> packed(static_cast<size_t>(cout) * K);
-    for (int co = 0; co < cout; ++co)
+    std::vector<double> wt(static_cast<size_t>(9) * cin);
+    const int blocks[2] = {split_at > 0 ? split_at : cin, cin - split_at};  // fused concat: skip block, then up block
+    for (int co = 0; co < cout; ++co) {
         for (int ci = 0; ci < cin; ++ci)
-            for (int t = 0; t < 9; ++t) {
-                const double v = static_cast<double>(w[(static_cast<size_t>(co) * cin + ci) * 9 + t]) * scale[co];
-                packed[co * K + static_cast<size_t>(t) * cin + ci] = f32_to_bf16_rn(static_cast<float>(v));
-            }
+            for (int t = 0; t < 9; ++t)
+                wt[static_cast<size_t>(t) * cin + ci] =
+                    static_cast<double>(w[(static_cast<size_t>(co) * cin + ci) * 9 + t]) * scale[co];
+        pack_row(wt, 9, cin, blocks, split_at > 0 ? 2 : 1, precise, packed.data() + co * K);
+    }
     out->cin = cin;
     out->n_total = cout;
     CUDA_TRY(out->w.upload(packed.data(), packed.size() * 2));
@@ -240,19 +274,20 @@ int load_conv3x3(const StateDict& sd, const std::string& key, int cin, int cout,
     return FI_OK;
 }
 
-int load_convT(const StateDict& sd, const std::string& key, int cin, int cout, ConvW* out) {
+int load_convT(const StateDict& sd, const std::string& key, int cin, int cout, ConvW* out, bool precise = false) {
     std::string err;
     const float* w = sd.get(key + ".weight", static_cast<int64_t>(cin) * cout * 4, &err);  // [cin][cout][2][2]
     const float* b = w ? sd.get(key + ".bias", cout, &err) : nullptr;
     if (!b) return fail(FI_ERR_WEIGHTS, "%s", err.c_str());
-    std::vector<uint16_t> packed(static_cast<size_t>(4) * cout * cin);
+    const size_t K = static_cast<size_t>(cin) * (precise ? 3 : 1);
+    std::vector<uint16_t> packed(static_cast<size_t>(4) * cout * K);
     std::vector<float> bias4(static_cast<size_t>(4) * cout);
+    std::vector<double> wt(cin);
     for (int ab = 0; ab < 4; ++ab)
         for (int co = 0; co < cout; ++co) {
             bias4[static_cast<size_t>(ab) * cout + co] = b[co];
-            for (int ci = 0; ci < cin; ++ci)
-                packed[(static_cast<size_t>(ab) * cout + co) * cin + ci] =
-                    f32_to_bf16_rn(w[(static_cast<size_t>(ci) * cout + co) * 4 + ab]);
+            for (int ci = 0; ci < cin; ++ci) wt[ci] = w[(static_cast<size_t>(ci) * cout + co) * 4 + ab];
+            pack_row(wt, 1, cin, &cin, 1, precise, packed.data() + (static_cast<size_t>(ab) * cout + co) * K);
         }
     out->cin = cin;
     out->n_total = 4 * cout;
@@ -288,6 +323,10 @@ int build_plan(fiNet* net, int N, int H, int W) {
         a.H = h;
         a.W = w;
         cursor = align_up(cursor + a.bytes(N), 1024);
+        if (net->precise) {
+            a.off_lo = cursor;
+            cursor = align_up(cursor + a.bytes(N), 1024);
+        }
         pl.acts[name] = a;
     };
     const int enc_c[5] = {64, cs[2].cout, cs[4].cout, cs[6].cout, cs[8].cout};
@@ -325,6 +364,9 @@ int build_plan(fiNet* net, int N, int H, int W) {
     auto ptr = [&](const std::string& name) -> void* {
         return static_cast<char*>(pl.arena.p) + pl.acts.at(name).off;
     };
+    auto ptr_lo = [&](const std::string& name) -> void* {
+        return net->precise ? static_cast<char*>(pl.arena.p) + pl.acts.at(name).off_lo : nullptr;
+    };
 
     pl.flops = 2.0 * N * H * W * 64.0 * 9 * stem.cin;
     auto push_conv = [&](fi::ConvDesc d, const std::string& name) -> int {
@@ -350,12 +392,15 @@ int build_plan(fiNet* net, int N, int H, int W) {
         fi::ConvDesc d;
         memset(&d, 0, sizeof d);
         d.src0 = ptr(src);
+        d.src0_lo = ptr_lo(src);
+        d.precise = net->precise;
         d.c0 = a.C;
         d.H = a.H;
         d.W = a.W;
         if (!src1.empty()) {
             const Act& b = pl.acts.at(src1);
             d.src1 = ptr(src1);
+            d.src1_lo = ptr_lo(src1);
             d.c1 = b.C;
             d.h1 = b.H;
             d.w1 = b.W;
@@ -377,7 +422,11 @@ int build_plan(fiNet* net, int N, int H, int W) {
             d.out_f32 = reinterpret_cast<float*>(16);  // patched per forward call
         } else {
             d.dst = ptr(dst);
-            if (mode == fi::EPI_STORE_POOL) d.dst_pool = ptr(pool);
+            d.dst_lo = ptr_lo(dst);
+            if (mode == fi::EPI_STORE_POOL) {
+                d.dst_pool = ptr(pool);
+                d.dst_pool_lo = ptr_lo(pool);
+            }
         }
         return push_conv(d, conv_prefix(idx));
     };
@@ -387,6 +436,7 @@ int build_plan(fiNet* net, int N, int H, int W) {
         Step s;
         s.kind = STEP_STEM;
         s.dst = ptr("inc.mid");
+        s.dst_lo = ptr_lo("inc.mid");
         snprintf(s.name, sizeof s.name, "inc.double_conv.0");
         s.flops = 2.0 * N * H * W * 64.0 * 9 * stem.cin;
         s.bytes = static_cast<double>(N) * H * W * (stem.cin * 4.0 + 128.0);
@@ -415,6 +465,8 @@ int build_plan(fiNet* net, int N, int H, int W) {
             s.kind = STEP_UPSAMPLE;
             s.src = ptr(below);
             s.dst = ptr(up);
+            s.src_lo = ptr_lo(below);
+            s.dst_lo = ptr_lo(up);
             s.h = lo.H;
             s.w = lo.W;
             s.C = lo.C;
@@ -426,6 +478,8 @@ int build_plan(fiNet* net, int N, int H, int W) {
             memset(&d, 0, sizeof d);
             const ConvW& cw = net->upT[i];
             d.src0 = ptr(below);
+            d.src0_lo = ptr_lo(below);
+            d.precise = net->precise;
             d.c0 = lo.C;
             d.H = lo.H;
             d.W = lo.W;
@@ -436,6 +490,7 @@ int build_plan(fiNet* net, int N, int H, int W) {
             d.mode = fi::EPI_CONVT;
             d.relu = 0;
             d.dst = ptr(up);
+            d.dst_lo = ptr_lo(up);
             if ((rc = push_conv(d, up))) return rc;
         }
         if ((rc = conv3(9 + 2 * i, skips[i], up, mid, "", fi::EPI_STORE))) return rc;
@@ -516,6 +571,18 @@ int fiNetCreate(fiNet** out, int device, int n_channels, int n_classes, int bili
     return FI_OK;
 }
 
+int fiNetSetPrecision(fiNet* net, int precision) {
+    if (!net) return fail(FI_ERR_INVALID, "net is null");
+    if (precision != FI_PRECISION_BF16 && precision != FI_PRECISION_FP32X3)
+        return fail(FI_ERR_INVALID, "unknown precision %d", precision);
+    if (net->precise != precision) {  // packed weights and the arena layout depend on it
+        net->precise = precision;
+        net->loaded = false;
+        net->plan.reset();
+    }
+    return FI_OK;
+}
+
 int fiNetDestroy(fiNet* net) {
     if (!net) return FI_OK;
     cudaSetDevice(net->device);
@@ -567,13 +634,17 @@ int fiNetLoadWeights(fiNet* net, const char* const* names, const float* const* d
         CUDA_TRY(net->stem_w.upload(packed.data(), packed.size() * 2));
         CUDA_TRY(net->stem_b.upload(shift.data(), shift.size() * 4));
     }
-    for (int i = 0; i < 17; ++i)
-        if ((rc = load_conv3x3(sd, conv_prefix(i), cs[i].cin, cs[i].cout, &net->convs[i]))) return rc;
+    for (int i = 0; i < 17; ++i) {
+        // up{k}.conv.double_conv.0 (indices 9, 11, 13, 15) reads [skip | up]: two K blocks of cin/2 channels each
+        const int split_at = (i >= 9 && (i - 9) % 2 == 0) ? cs[i].cin / 2 : 0;
+        if ((rc = load_conv3x3(sd, conv_prefix(i), cs[i].cin, cs[i].cout, &net->convs[i], net->precise != 0, split_at)))
+            return rc;
+    }
     if (!net->bilinear) {
         for (int i = 0; i < 4; ++i) {
             char key[32];
             snprintf(key, sizeof key, "up%d.up", i + 1);
-            if ((rc = load_convT(sd, key, upc[i][0], upc[i][1], &net->upT[i]))) return rc;
+            if ((rc = load_convT(sd, key, upc[i][0], upc[i][1], &net->upT[i], net->precise != 0))) return rc;
         }
     }
     {
@@ -624,9 +695,10 @@ int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dt
             d.wpack = net->stem_w.p;
             d.bias = static_cast<const float*>(net->stem_b.p);
             d.dst = s.dst;
+            d.dst_lo = s.dst_lo;
             KERNEL_TRY(fi::stem_conv_launch(d, st));
         } else if (s.kind == STEP_UPSAMPLE) {
-            KERNEL_TRY(fi::upsample2x_launch(s.src, s.dst, N, s.h, s.w, s.C, st));
+            KERNEL_TRY(fi::upsample2x_launch(s.src, s.dst, N, s.h, s.w, s.C, st, s.src_lo, s.dst_lo));
         } else {
             if (static_cast<int>(i) == pl.head_step) {
                 s.conv.p.out_f32 = out_f32;
@@ -832,16 +904,28 @@ int fiNetReadActivation(fiNet* net, const char* name, float* out_host, int64_t c
     if (capacity < n) return fail(FI_ERR_INVALID, "buffer too small: need %lld floats", static_cast<long long>(n));
     int rc = set_device(net->device);
     if (rc) return rc;
-    std::vector<uint16_t> raw(static_cast<size_t>(n));
+    std::vector<uint16_t> raw(static_cast<size_t>(n)), raw_lo;
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(raw.data(), static_cast<char*>(pl.arena.p) + a.off, raw.size() * 2, cudaMemcpyDeviceToHost));
+    if (net->precise) {
+        raw_lo.resize(raw.size());
+        CUDA_TRY(cudaMemcpy(raw_lo.data(), static_cast<char*>(pl.arena.p) + a.off_lo, raw.size() * 2,
+                            cudaMemcpyDeviceToHost));
+    }
     for (int nn = 0; nn < pl.N; ++nn)
         for (int y = 0; y < a.H; ++y)
             for (int x = 0; x < a.W; ++x)
                 for (int c = 0; c < a.C; ++c) {
-                    const uint32_t bits = static_cast<uint32_t>(raw[((static_cast<size_t>(nn) * a.H + y) * a.W + x) * a.C + c]) << 16;
+                    const size_t src_i = ((static_cast<size_t>(nn) * a.H + y) * a.W + x) * a.C + c;
+                    const uint32_t bits = static_cast<uint32_t>(raw[src_i]) << 16;
                     float f;
                     memcpy(&f, &bits, 4);
+                    if (net->precise) {
+                        const uint32_t lb = static_cast<uint32_t>(raw_lo[src_i]) << 16;
+                        float fl;
+                        memcpy(&fl, &lb, 4);
+                        f += fl;
+                    }
                     out_host[((static_cast<size_t>(nn) * a.C + c) * a.H + y) * a.W + x] = f;
                 }
     if (C) *C = a.C;
@@ -882,6 +966,11 @@ int fiConvGemm(const fiConvDesc* desc, void* stream) {
     d.N = desc->N;
     d.H = desc->H;
     d.W = desc->W;
+    d.precise = desc->precise;
+    d.src0_lo = desc->src0_lo;
+    d.src1_lo = desc->src1_lo;
+    d.dst_lo = desc->dst_lo;
+    d.dst_pool_lo = desc->dst_pool_lo;
     fi::ConvLaunch l;
     const char* e = fi::conv_prepare(d, sms, &l);
     if (e) return fail(FI_ERR_INVALID, "%s", e);

@@ -204,4 +204,47 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
     return r;
 }
 
+// ------------------------------------------------------------------ precise mode helpers (value = bf16 hi + bf16 lo)
+__device__ __forceinline__ float bf16lo_f(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16hi_f(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+// 64 fp32 values -> 32 packed bf16x2 hi words + 32 packed lo words (lo = bf16(f - hi): ~16 mantissa bits in total)
+__device__ __forceinline__ void split_hi_lo(const float (&f)[64], uint32_t (&hi)[32], uint32_t (&lo)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const uint32_t h = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+        hi[j] = h;
+        lo[j] = pack_bf16x2(f[2 * j] - bf16lo_f(h), f[2 * j + 1] - bf16hi_f(h));
+    }
+}
+
+// 2x2 max-pool of (hi, lo) pairs: 16-byte chunk j of four staged rows (128B-swizzled staging tiles shi / slo).
+// hi + lo is exact in fp32 (<= 17 significant bits), so the max is taken on the true values and re-split.
+__device__ __forceinline__ void pool4_hi_lo(uint32_t shi, uint32_t slo, const int (&rows)[4], int j, uint4& mh,
+                                            uint4& ml) {
+    float m[8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t off = rows[r] * 128 + ((j ^ (rows[r] & 7)) << 4);
+        const uint4 h = ld_shared_v4(shi + off);
+        const uint4 l = ld_shared_v4(slo + off);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float v0 = bf16lo_f(hw[w]) + bf16lo_f(lw[w]);
+            const float v1 = bf16hi_f(hw[w]) + bf16hi_f(lw[w]);
+            m[2 * w] = r == 0 ? v0 : fmaxf(m[2 * w], v0);
+            m[2 * w + 1] = r == 0 ? v1 : fmaxf(m[2 * w + 1], v1);
+        }
+    }
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        oh[w] = pack_bf16x2(m[2 * w], m[2 * w + 1]);
+        ol[w] = pack_bf16x2(m[2 * w] - bf16lo_f(oh[w]), m[2 * w + 1] - bf16hi_f(oh[w]));
+    }
+    mh = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    ml = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+}
+
 }  // namespace fi

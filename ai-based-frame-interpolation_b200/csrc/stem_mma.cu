@@ -28,6 +28,7 @@ constexpr int SM_A_BYTES = 128 * 128;  // 128 pixels x 64 bf16
 struct StemParams {
     PlaneSrc src[2];
     int N, H, W, tiles_x, tiles_y;
+    int split;  // precise mode: also store lo = bf16(value - hi)
     const float* bias;
 };
 
@@ -50,7 +51,7 @@ __device__ __forceinline__ uint32_t bf16_bits(float v) {  // round-to-nearest-ev
 template <int CIN, bool U8>
 __global__ void __launch_bounds__(SM_THREADS, CIN <= 3 ? 2 : 1)
 stem_mma_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
-                const StemParams p) {
+                const __grid_constant__ CUtensorMap map_out_lo, const StemParams p) {
     constexpr int KT = 9 * CIN;
     constexpr int SLABS = stem_slabs(CIN);
     constexpr uint32_t IDESC = umma_idesc_bf16(128, 64);
@@ -260,34 +261,46 @@ stem_mma_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             __syncwarp();
             if (elect_one()) mbar_arrive(bar_tempty + 8 * acc);  // accumulator is in registers: release it early
             const float4* bias4 = reinterpret_cast<const float4*>(p.bias);
-            uint32_t pk[32];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 b = __ldg(bias4 + j);
-                pk[2 * j] = pack_bf16x2(fmaxf(__uint_as_float(v0[4 * j]) + b.x, 0.f),
-                                        fmaxf(__uint_as_float(v0[4 * j + 1]) + b.y, 0.f));
-                pk[2 * j + 1] = pack_bf16x2(fmaxf(__uint_as_float(v0[4 * j + 2]) + b.z, 0.f),
-                                            fmaxf(__uint_as_float(v0[4 * j + 3]) + b.w, 0.f));
+            // split: buffer 0 = hi tile, buffer 1 = lo tile (both must be free); else the two buffers alternate
+            if (elect_one()) {
+                if (p.split) tma_store_wait_read<0>();
+                else tma_store_wait_read<1>();
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 b = __ldg(bias4 + 8 + j);
-                pk[16 + 2 * j] = pack_bf16x2(fmaxf(__uint_as_float(v1[4 * j]) + b.x, 0.f),
-                                             fmaxf(__uint_as_float(v1[4 * j + 1]) + b.y, 0.f));
-                pk[16 + 2 * j + 1] = pack_bf16x2(fmaxf(__uint_as_float(v1[4 * j + 2]) + b.z, 0.f),
-                                                 fmaxf(__uint_as_float(v1[4 * j + 3]) + b.w, 0.f));
-            }
-            if (elect_one()) tma_store_wait_read<1>();
             __syncwarp();
-            const uint32_t sbuf = my_stage + buf * 4096;
-            const uint32_t row = sbuf + lane * 128;
+            const uint32_t sbuf = p.split ? my_stage : my_stage + buf * 4096;
+            const uint32_t slo = my_stage + 4096;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                st_shared_v4(row + ((j ^ (lane & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) {  // 16-byte chunk j = channels 8j .. 8j+7
+                const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
+                const uint32_t* v = j < 4 ? v0 : v1;
+                const int o = (j & 3) * 8;
+                float f[8];
+                f[0] = fmaxf(__uint_as_float(v[o + 0]) + b0.x, 0.f);
+                f[1] = fmaxf(__uint_as_float(v[o + 1]) + b0.y, 0.f);
+                f[2] = fmaxf(__uint_as_float(v[o + 2]) + b0.z, 0.f);
+                f[3] = fmaxf(__uint_as_float(v[o + 3]) + b0.w, 0.f);
+                f[4] = fmaxf(__uint_as_float(v[o + 4]) + b1.x, 0.f);
+                f[5] = fmaxf(__uint_as_float(v[o + 5]) + b1.y, 0.f);
+                f[6] = fmaxf(__uint_as_float(v[o + 6]) + b1.z, 0.f);
+                f[7] = fmaxf(__uint_as_float(v[o + 7]) + b1.w, 0.f);
+                uint32_t hw[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) hw[k] = pack_bf16x2(f[2 * k], f[2 * k + 1]);
+                const uint32_t off = lane * 128 + ((j ^ (lane & 7)) << 4);
+                st_shared_v4(sbuf + off, hw[0], hw[1], hw[2], hw[3]);
+                if (p.split) {
+                    uint32_t lw[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        lw[k] = pack_bf16x2(f[2 * k] - bf16lo_f(hw[k]), f[2 * k + 1] - bf16hi_f(hw[k]));
+                    st_shared_v4(slo + off, lw[0], lw[1], lw[2], lw[3]);
+                }
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (elect_one()) {
                 tma_store_4d(&map_out, sbuf, 0, x0, y0 + 2 * q, img);  // box {64, 16, 2, 1}
+                if (p.split) tma_store_4d(&map_out_lo, slo, 0, x0, y0 + 2 * q, img);
                 tma_store_commit();
             }
             buf ^= 1;
@@ -305,8 +318,8 @@ stem_mma_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
 }
 
 template <int CIN>
-const char* launch_stem(const StemDesc& d, const CUtensorMap& map_b, const CUtensorMap& map_out, const StemParams& p,
-                        int grid, cudaStream_t stream) {
+const char* launch_stem(const StemDesc& d, const CUtensorMap& map_b, const CUtensorMap& map_out,
+                        const CUtensorMap& map_out_lo, const StemParams& p, int grid, cudaStream_t stream) {
     constexpr int smem = stem_smem_bytes(CIN);
     static bool configured[2] = {false, false};
     if (d.is_u8) {
@@ -316,7 +329,7 @@ const char* launch_stem(const StemDesc& d, const CUtensorMap& map_b, const CUten
                 return "stem: cudaFuncSetAttribute failed";
             configured[1] = true;
         }
-        k<<<grid, SM_THREADS, smem, stream>>>(map_b, map_out, p);
+        k<<<grid, SM_THREADS, smem, stream>>>(map_b, map_out, map_out_lo, p);
     } else {
         auto k = stem_mma_kernel<CIN, false>;
         if (!configured[0]) {
@@ -324,7 +337,7 @@ const char* launch_stem(const StemDesc& d, const CUtensorMap& map_b, const CUten
                 return "stem: cudaFuncSetAttribute failed";
             configured[0] = true;
         }
-        k<<<grid, SM_THREADS, smem, stream>>>(map_b, map_out, p);
+        k<<<grid, SM_THREADS, smem, stream>>>(map_b, map_out, map_out_lo, p);
     }
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
@@ -381,9 +394,10 @@ const char* stem_conv_launch(const StemDesc& d, cudaStream_t stream) {
     p.tiles_x = (d.W + TILE_W - 1) / TILE_W;
     p.tiles_y = (d.H + TILE_H - 1) / TILE_H;
     p.bias = d.bias;
+    p.split = d.dst_lo != nullptr;
     const long long tiles = static_cast<long long>(d.N) * p.tiles_x * p.tiles_y;
     if (tiles > 0x7fffffffLL) return "stem: too many tiles";
-    alignas(64) CUtensorMap map_b, map_out;
+    alignas(64) CUtensorMap map_b, map_out, map_out_lo;
     const char* e;
     {
         const uint64_t kp = stem_packed_k(d.cin);
@@ -398,20 +412,22 @@ const char* stem_conv_launch(const StemDesc& d, cudaStream_t stream) {
         const uint64_t strides[3] = {64, static_cast<uint64_t>(d.W) * 64, static_cast<uint64_t>(d.H) * d.W * 64};
         const uint32_t box[4] = {64, TILE_W, 2, 1};
         if ((e = encode_bf16_map_public(&map_out, d.dst, 4, dims, strides, box))) return e;
+        map_out_lo = map_out;
+        if (d.dst_lo && (e = encode_bf16_map_public(&map_out_lo, d.dst_lo, 4, dims, strides, box))) return e;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = static_cast<int>(tiles < 2LL * sms ? tiles : 2LL * sms);
     switch (d.cin) {
-        case 1: return launch_stem<1>(d, map_b, map_out, p, grid, stream);
-        case 2: return launch_stem<2>(d, map_b, map_out, p, grid, stream);
-        case 3: return launch_stem<3>(d, map_b, map_out, p, grid, stream);
-        case 4: return launch_stem<4>(d, map_b, map_out, p, grid, stream);
-        case 5: return launch_stem<5>(d, map_b, map_out, p, grid, stream);
-        case 6: return launch_stem<6>(d, map_b, map_out, p, grid, stream);
-        case 7: return launch_stem<7>(d, map_b, map_out, p, grid, stream);
-        default: return launch_stem<8>(d, map_b, map_out, p, grid, stream);
+        case 1: return launch_stem<1>(d, map_b, map_out, map_out_lo, p, grid, stream);
+        case 2: return launch_stem<2>(d, map_b, map_out, map_out_lo, p, grid, stream);
+        case 3: return launch_stem<3>(d, map_b, map_out, map_out_lo, p, grid, stream);
+        case 4: return launch_stem<4>(d, map_b, map_out, map_out_lo, p, grid, stream);
+        case 5: return launch_stem<5>(d, map_b, map_out, map_out_lo, p, grid, stream);
+        case 6: return launch_stem<6>(d, map_b, map_out, map_out_lo, p, grid, stream);
+        case 7: return launch_stem<7>(d, map_b, map_out, map_out_lo, p, grid, stream);
+        default: return launch_stem<8>(d, map_b, map_out, map_out_lo, p, grid, stream);
     }
 }
 

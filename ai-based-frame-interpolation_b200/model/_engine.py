@@ -32,7 +32,9 @@ class ConvDesc(C.Structure):
                 ("w1", C.c_int), ("off_y", C.c_int), ("off_x", C.c_int), ("wpack", C.c_void_p), ("bias", C.c_void_p),
                 ("n_total", C.c_int), ("taps", C.c_int), ("mode", C.c_int), ("relu", C.c_int), ("dst", C.c_void_p),
                 ("dst_pool", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("n_classes", C.c_int),
-                ("out_f32", C.c_void_p), ("out_u8", C.c_void_p), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int)]
+                ("out_f32", C.c_void_p), ("out_u8", C.c_void_p), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("precise", C.c_int), ("src0_lo", C.c_void_p), ("src1_lo", C.c_void_p), ("dst_lo", C.c_void_p),
+                ("dst_pool_lo", C.c_void_p)]
 
 
 class LaunchProfile(C.Structure):
@@ -47,6 +49,7 @@ _SIGNATURES = {
     "fiLastError": (C.c_char_p, []),
     "fiNetCreate": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]),
     "fiNetDestroy": (C.c_int, [C.c_void_p]),
+    "fiNetSetPrecision": (C.c_int, [C.c_void_p, C.c_int]),
     "fiNetLoadWeights": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                    C.c_int]),
     "fiNetForward": (C.c_int, [C.c_void_p, C.POINTER(Planes), C.POINTER(Planes), C.c_int, C.c_void_p, C.c_void_p,
@@ -119,13 +122,19 @@ def require_cuda(device) -> torch.device:
 class Net:
     """Owner of one fiNet handle (weights + activation arena on one GPU)."""
 
-    def __init__(self, device, n_channels=2, n_classes=1, bilinear=False):
+    PRECISIONS = {"bf16": 0, "fp32": 1}
+
+    def __init__(self, device, n_channels=2, n_classes=1, bilinear=False, precision="bf16"):
+        if precision not in self.PRECISIONS:
+            raise FiError(f"precision must be one of {sorted(self.PRECISIONS)}, got {precision!r}")
         device = require_cuda(device)
         self.device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
         self.n_channels, self.n_classes, self.bilinear = n_channels, n_classes, bool(bilinear)
         h = C.c_void_p()
         check(lib().fiNetCreate(C.byref(h), self.device.index, n_channels, n_classes, int(self.bilinear)))
         self._h = h
+        self.precision = precision
+        check(lib().fiNetSetPrecision(self._h, self.PRECISIONS[precision]))
         self.loaded = False
 
     def close(self):

@@ -30,7 +30,12 @@ def _fused_only(name):
 
 
 class _EngineBacked(nn.Module):
-    """Mixin: lazily mirrors this module's parameters into a fiNet handle and re-uploads when they change."""
+    """Mixin: lazily mirrors this module's parameters into a fiNet handle and re-uploads when they change.
+
+    `module.precision` selects the arithmetic: "bf16" (default; bf16 operands, fp32 accumulate, <= 2e-2 pixel error) or
+    "fp32" (hi/lo-split bf16 operands, three products per MAC: fp32-grade, <= 1e-3; about 3x slower)."""
+
+    precision = "bf16"
 
     def _engine_spec(self):  # (n_channels, n_classes, bilinear)
         raise NotImplementedError
@@ -43,11 +48,11 @@ class _EngineBacked(nn.Module):
             raise _E.FiError("training-mode forward (batch-statistics BatchNorm) is not part of the B200 inference "
                              "path; call .eval() first")
         net = self.__dict__.get("_fi_net")
-        if net is None or net.device != device:
+        if net is None or net.device != device or net.precision != self.precision:
             if net is not None:
                 net.close()
             n_ch, n_cls, bil = self._engine_spec()
-            net = _E.Net(device, n_ch, n_cls, bil)
+            net = _E.Net(device, n_ch, n_cls, bil, self.precision)
             self.__dict__["_fi_net"] = net
             self.__dict__["_fi_print"] = None
         fp = self._fingerprint()

@@ -167,6 +167,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=4, help="frame pairs per forward (per GPU)")
     ap.add_argument("--bilinear", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16 (headline) or the hi/lo-split fp32-grade path (3x the tensor work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-launch table (JSON) here")
     args = ap.parse_args()
@@ -201,7 +203,7 @@ def main():
         return float(t.item())
 
     B = args.pairs
-    net = E.Net(dev, 2, 1, args.bilinear)
+    net = E.Net(dev, 2, 1, args.bilinear, args.precision)
     net.load_state_dict(O.init_state_dict(0, 2, 1, args.bilinear))
 
     # this rank's contiguous shard of the 599 frame pairs (neighbouring ranks share one boundary frame); the timed
@@ -265,7 +267,7 @@ def main():
     all_ms = sum(p["ms_total"] for p in prof)
     traffic = None  # DRAM bytes per conv launch from the committed ncu --set full capture, scaled to this batch
     tf = ROOT / "profiles" / "ncu_traffic.json"
-    if tf.exists() and not args.bilinear:
+    if tf.exists() and not args.bilinear and args.precision == "bf16":
         t = json.loads(tf.read_text())
         traffic = t["dram_bytes"] / t["pairs"] * B / t["conv_launches"]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -293,7 +295,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (hi/lo split, fp32-grade)",
+        "data": "synthetic",
         "config": {"workload": "1080p (1920x1080) 2x video interpolation, 600 synthetic frames, "
                                "UNet(2,1,bilinear=%s) random-init, frame pairs sharded across GPUs" % args.bilinear,
                    "pairs_per_step": B, "frame": [H, W],

@@ -45,6 +45,15 @@ typedef struct fiNet fiNet;
 int fiNetCreate(fiNet** out, int device, int n_channels, int n_classes, int bilinear);
 int fiNetDestroy(fiNet* net);
 
+/* Arithmetic of the tensor-core convolutions. Call before fiNetLoadWeights (it invalidates loaded weights).
+ *   FI_PRECISION_BF16   (default) bf16 operands, fp32 accumulate: max |err| <= 2e-2 in [0,1] pixel units.
+ *   FI_PRECISION_FP32X3 the "fp32 path": every activation and weight is a bf16 hi + bf16 lo pair and each MAC is
+ *                       x_hi*w_hi + x_hi*w_lo + x_lo*w_hi in fp32 (~16 mantissa bits per operand): <= 1e-3.
+ *                       3x the tensor work and 2x the activation bytes of the bf16 path. */
+#define FI_PRECISION_BF16 0
+#define FI_PRECISION_FP32X3 1
+int fiNetSetPrecision(fiNet* net, int precision);
+
 /* load_state_dict (model/inference.py:83-94, schema SURVEY.md A.5). names[i] are state-dict keys with or without the
  * "unet." prefix; data_host[i] is the fp32 host tensor, numel[i] its element count. Eval-mode BatchNorm
  * (model/unet.py:13,16) is folded here: W' = W*gamma/sqrt(var+eps) (rounded once to bf16), b' = beta - mean*scale. */
@@ -132,6 +141,14 @@ typedef struct fiConvDesc {
     float* out_f32;     /* HEAD: fp32 NCHW [N,n_classes,H,W] or NULL */
     uint8_t* out_u8;    /* HEAD: u8 NCHW or NULL */
     int N, H, W;
+    /* precise ("fp32x3") mode: activations are bf16 hi + bf16 lo pairs (value = hi + lo) and the GEMM accumulates
+     * x_hi*w_hi + x_hi*w_lo + x_lo*w_hi in fp32. wpack is then bf16 [n_total][taps*3*(c0+c1)], per tap
+     * [w0_hi | w0_lo | w0_hi | w1_hi | w1_lo | w1_hi] (w0 / w1 = the weight columns of src0 / src1 channels). */
+    int precise;
+    const void* src0_lo; /* lo halves, same shapes as src0 / src1 */
+    const void* src1_lo;
+    void* dst_lo;        /* lo halves of dst / dst_pool (not used by HEAD) */
+    void* dst_pool_lo;
 } fiConvDesc;
 
 int fiConvGemm(const fiConvDesc* desc, void* stream);

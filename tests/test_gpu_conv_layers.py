@@ -6,7 +6,7 @@ import torch
 import torch.nn.functional as F
 
 from model import _engine as E
-from layer_utils import bf16_round, ref_conv3x3, run_conv
+from layer_utils import bf16_round, ref_conv3x3, run_conv, run_conv_precise
 
 pytestmark = pytest.mark.gpu
 
@@ -112,3 +112,54 @@ def test_head_epilogue(cuda_device, ncls, h, w):
     t = out["f32"]
     exp = (torch.clamp((t + 1.0) / 2.0, 0.0, 1.0).numpy() * 255).astype("uint8")
     assert (out["u8"].numpy() == exp).all()
+
+
+# ------------------------------------------------------------------------------------------------ precise (fp32x3) mode
+def ref_fp64(x, w, b, relu=True, x1=None, off=(0, 0)):
+    xin = x
+    if x1 is not None:
+        h, wd = x.shape[2], x.shape[3]
+        xin = torch.cat([x, F.pad(x1, [off[1], wd - x1.shape[3] - off[1], off[0], h - x1.shape[2] - off[0]])], 1)
+    y = F.conv2d(xin.double(), w.double(), b.double(), padding=1)
+    return (F.relu(y) if relu else y).float()
+
+
+def close_precise(a, b, what):
+    assert a.shape == b.shape and not torch.isnan(a).any(), what
+    err = (a - b).abs().max().item()
+    scale = b.abs().max().item()
+    # three bf16 x bf16 products of hi/lo splits: ~2^-16 relative per operand; output re-split to 16 bits
+    assert err <= 2.0 ** -13 * scale + 1e-6, f"{what}: max err {err:.3g} (scale {scale:.3g})"
+
+
+@pytest.mark.parametrize("n,c0,c1,cout,h,w,mode", [
+    (1, 64, 0, 64, 16, 32, E.EPI_STORE), (2, 128, 0, 128, 19, 23, E.EPI_STORE_POOL),
+    (1, 256, 0, 256, 9, 17, E.EPI_STORE), (1, 64, 64, 64, 18, 34, E.EPI_STORE), (1, 256, 256, 256, 17, 20, E.EPI_STORE_POOL),
+    (1, 128, 128, 128, 16, 48, E.EPI_STORE),
+])
+def test_precise_conv3x3(cuda_device, n, c0, c1, cout, h, w, mode):
+    g = torch.Generator().manual_seed(c0 + c1 + cout + h)
+    x = rnd(g, n, c0, h, w)
+    x1 = rnd(g, n, c1, h - 1, w - 2) if c1 else None
+    off = (0, 1)
+    wt = rnd(g, cout, c0 + c1, 3, 3, scale=(2.0 / (9 * (c0 + c1))) ** 0.5)
+    b = rnd(g, cout, scale=0.1)
+    out = run_conv_precise(cuda_device, x, wt, b, mode=mode, x1=x1, off=off)
+    ref = ref_fp64(x, wt, b, x1=x1, off=off)
+    close_precise(out["dst"], ref, "precise conv")
+    if mode == E.EPI_STORE_POOL:
+        close_precise(out["pool"], F.max_pool2d(ref, 2), "precise pooled")
+        assert (out["pool"] - F.max_pool2d(out["dst"], 2)).abs().max() <= 2.0 ** -15 * ref.abs().max()
+
+
+def test_precise_conv_transpose_and_head(cuda_device):
+    g = torch.Generator().manual_seed(77)
+    x, wt, b = rnd(g, 1, 128, 9, 20), rnd(g, 128, 64, 2, 2, scale=0.09), rnd(g, 64, scale=0.1)
+    got = run_conv_precise(cuda_device, x, wt, b, relu=False, mode=E.EPI_CONVT)["dst"]
+    ref = F.conv_transpose2d(x.double(), wt.double(), b.double(), stride=2).float()
+    close_precise(got, ref, "precise conv transpose")
+    x, wt, b = rnd(g, 1, 64, 20, 24), rnd(g, 64, 64, 3, 3, scale=0.06), rnd(g, 64, scale=0.1)
+    hw_, hb = rnd(g, 2, 64, scale=0.4), rnd(g, 2, scale=0.2)
+    out = run_conv_precise(cuda_device, x, wt, b, mode=E.EPI_HEAD, head_w=hw_, head_b=hb)["f32"]
+    ref = F.conv2d(ref_fp64(x, wt, b).double(), hw_.double()[:, :, None, None], hb.double()).float()
+    assert (out - ref).abs().max() <= 2.0 ** -13 * ref.abs().max()

@@ -127,3 +127,38 @@ def test_errors_are_loud(cuda_device):
     m.train()
     with pytest.raises(FiError):
         m(torch.zeros(1, 1, 32, 32, device=cuda_device), torch.zeros(1, 1, 32, 32, device=cuda_device))
+
+
+@pytest.mark.parametrize("bilinear", [False, True])
+def test_fp32_path_meets_1e_3(cuda_device, bilinear):
+    """precision='fp32' (hi/lo-split operands, 3 products per MAC): north-star bar max |err| <= 1e-3 in [0,1] pixel units
+    on the STRESSED fixture (the default-init fixture would pass even in bf16), PSNR far above 45 dB, per-layer taps
+    at fp32-grade relative error."""
+    n, h, w = 1, 70, 118  # odd sizes: F.pad path in two decoder levels
+    f1, f2 = frames(11, n, 1, h, w), frames(12, n, 1, h, w)
+    x = torch.cat([O.preprocess_u8(f1.numpy()), O.preprocess_u8(f2.numpy())], 1)
+    sd = O.calibrate_head(O.stress_state_dict(O.init_state_dict(0, 2, 1, bilinear), seed=1), x)
+    taps = {}
+    ref = O.unet_forward(sd, x, taps)
+    m = build(sd, cuda_device, bilinear=bilinear)
+    m.precision = "fp32"
+    got = m(x[:, :1].to(cuda_device), x[:, 1:].to(cuda_device)).cpu()
+    err = (got - ref).abs().max().item() / 2
+    psnr = psnr_unit(got / 2, ref / 2)
+    print(f"fp32 path bilinear={bilinear}: max abs {err:.2e} psnr {psnr:.1f} dB")
+    assert err <= 1e-3, f"max abs pixel error {err}"
+    assert psnr >= 80.0
+    net = m._fi_net
+    for name in ("inc", "down2", "down4", "up1.up", "up2", "up3"):
+        a, b = net.read_activation(name, n), taps[name]
+        rel = (a - b).norm() / (b.norm() + 1e-12)
+        assert rel < 1e-4, f"layer {name}: relative L2 error {rel:.2e}"
+    # same module back in bf16: engine is rebuilt, result changes but stays inside the bf16 bar
+    m.precision = "bf16"
+    got16 = m(x[:, :1].to(cuda_device), x[:, 1:].to(cuda_device)).cpu()
+    assert 1e-3 < (got16 - ref).abs().max().item() / 2 <= 2e-2
+    # the u8 output of the fp32 path equals the oracle's post-processed frame except at truncation boundaries
+    m.precision = "fp32"
+    out_u8 = m.forward_u8(f1.to(cuda_device), f2.to(cuda_device)).cpu().numpy()
+    d = np.abs(out_u8.astype(np.int32) - O.postprocess(ref).astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 0.02
