@@ -162,3 +162,19 @@ def test_fp32_path_meets_1e_3(cuda_device, bilinear):
     out_u8 = m.forward_u8(f1.to(cuda_device), f2.to(cuda_device)).cpu().numpy()
     d = np.abs(out_u8.astype(np.int32) - O.postprocess(ref).astype(np.int32))
     assert d.max() <= 1 and (d > 0).mean() < 0.02
+
+
+def test_all_modes_small_clip(cuda_device):
+    """Every kernel variant on one odd-sized clip: ConvT/bilinear x bf16/fp32, pipelined clip entry point, metrics."""
+    from model import _engine as E
+    rs = np.random.RandomState(0)
+    f = rs.randint(0, 256, size=(4, 1, 38, 54)).astype(np.uint8)
+    for bilinear in (False, True):
+        sd = O.init_state_dict(0, 2, 1, bilinear)
+        ref = O.postprocess(O.unet_forward(sd, torch.cat([O.preprocess_u8(f[:-1]), O.preprocess_u8(f[1:])], 1)))
+        for precision, tol in (("bf16", 6), ("fp32", 1)):
+            net = E.Net(cuda_device, 2, 1, bilinear, precision)
+            net.load_state_dict(sd)
+            out = net.interpolate_clip_host_u8(f, pairs_per_batch=2)
+            assert np.abs(out.astype(int) - ref.astype(int)).max() <= tol, (bilinear, precision)
+            net.close()
