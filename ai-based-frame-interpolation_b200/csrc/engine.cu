@@ -87,23 +87,26 @@ struct Step {
     void* dst_lo = nullptr;
     int h = 0, w = 0, C = 0;
     char name[48] = "";
-    double flops = 0;  // algorithmic FLOPs of the launch
-    double bytes = 0;  // algorithmic HBM bytes of the launch (inputs + weights + outputs, each touched once)
+    double flops = 0;  // algorithmic FLOPs of the launch, per image
+    double bytes = 0;  // algorithmic HBM bytes of the launch per image (activations in + out; weights excluded)
+    double weight_bytes = 0;
 };
 
 struct Plan {
-    int N = 0, H = 0, W = 0;
+    int N = 0, H = 0, W = 0;  // N = batch CAPACITY of the arena / tensor maps; any batch <= N runs without re-planning
     DevBuf arena;
     std::map<std::string, Act> acts;
     std::vector<Step> steps;
     int head_step = -1;
-    double flops = 0;
+    int last_n = 0;    // batch of the most recent forward
+    double flops = 0;  // per image
     void reset() {
         steps.clear();
         acts.clear();
         arena.release();
         N = H = W = 0;
         head_step = -1;
+        last_n = 0;
         flops = 0;
     }
 };
@@ -300,7 +303,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int build_plan(fiNet* net, int N, int H, int W) {
     Plan& pl = net->plan;
-    if (pl.N == N && pl.H == H && pl.W == W && pl.arena.p) return FI_OK;
+    if (pl.N >= N && pl.H == H && pl.W == W && pl.arena.p) return FI_OK;
     pl.reset();
     if ((H >> 4) < 1 || (W >> 4) < 1) return fail(FI_ERR_INVALID, "input %dx%d is smaller than 16x16 (4 poolings)", H, W);
 
@@ -368,19 +371,19 @@ int build_plan(fiNet* net, int N, int H, int W) {
         return net->precise ? static_cast<char*>(pl.arena.p) + pl.acts.at(name).off_lo : nullptr;
     };
 
-    pl.flops = 2.0 * N * H * W * 64.0 * 9 * stem.cin;
+    pl.flops = 2.0 * H * W * 64.0 * 9 * stem.cin;
     auto push_conv = [&](fi::ConvDesc d, const std::string& name) -> int {
         Step s;
         s.kind = STEP_CONV;
         d.N = N;
         const char* e = fi::conv_prepare(d, net->num_sms, &s.conv);
         if (e) return fail(FI_ERR_INVALID, "%s", e);
-        pl.flops += s.conv.flops;
+        pl.flops += s.conv.flops / N;
         snprintf(s.name, sizeof s.name, "%s", name.c_str());
-        s.flops = s.conv.flops;
-        const double px = static_cast<double>(N) * d.H * d.W;
-        s.bytes = px * d.c0 * 2 + static_cast<double>(N) * d.h1 * d.w1 * d.c1 * 2 +
-                  static_cast<double>(d.n_total) * d.taps * (d.c0 + d.c1) * 2;
+        s.flops = s.conv.flops / N;
+        const double px = static_cast<double>(d.H) * d.W;
+        s.bytes = px * d.c0 * 2 + static_cast<double>(d.h1) * d.w1 * d.c1 * 2;
+        s.weight_bytes = static_cast<double>(d.n_total) * d.taps * (d.c0 + d.c1) * 2;
         if (d.mode == fi::EPI_HEAD) s.bytes += px * d.n_classes * 4;
         else s.bytes += px * d.n_total * 2 * (d.mode == fi::EPI_STORE_POOL ? 1.25 : 1.0);
         pl.steps.push_back(s);
@@ -438,8 +441,8 @@ int build_plan(fiNet* net, int N, int H, int W) {
         s.dst = ptr("inc.mid");
         s.dst_lo = ptr_lo("inc.mid");
         snprintf(s.name, sizeof s.name, "inc.double_conv.0");
-        s.flops = 2.0 * N * H * W * 64.0 * 9 * stem.cin;
-        s.bytes = static_cast<double>(N) * H * W * (stem.cin * 4.0 + 128.0);
+        s.flops = 2.0 * H * W * 64.0 * 9 * stem.cin;
+        s.bytes = static_cast<double>(H) * W * (stem.cin * 4.0 + 128.0);
         pl.steps.push_back(s);
     }
     if ((rc = conv3(0, "inc.mid", "", "inc", "pool1", fi::EPI_STORE_POOL))) return rc;
@@ -471,7 +474,7 @@ int build_plan(fiNet* net, int N, int H, int W) {
             s.w = lo.W;
             s.C = lo.C;
             snprintf(s.name, sizeof s.name, "up%d.up", i + 1);
-            s.bytes = static_cast<double>(N) * lo.H * lo.W * lo.C * 2 * 5.0;
+            s.bytes = static_cast<double>(lo.H) * lo.W * lo.C * 2 * 5.0;
             pl.steps.push_back(s);
         } else {
             fi::ConvDesc d;
@@ -671,6 +674,7 @@ int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dt
     if ((rc = build_plan(net, N, H, W))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Plan& pl = net->plan;
+    pl.last_n = N;
     cudaEvent_t* evs = nullptr;
     if (net->profiling) {
         const size_t base = net->prof_events.size();
@@ -704,6 +708,10 @@ int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dt
                 s.conv.p.out_f32 = out_f32;
                 s.conv.p.out_u8 = out_u8;
             }
+            // the plan's arena and tensor maps are sized for pl.N images; this call uses the first N of them
+            s.conv.p.n_img = N;
+            const long long tiles = static_cast<long long>(s.conv.p.n_blocks) * N * s.conv.p.tiles_y * s.conv.p.tiles_x;
+            s.conv.grid = static_cast<int>(tiles < net->num_sms ? tiles : net->num_sms);
             KERNEL_TRY(fi::conv_launch(s.conv, st));
         }
         if (evs) CUDA_TRY(cudaEventRecord(evs[2 * i + 1], st));
@@ -737,8 +745,8 @@ int fiNetGetProfile(fiNet* net, fiLaunchProfile* out, int capacity, int* count) 
         memset(&out[i], 0, sizeof out[i]);
         snprintf(out[i].name, sizeof out[i].name, "%s", s.name);
         out[i].kind = s.kind == STEP_CONV ? 1 : (s.kind == STEP_STEM ? 0 : 2);
-        out[i].flops = s.flops;
-        out[i].bytes = s.bytes;
+        out[i].flops = s.flops * pl.last_n;
+        out[i].bytes = s.bytes * pl.last_n + s.weight_bytes;
         out[i].calls = net->prof_calls;
         double ms = 0;
         for (int c = 0; c < net->prof_calls; ++c) {
@@ -889,7 +897,7 @@ int fiNetForwardCost(fiNet* net, int N, int H, int W, double* flops, int* launch
     int rc = set_device(net->device);
     if (rc) return rc;
     if ((rc = build_plan(net, N, H, W))) return rc;
-    if (flops) *flops = net->plan.flops;
+    if (flops) *flops = net->plan.flops * N;
     if (launches) *launches = static_cast<int>(net->plan.steps.size());
     return FI_OK;
 }
@@ -900,7 +908,7 @@ int fiNetReadActivation(fiNet* net, const char* name, float* out_host, int64_t c
     auto it = pl.acts.find(name);
     if (!pl.arena.p || it == pl.acts.end()) return fail(FI_ERR_INVALID, "no activation named '%s' in the current plan", name);
     const Act& a = it->second;
-    const int64_t n = static_cast<int64_t>(pl.N) * a.C * a.H * a.W;
+    const int64_t n = static_cast<int64_t>(pl.last_n) * a.C * a.H * a.W;
     if (capacity < n) return fail(FI_ERR_INVALID, "buffer too small: need %lld floats", static_cast<long long>(n));
     int rc = set_device(net->device);
     if (rc) return rc;
@@ -912,7 +920,7 @@ int fiNetReadActivation(fiNet* net, const char* name, float* out_host, int64_t c
         CUDA_TRY(cudaMemcpy(raw_lo.data(), static_cast<char*>(pl.arena.p) + a.off_lo, raw.size() * 2,
                             cudaMemcpyDeviceToHost));
     }
-    for (int nn = 0; nn < pl.N; ++nn)
+    for (int nn = 0; nn < pl.last_n; ++nn)
         for (int y = 0; y < a.H; ++y)
             for (int x = 0; x < a.W; ++x)
                 for (int c = 0; c < a.C; ++c) {

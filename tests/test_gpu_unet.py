@@ -178,3 +178,22 @@ def test_all_modes_small_clip(cuda_device):
             out = net.interpolate_clip_host_u8(f, pairs_per_batch=2)
             assert np.abs(out.astype(int) - ref.astype(int)).max() <= tol, (bilinear, precision)
             net.close()
+
+
+def test_batch_sizes_share_one_plan(cuda_device):
+    """The arena / tensor maps are sized for the largest batch seen; smaller batches reuse them (ragged last batch of a
+    clip, API requests of varying size) and give bit-identical per-image results."""
+    from model import _engine as E
+    sd = O.init_state_dict(0, 2, 1, False)
+    net = E.Net(cuda_device, 2, 1, False)
+    net.load_state_dict(sd)
+    f = frames(21, 5, 1, 48, 80).to(cuda_device)
+    full = net.forward(f[:4], f[1:5], want_f32=True)[0].clone()
+    one = net.forward(f[2:3], f[3:4], want_f32=True)[0].clone()
+    two = net.forward(f[1:3], f[2:4], want_f32=True)[0].clone()
+    assert torch.equal(one[0], full[2]) and torch.equal(two, full[1:3])
+    fl4, launches = net.cost(4, 48, 80)
+    fl1, _ = net.cost(1, 48, 80)
+    assert abs(fl4 - 4 * fl1) < 1 and abs(fl1 - O.flops_per_forward(1, 48, 80)) < 1 and launches == 22
+    again = net.forward(f[:4], f[1:5], want_f32=True)[0]
+    assert torch.equal(again, full)
