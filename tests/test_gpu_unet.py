@@ -197,3 +197,34 @@ def test_batch_sizes_share_one_plan(cuda_device):
     assert abs(fl4 - 4 * fl1) < 1 and abs(fl1 - O.flops_per_forward(1, 48, 80)) < 1 and launches == 22
     again = net.forward(f[:4], f[1:5], want_f32=True)[0]
     assert torch.equal(again, full)
+
+
+def test_random_shape_fuzz(cuda_device):
+    """Seeded shape fuzz (the reference pins nothing but one output shape): random odd/even sizes down to the 16x16
+    minimum, batches 1-3, both decoders, compared with the oracle on the output and on the deepest tap."""
+    from model import _engine as E
+    rs = np.random.RandomState(2024)
+    nets = {}
+    for case in range(14):
+        bilinear = bool(case % 2)
+        n, h, w = int(rs.randint(1, 4)), int(rs.randint(16, 90)), int(rs.randint(16, 130))
+        if case == 0:
+            n, h, w = 1, 16, 16
+        if case == 1:
+            n, h, w = 2, 17, 31
+        if bilinear not in nets:
+            sd = O.init_state_dict(0, 2, 1, bilinear)
+            net = E.Net(cuda_device, 2, 1, bilinear)
+            net.load_state_dict(sd)
+            nets[bilinear] = (sd, net)
+        sd, net = nets[bilinear]
+        f1 = torch.from_numpy(rs.randint(0, 256, size=(n, 1, h, w)).astype(np.uint8))
+        f2 = torch.from_numpy(rs.randint(0, 256, size=(n, 1, h, w)).astype(np.uint8))
+        taps = {}
+        ref = O.unet_forward(sd, torch.cat([O.preprocess_u8(f1.numpy()), O.preprocess_u8(f2.numpy())], 1), taps)
+        got = net.forward(f1.to(cuda_device), f2.to(cuda_device), want_f32=True)[0].cpu()
+        assert got.shape == ref.shape, (n, h, w)
+        rel = ((got - ref).norm() / ref.norm()).item()
+        deep = net.read_activation("down4", n)
+        rel_deep = ((deep - taps["down4"]).norm() / (taps["down4"].norm() + 1e-12)).item()
+        assert rel < 2e-2 and rel_deep < 2e-2, (bilinear, n, h, w, rel, rel_deep)
