@@ -14,6 +14,7 @@
 // Both land in 128B-swizzled K-major smem tiles that tcgen05.mma reads through shared-memory descriptors.
 // Accumulators: fp32 in TMEM, double buffered (2 x BLOCK_N columns) so the epilogue of tile i overlaps tile i+1.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
+#include "conv_epilogue.cuh"
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
 
@@ -199,160 +200,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 64; ++c) {
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32b_x32(taddr + c * 64, v0);
-                tmem_ld_32x32b_x32(taddr + c * 64 + 32, v1);
-                tmem_ld_wait();
-                const int n_glob = tc.nb * BLOCK_N + c * 64;
-                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n_glob);
-                float f[64];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b = __ldg(bias4 + j);
-                    f[4 * j + 0] = __uint_as_float(v0[4 * j + 0]) + b.x;
-                    f[4 * j + 1] = __uint_as_float(v0[4 * j + 1]) + b.y;
-                    f[4 * j + 2] = __uint_as_float(v0[4 * j + 2]) + b.z;
-                    f[4 * j + 3] = __uint_as_float(v0[4 * j + 3]) + b.w;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b = __ldg(bias4 + 8 + j);
-                    f[32 + 4 * j + 0] = __uint_as_float(v1[4 * j + 0]) + b.x;
-                    f[32 + 4 * j + 1] = __uint_as_float(v1[4 * j + 1]) + b.y;
-                    f[32 + 4 * j + 2] = __uint_as_float(v1[4 * j + 2]) + b.z;
-                    f[32 + 4 * j + 3] = __uint_as_float(v1[4 * j + 3]) + b.w;
-                }
-                if (p.relu) {
-#pragma unroll
-                    for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
-                }
-
-                if constexpr (MODE == EPI_HEAD) {
-                    // 1x1 head on the fp32 (un-rounded) activations; thread = pixel.
-                    const int y = tc.y0 + 2 * q + (lane >> 4);
-                    const int x = tc.x0 + (lane & 15);
-                    const bool inside = (y < p.H) && (x < p.W);
-                    for (int k = 0; k < p.n_classes; ++k) {
-                        const float4* w4 = reinterpret_cast<const float4*>(p.head_w + k * 64);
-                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float4 w = __ldg(w4 + j);
-                            a0 = fmaf(f[4 * j + 0], w.x, a0);
-                            a1 = fmaf(f[4 * j + 1], w.y, a1);
-                            a2 = fmaf(f[4 * j + 2], w.z, a2);
-                            a3 = fmaf(f[4 * j + 3], w.w, a3);
-                        }
-                        const float yv = (a0 + a1) + (a2 + a3) + __ldg(p.head_b + k);
-                        if (inside) {
-                            const size_t o = ((static_cast<size_t>(tc.img) * p.n_classes + k) * p.H + y) * p.W + x;
-                            if (p.out_f32) p.out_f32[o] = yv;
-                            if (p.out_u8) {
-                                // postprocess_image (reference model/inference.py:54-61): (t+1)/2, clamp, *255, truncate
-                                float u = __fmul_rn(__fadd_rn(yv, 1.0f), 0.5f);
-                                u = fminf(fmaxf(u, 0.0f), 1.0f);
-                                p.out_u8[o] = static_cast<uint8_t>(__fmul_rn(u, 255.0f));
-                            }
-                        }
-                    }
-                } else if constexpr (!SPLIT) {
-                    uint32_t pk[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                    // The staging buffer used two chunks ago must have been read by its TMA store.
-                    if (elect_one()) tma_store_wait_read<1>();
-                    __syncwarp();
-                    const uint32_t sbuf = my_stage + buf * 4096;
-                    const uint32_t row = sbuf + lane * 128;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        st_shared_v4(row + ((j ^ (lane & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2],
-                                     pk[4 * j + 3]);
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (elect_one()) {
-                        if constexpr (MODE == EPI_CONVT) {
-                            const int a = n_glob / p.cout2;
-                            tma_store_5d(&maps.out[0], sbuf, n_glob - a * p.cout2, tc.x0, a, tc.y0 + 2 * q, tc.img);
-                        } else {
-                            tma_store_4d(&maps.out[0], sbuf, n_glob, tc.x0, tc.y0 + 2 * q, tc.img);
-                        }
-                    }
-                    if constexpr (MODE == EPI_STORE_POOL) {
-                        // 2x2 max over (rows 2q,2q+1) x (cols 2p,2p+1): bf16 max commutes with the rounding above.
-                        const uint32_t pbuf = my_pool + buf * 1024;
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const int pp = lane >> 2;
-                            const int j = (lane & 3) * 2 + i;
-                            const int r0 = 2 * pp, r1 = 2 * pp + 1, r2 = 16 + 2 * pp, r3 = 17 + 2 * pp;
-                            const uint4 m0 = ld_shared_v4(sbuf + r0 * 128 + ((j ^ (r0 & 7)) << 4));
-                            const uint4 m1 = ld_shared_v4(sbuf + r1 * 128 + ((j ^ (r1 & 7)) << 4));
-                            const uint4 m2 = ld_shared_v4(sbuf + r2 * 128 + ((j ^ (r2 & 7)) << 4));
-                            const uint4 m3 = ld_shared_v4(sbuf + r3 * 128 + ((j ^ (r3 & 7)) << 4));
-                            uint4 m;
-                            m.x = bf16x2_max(bf16x2_max(m0.x, m1.x), bf16x2_max(m2.x, m3.x));
-                            m.y = bf16x2_max(bf16x2_max(m0.y, m1.y), bf16x2_max(m2.y, m3.y));
-                            m.z = bf16x2_max(bf16x2_max(m0.z, m1.z), bf16x2_max(m2.z, m3.z));
-                            m.w = bf16x2_max(bf16x2_max(m0.w, m1.w), bf16x2_max(m2.w, m3.w));
-                            st_shared_v4(pbuf + pp * 128 + ((j ^ (pp & 7)) << 4), m.x, m.y, m.z, m.w);
-                        }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (elect_one()) {
-                            tma_store_4d(&maps.pool[0], pbuf, n_glob, tc.x0 >> 1, (tc.y0 >> 1) + q, tc.img);
-                        }
-                    }
-                    if (elect_one()) tma_store_commit();
-                    buf ^= 1;
-                } else {
-                    // precise mode: value = hi + lo, both bf16; the two staging buffers hold the hi and the lo tile
-                    uint32_t pk[32], pl[32];
-                    split_hi_lo(f, pk, pl);
-                    if (elect_one()) tma_store_wait_read<0>();
-                    __syncwarp();
-                    const uint32_t shi = my_stage, slo = my_stage + 4096;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t o = lane * 128 + ((j ^ (lane & 7)) << 4);
-                        st_shared_v4(shi + o, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                        st_shared_v4(slo + o, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (elect_one()) {
-                        if constexpr (MODE == EPI_CONVT) {
-                            const int a = n_glob / p.cout2;
-                            tma_store_5d(&maps.out[0], shi, n_glob - a * p.cout2, tc.x0, a, tc.y0 + 2 * q, tc.img);
-                            tma_store_5d(&maps.out[1], slo, n_glob - a * p.cout2, tc.x0, a, tc.y0 + 2 * q, tc.img);
-                        } else {
-                            tma_store_4d(&maps.out[0], shi, n_glob, tc.x0, tc.y0 + 2 * q, tc.img);
-                            tma_store_4d(&maps.out[1], slo, n_glob, tc.x0, tc.y0 + 2 * q, tc.img);
-                        }
-                    }
-                    if constexpr (MODE == EPI_STORE_POOL) {
-                        const uint32_t phi = my_pool, plo = my_pool + 1024;
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const int pp = lane >> 2;
-                            const int j = (lane & 3) * 2 + i;
-                            const int rows[4] = {2 * pp, 2 * pp + 1, 16 + 2 * pp, 17 + 2 * pp};
-                            uint4 mh, ml;
-                            pool4_hi_lo(shi, slo, rows, j, mh, ml);
-                            const uint32_t o = pp * 128 + ((j ^ (pp & 7)) << 4);
-                            st_shared_v4(phi + o, mh.x, mh.y, mh.z, mh.w);
-                            st_shared_v4(plo + o, ml.x, ml.y, ml.z, ml.w);
-                        }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (elect_one()) {
-                            tma_store_4d(&maps.pool[0], phi, n_glob, tc.x0 >> 1, (tc.y0 >> 1) + q, tc.img);
-                            tma_store_4d(&maps.pool[1], plo, n_glob, tc.x0 >> 1, (tc.y0 >> 1) + q, tc.img);
-                        }
-                    }
-                    if (elect_one()) tma_store_commit();
-                }
+                epilogue_chunk_8x16<BLOCK_N, MODE, SPLIT>(maps, p, EpiTile{tc.nb, tc.img, tc.y0, tc.x0}, taddr, c, q, lane,
+                                                           my_stage, my_pool, buf, true);
             }
             // All TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back to the MMA warp.
             tc_fence_before();
@@ -504,10 +353,22 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     }
     const int kmul = precise ? 3 : 1;
     {
+        // CTA pairs halve the weight traffic per SM. Not for the transposed convs with a short K: they are bound by
+        // their scatter store, and the pair only adds synchronisation there (measured: up4.up 0.31 -> 0.42 ms).
+        // Nor for the 64->64 layers (inc.3, up4.3): their weights are already resident in the single-CTA halo kernel
+        // and they are HBM-heavy; coupling two CTAs in lockstep costs more than the halved B reads save
+        // (measured: inc.3 0.62 -> 0.83 ms). FI_CTA2=0 forces the single-CTA kernels everywhere (tests use it).
+        const char* cta2 = getenv("FI_CTA2");
+        const bool want = cta2 ? cta2[0] != '0' : true;
+        const bool narrow_resident = l.halo && d.n_total == 64 && kmul * (d.c0 + d.c1) == BLOCK_K;
+        l.pair = want && ((l.halo && !narrow_resident) || (!l.halo && block_n == 256 && d.mode != EPI_HEAD &&
+                                                            (d.mode != EPI_CONVT || d.c0 >= 1024)));
+    }
+    {
         const uint64_t k_total = static_cast<uint64_t>(d.taps) * kmul * (d.c0 + d.c1);
         const uint64_t dims[2] = {k_total, static_cast<uint64_t>(d.n_total)};
         const uint64_t strides[1] = {k_total};
-        const uint32_t box[2] = {64, static_cast<uint32_t>(block_n)};
+        const uint32_t box[2] = {64, static_cast<uint32_t>(l.pair ? block_n / 2 : block_n)};  // pair: half a slab per CTA
         if ((e = encode_bf16_map(&m.b, d.wpack, 2, dims, strides, box))) return e;
     }
     m.out[0] = m.out[1] = m.pool[0] = m.pool[1] = m.a[0];
@@ -575,6 +436,12 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     const long long total = static_cast<long long>(p.n_blocks) * p.n_img * p.tiles_y * p.tiles_x;
     if (total > 0x7fffffffLL) return "conv: too many tiles";
     l.grid = static_cast<int>(total < num_sms ? total : num_sms);
+    if (l.pair) {
+        const long long m_tiles = static_cast<long long>(p.n_img) * p.tiles_y * p.tiles_x;
+        const long long pairs = p.n_blocks * ((m_tiles + 1) / 2);
+        const long long clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
+        l.grid = static_cast<int>(2 * clusters);
+    }
     l.flops = 2.0 * d.N * d.H * d.W * static_cast<double>(d.n_total) * d.taps * (d.c0 + d.c1);
     if (d.mode == EPI_HEAD) l.flops += 2.0 * d.N * d.H * d.W * 64.0 * d.n_classes;
     *out = l;
@@ -582,7 +449,8 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
 }
 
 const char* conv_launch(const ConvLaunch& l, cudaStream_t stream) {
-    if (l.halo) return conv_halo_launch(l, stream);
+    if (l.halo) return l.pair ? conv_halo_pair_launch(l, stream) : conv_halo_launch(l, stream);
+    if (l.pair) return conv_pair_launch(l, stream);
     switch (l.block_n * 4 + l.mode) {
         case 64 * 4 + EPI_STORE: return launch_inst<64, EPI_STORE>(l, stream);
         case 64 * 4 + EPI_STORE_POOL: return launch_inst<64, EPI_STORE_POOL>(l, stream);

@@ -11,6 +11,7 @@
 // (validated on B200 against the oracle; p.desc_mode keeps the descriptor's base-offset alternative selectable).
 // Weights stream per (tap, slab) through their own ring. Warp roles (224 threads): 0 = A producer, 1 = TMEM owner +
 // MMA issuer, 2 = B producer, 3..6 = epilogue. TMEM: 2 accumulator sets x 2 halves x Cout columns.
+#include "conv_epilogue.cuh"
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
 
@@ -270,149 +271,8 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS;
 #pragma unroll 1
             for (int c = 0; c < ACC_COLS / 64; ++c) {
-                const int half = c / (COUT / 64);
-                const int n_glob = (c % (COUT / 64)) * 64;
-                const int xh = tc.x0 + 8 * half;  // first column of this half
-                const int yq = tc.y0 + 4 * q;     // first row of this warp
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32b_x32(taddr + c * 64, v0);
-                tmem_ld_32x32b_x32(taddr + c * 64 + 32, v1);
-                tmem_ld_wait();
-                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n_glob);
-                float f[64];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b = __ldg(bias4 + j);
-                    f[4 * j + 0] = __uint_as_float(v0[4 * j + 0]) + b.x;
-                    f[4 * j + 1] = __uint_as_float(v0[4 * j + 1]) + b.y;
-                    f[4 * j + 2] = __uint_as_float(v0[4 * j + 2]) + b.z;
-                    f[4 * j + 3] = __uint_as_float(v0[4 * j + 3]) + b.w;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b = __ldg(bias4 + 8 + j);
-                    f[32 + 4 * j + 0] = __uint_as_float(v1[4 * j + 0]) + b.x;
-                    f[32 + 4 * j + 1] = __uint_as_float(v1[4 * j + 1]) + b.y;
-                    f[32 + 4 * j + 2] = __uint_as_float(v1[4 * j + 2]) + b.z;
-                    f[32 + 4 * j + 3] = __uint_as_float(v1[4 * j + 3]) + b.w;
-                }
-                if (p.relu) {
-#pragma unroll
-                    for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
-                }
-
-                if constexpr (MODE == EPI_HEAD) {
-                    const int y = yq + (lane >> 3);
-                    const int x = xh + (lane & 7);
-                    const bool inside = (y < p.H) && (x < p.W);
-                    for (int k = 0; k < p.n_classes; ++k) {
-                        const float4* w4 = reinterpret_cast<const float4*>(p.head_w + k * 64);
-                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float4 w = __ldg(w4 + j);
-                            a0 = fmaf(f[4 * j + 0], w.x, a0);
-                            a1 = fmaf(f[4 * j + 1], w.y, a1);
-                            a2 = fmaf(f[4 * j + 2], w.z, a2);
-                            a3 = fmaf(f[4 * j + 3], w.w, a3);
-                        }
-                        const float yv = (a0 + a1) + (a2 + a3) + __ldg(p.head_b + k);
-                        if (inside) {
-                            const size_t o = ((static_cast<size_t>(tc.img) * p.n_classes + k) * p.H + y) * p.W + x;
-                            if (p.out_f32) p.out_f32[o] = yv;
-                            if (p.out_u8) {
-                                float u = __fmul_rn(__fadd_rn(yv, 1.0f), 0.5f);
-                                u = fminf(fmaxf(u, 0.0f), 1.0f);
-                                p.out_u8[o] = static_cast<uint8_t>(__fmul_rn(u, 255.0f));
-                            }
-                        }
-                    }
-                } else if constexpr (!SPLIT) {
-                    uint32_t pk[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                    if (elect_one()) tma_store_wait_read<1>();
-                    __syncwarp();
-                    const uint32_t sbuf = my_stage + buf * 4096;
-                    const uint32_t row = sbuf + lane * 128;  // lane = (row in 0..3) * 8 + column
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        st_shared_v4(row + ((j ^ (lane & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2],
-                                     pk[4 * j + 3]);
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (elect_one()) tma_store_4d(&maps.out[0], sbuf, n_glob, xh, yq, tc.img);  // box {64, 8, 4, 1}
-                    if constexpr (MODE == EPI_STORE_POOL) {
-                        // pooled 2 rows x 4 columns: max over lanes {2ph*8 + 2pw, +1, +8, +9}
-                        const uint32_t pbuf = my_pool + buf * 1024;
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const int pp = lane >> 2;  // pooled pixel 0..7 = ph*4 + pw
-                            const int j = (lane & 3) * 2 + i;
-                            const int r0 = (pp >> 2) * 16 + (pp & 3) * 2;
-                            const int r1 = r0 + 1, r2 = r0 + 8, r3 = r0 + 9;
-                            const uint4 m0 = ld_shared_v4(sbuf + r0 * 128 + ((j ^ (r0 & 7)) << 4));
-                            const uint4 m1 = ld_shared_v4(sbuf + r1 * 128 + ((j ^ (r1 & 7)) << 4));
-                            const uint4 m2 = ld_shared_v4(sbuf + r2 * 128 + ((j ^ (r2 & 7)) << 4));
-                            const uint4 m3 = ld_shared_v4(sbuf + r3 * 128 + ((j ^ (r3 & 7)) << 4));
-                            uint4 m;
-                            m.x = bf16x2_max(bf16x2_max(m0.x, m1.x), bf16x2_max(m2.x, m3.x));
-                            m.y = bf16x2_max(bf16x2_max(m0.y, m1.y), bf16x2_max(m2.y, m3.y));
-                            m.z = bf16x2_max(bf16x2_max(m0.z, m1.z), bf16x2_max(m2.z, m3.z));
-                            m.w = bf16x2_max(bf16x2_max(m0.w, m1.w), bf16x2_max(m2.w, m3.w));
-                            st_shared_v4(pbuf + pp * 128 + ((j ^ (pp & 7)) << 4), m.x, m.y, m.z, m.w);
-                        }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (elect_one()) {
-                            tma_store_4d(&maps.pool[0], pbuf, n_glob, xh >> 1, yq >> 1, tc.img);  // box {64, 4, 2, 1}
-                        }
-                    }
-                    if (elect_one()) tma_store_commit();
-                    buf ^= 1;
-                } else {
-                    // precise mode: hi tile in staging buffer 0, lo tile in buffer 1
-                    uint32_t pk[32], pl[32];
-                    split_hi_lo(f, pk, pl);
-                    if (elect_one()) tma_store_wait_read<0>();
-                    __syncwarp();
-                    const uint32_t shi = my_stage, slo = my_stage + 4096;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t o = lane * 128 + ((j ^ (lane & 7)) << 4);
-                        st_shared_v4(shi + o, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                        st_shared_v4(slo + o, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (elect_one()) {
-                        tma_store_4d(&maps.out[0], shi, n_glob, xh, yq, tc.img);
-                        tma_store_4d(&maps.out[1], slo, n_glob, xh, yq, tc.img);
-                    }
-                    if constexpr (MODE == EPI_STORE_POOL) {
-                        const uint32_t phi = my_pool, plo = my_pool + 1024;
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const int pp = lane >> 2;
-                            const int j = (lane & 3) * 2 + i;
-                            const int r0 = (pp >> 2) * 16 + (pp & 3) * 2;
-                            const int rows[4] = {r0, r0 + 1, r0 + 8, r0 + 9};
-                            uint4 mh, ml;
-                            pool4_hi_lo(shi, slo, rows, j, mh, ml);
-                            const uint32_t o = pp * 128 + ((j ^ (pp & 7)) << 4);
-                            st_shared_v4(phi + o, mh.x, mh.y, mh.z, mh.w);
-                            st_shared_v4(plo + o, ml.x, ml.y, ml.z, ml.w);
-                        }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (elect_one()) {
-                            tma_store_4d(&maps.pool[0], phi, n_glob, xh >> 1, yq >> 1, tc.img);
-                            tma_store_4d(&maps.pool[1], plo, n_glob, xh >> 1, yq >> 1, tc.img);
-                        }
-                    }
-                    if (elect_one()) tma_store_commit();
-                }
+                epilogue_chunk_halo<COUT, MODE, SPLIT>(maps, p, HaloTile{tc.img, tc.y0, tc.x0}, taddr, c, q, lane, my_stage,
+                                                       my_pool, buf, true);
             }
             tc_fence_before();
             __syncwarp();

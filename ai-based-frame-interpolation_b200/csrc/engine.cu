@@ -710,8 +710,14 @@ int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dt
             }
             // the plan's arena and tensor maps are sized for pl.N images; this call uses the first N of them
             s.conv.p.n_img = N;
-            const long long tiles = static_cast<long long>(s.conv.p.n_blocks) * N * s.conv.p.tiles_y * s.conv.p.tiles_x;
-            s.conv.grid = static_cast<int>(tiles < net->num_sms ? tiles : net->num_sms);
+            const long long m_tiles = static_cast<long long>(N) * s.conv.p.tiles_y * s.conv.p.tiles_x;
+            if (s.conv.pair) {
+                const long long pairs = s.conv.p.n_blocks * ((m_tiles + 1) / 2);
+                s.conv.grid = static_cast<int>(2 * (pairs < net->num_sms / 2 ? pairs : net->num_sms / 2));
+            } else {
+                const long long tiles = s.conv.p.n_blocks * m_tiles;
+                s.conv.grid = static_cast<int>(tiles < net->num_sms ? tiles : net->num_sms);
+            }
             KERNEL_TRY(fi::conv_launch(s.conv, st));
         }
         if (evs) CUDA_TRY(cudaEventRecord(evs[2 * i + 1], st));

@@ -11,10 +11,12 @@ from layer_utils import bf16_round, ref_conv3x3, run_conv, run_conv_precise
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["halo", "per-tap"], autouse=True)
+@pytest.fixture(params=["halo", "per-tap", "pair"], autouse=True)
 def kernel_variant(request, monkeypatch):
-    """Cout 64/128 layers have two kernels (conv_halo.cu / conv_gemm.cu); run every case through both."""
-    monkeypatch.setenv("FI_NO_HALO", "0" if request.param == "halo" else "1")
+    """Cout 64/128 layers have two kernels (conv_halo.cu / conv_gemm.cu) and Cout multiples of 256 have the single-CTA
+    and the CTA-pair kernel (conv_gemm.cu / conv_gemm2.cu); run every case through all selections."""
+    monkeypatch.setenv("FI_NO_HALO", "1" if request.param == "per-tap" else "0")
+    monkeypatch.setenv("FI_CTA2", "1" if request.param == "pair" else "0")
     return request.param
 
 
