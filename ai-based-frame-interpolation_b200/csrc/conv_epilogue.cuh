@@ -177,7 +177,9 @@ struct HaloTile {
     int img, y0, x0;
 };
 
-template <int COUT, int MODE, bool SPLIT>
+// DOUBLE_BUF: two staging tiles per warp alternate (wait for the store before last); otherwise one tile per warp (eight
+// epilogue warps share the same 40 KB) and the previous store must have drained.
+template <int COUT, int MODE, bool SPLIT, bool DOUBLE_BUF>
 __device__ __forceinline__ void epilogue_chunk_halo(const ConvMaps& maps, const ConvKernelParams& p, const HaloTile& tc,
                                                     uint32_t taddr, int c, int q, int lane, uint32_t my_stage,
                                                     uint32_t my_pool, int& buf, bool store_enabled) {
@@ -242,9 +244,12 @@ __device__ __forceinline__ void epilogue_chunk_halo(const ConvMaps& maps, const 
         uint32_t pk[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-        if (elect_one()) tma_store_wait_read<1>();
+        if (elect_one()) {
+            if (DOUBLE_BUF) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+        }
         __syncwarp();
-        const uint32_t sbuf = my_stage + buf * 4096;
+        const uint32_t sbuf = my_stage + (DOUBLE_BUF ? buf * 4096 : 0);
         const uint32_t row = sbuf + lane * 128;  // lane = (row in 0..3) * 8 + column
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -256,7 +261,7 @@ __device__ __forceinline__ void epilogue_chunk_halo(const ConvMaps& maps, const 
         if (store_enabled && elect_one()) tma_store_4d(&maps.out[0], sbuf, n_glob, xh, yq, tc.img);  // box {64, 8, 4, 1}
         if constexpr (MODE == EPI_STORE_POOL) {
             // pooled 2 rows x 4 columns: max over lanes {2ph*8 + 2pw, +1, +8, +9}
-            const uint32_t pbuf = my_pool + buf * 1024;
+            const uint32_t pbuf = my_pool + (DOUBLE_BUF ? buf * 1024 : 0);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int pp = lane >> 2;  // pooled pixel 0..7 = ph*4 + pw

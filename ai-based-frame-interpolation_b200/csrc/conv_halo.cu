@@ -25,7 +25,8 @@ namespace {
 constexpr int HT = 16;                                 // super tile: 16 x 16 output pixels
 constexpr int HALO_W = 24, HALO_H = 18;                // TMA box (pixels): 16+2 columns padded to 24, 16+2 rows
 constexpr int HALO_BYTES = HALO_W * HALO_H * 128;      // 55296
-constexpr int HALO_THREADS = 224;
+constexpr int HALO_THREADS = 224;        // 3 role warps + 4 epilogue warps (precise mode)
+constexpr int HALO_THREADS_8 = 352;      // 3 role warps + 8 epilogue warps (one set per column half)
 constexpr int A_STAGES = 2;
 constexpr int B_RING_BYTES = 65536;
 constexpr int H_STAGING_PER_WARP = 2 * 4096;
@@ -69,7 +70,7 @@ __device__ __forceinline__ HTile decode_htile(int t, const ConvKernelParams& p) 
 }
 
 template <int COUT, int MODE, bool RESIDENT, bool SPLIT>
-__global__ void __launch_bounds__(HALO_THREADS, 1)
+__global__ void __launch_bounds__(SPLIT ? HALO_THREADS : HALO_THREADS_8, 1)
 conv_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p) {
     constexpr int B_STAGES = halo_b_stages(COUT);
     constexpr int B_STAGE_BYTES = halo_b_stage_bytes(COUT);
@@ -77,6 +78,10 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
     constexpr int TMEM_COLS = 2 * ACC_COLS;     // double buffered: 256 (Cout 64) or 512 (Cout 128)
     constexpr uint32_t IDESC = umma_idesc_bf16(128, COUT);
     static_assert(MODE != EPI_HEAD || COUT == 64, "head epilogue consumes exactly 64 channels");
+    // bf16 mode: 8 epilogue warps, one set of 4 per column half, single staging tile each; precise mode: 4 warps
+    constexpr int EPI_SETS = SPLIT ? 1 : 2;
+    constexpr int STAGE_PER_WARP = SPLIT ? 2 * 4096 : 4096;
+    constexpr int POOL_PER_WARP = SPLIT ? 2 * 1024 : 1024;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -114,7 +119,7 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
-            mbar_init(bar_tempty + 8 * a, 4);
+            mbar_init(bar_tempty + 8 * a, 4 * EPI_SETS);
         }
         mbar_init(bar_bres, 1);
         fence_mbar_init();
@@ -258,8 +263,10 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
     } else {
         // ------------------------------------------------------------ epilogue warps 3..6
         const int q = warp & 3;  // TMEM lanes [32q, 32q+32) <-> tile rows 4q..4q+3, 8 columns of one half
-        const uint32_t my_stage = smem_stage + q * H_STAGING_PER_WARP;
-        const uint32_t my_pool = smem_pool + q * H_POOL_PER_WARP;
+        const int ew = warp - 3;          // 0..7 (0..3 in precise mode)
+        const int set = ew >> 2;          // which column half this warp drains (bf16 mode)
+        const uint32_t my_stage = smem_stage + ew * STAGE_PER_WARP;
+        const uint32_t my_pool = smem_pool + ew * POOL_PER_WARP;
         int buf = 0;
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -270,8 +277,8 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS;
 #pragma unroll 1
-            for (int c = 0; c < ACC_COLS / 64; ++c) {
-                epilogue_chunk_halo<COUT, MODE, SPLIT>(maps, p, HaloTile{tc.img, tc.y0, tc.x0}, taddr, c, q, lane, my_stage,
+            for (int c = set * (ACC_COLS / 64 / EPI_SETS); c < (set + 1) * (ACC_COLS / 64 / EPI_SETS); ++c) {
+                epilogue_chunk_halo<COUT, MODE, SPLIT, SPLIT>(maps, p, HaloTile{tc.img, tc.y0, tc.x0}, taddr, c, q, lane, my_stage,
                                                        my_pool, buf, true);
             }
             tc_fence_before();
@@ -307,7 +314,7 @@ const char* launch_halo_inst(const ConvLaunch& l, cudaStream_t stream) {
             return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
         configured = true;
     }
-    kfn<<<l.grid, HALO_THREADS, smem, stream>>>(l.maps, l.p);
+    kfn<<<l.grid, SPLIT ? HALO_THREADS : HALO_THREADS_8, smem, stream>>>(l.maps, l.p);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -24,6 +24,7 @@ constexpr int H2_T = 16;
 constexpr int H2_W = 24, H2_H = 18;
 constexpr int H2_HALO_BYTES = H2_W * H2_H * 128;  // 55296
 constexpr int H2_THREADS = 224;
+constexpr int H2_THREADS_8 = 352;
 constexpr int H2_A_STAGES = 2;
 constexpr int H2_B_BYTES = 73728;                 // weight region: a ring, or up to 72 KB of resident half slabs
 constexpr int H2_STAGING = 4 * (2 * 4096 + 2 * 1024);
@@ -60,7 +61,7 @@ __device__ __forceinline__ PairHTile decode_pair_htile(int qi, uint32_t rank, co
 }
 
 template <int COUT, int MODE, bool RESIDENT, bool SPLIT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SPLIT ? H2_THREADS : H2_THREADS_8, 1)
 conv_halo2_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p) {
     constexpr int B_HALF_BYTES = (COUT / 2) * 128;        // this CTA's half of one [Cout x 64] weight slab
     constexpr int B_STAGES = 65536 / B_HALF_BYTES;        // ring depth when streaming (16 or 8)
@@ -68,6 +69,10 @@ conv_halo2_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams 
     constexpr int TMEM_COLS = 2 * ACC_COLS;
     constexpr uint32_t IDESC = umma_idesc_bf16(256, COUT);
     static_assert(MODE != EPI_HEAD || COUT == 64, "head epilogue consumes exactly 64 channels");
+    // bf16 mode: 8 epilogue warps, one set of 4 per column half, single staging tile each; precise mode: 4 warps
+    constexpr int EPI_SETS = SPLIT ? 1 : 2;
+    constexpr int STAGE_PER_WARP = SPLIT ? 2 * 4096 : 4096;
+    constexpr int POOL_PER_WARP = SPLIT ? 2 * 1024 : 1024;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -109,7 +114,7 @@ conv_halo2_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
-            mbar_init(bar_tempty + 8 * a, 8);
+            mbar_init(bar_tempty + 8 * a, 8 * EPI_SETS);
         }
         mbar_init(bar_bres, 1);
         fence_mbar_init();
@@ -251,8 +256,10 @@ conv_halo2_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams 
     } else {
         // ------------------------------------------------------------ epilogue warps 3..6 (both CTAs)
         const int q = warp & 3;
-        const uint32_t my_stage = smem_stage + q * (2 * 4096);
-        const uint32_t my_pool = smem_pool + q * (2 * 1024);
+        const int ew = warp - 3;
+        const int set = ew >> 2;
+        const uint32_t my_stage = smem_stage + ew * STAGE_PER_WARP;
+        const uint32_t my_pool = smem_pool + ew * POOL_PER_WARP;
         int buf = 0;
         int it = 0;
         for (int qi = cluster_id; qi < total; qi += n_clusters, ++it) {
@@ -262,8 +269,8 @@ conv_halo2_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams 
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS;
 #pragma unroll 1
-            for (int c = 0; c < ACC_COLS / 64; ++c) {
-                epilogue_chunk_halo<COUT, MODE, SPLIT>(maps, p, pt.t, taddr, c, q, lane, my_stage, my_pool, buf,
+            for (int c = set * (ACC_COLS / 64 / EPI_SETS); c < (set + 1) * (ACC_COLS / 64 / EPI_SETS); ++c) {
+                epilogue_chunk_halo<COUT, MODE, SPLIT, SPLIT>(maps, p, pt.t, taddr, c, q, lane, my_stage, my_pool, buf,
                                                        pt.valid);
             }
             tc_fence_before();
@@ -299,7 +306,7 @@ const char* launch_halo2_inst(const ConvLaunch& l, cudaStream_t stream) {
             return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
         configured = true;
     }
-    kfn<<<l.grid, H2_THREADS, H2_SMEM, stream>>>(l.maps, l.p);
+    kfn<<<l.grid, SPLIT ? H2_THREADS : H2_THREADS_8, H2_SMEM, stream>>>(l.maps, l.p);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
