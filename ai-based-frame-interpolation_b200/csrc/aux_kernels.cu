@@ -86,6 +86,29 @@ upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int h,
     }
 }
 
+// ------------------------------------------------------------------------------------------------ max pool 2x2
+// nn.MaxPool2d(2) on bf16 NHWC (floor semantics). Inside the network the pool is fused into the producing conv's
+// epilogue; this kernel serves the stand-alone Down module only.
+__global__ void __launch_bounds__(256)
+maxpool2x2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int H, int W, int c8) {
+    const int oh = H / 2, ow = W / 2;
+    const int n = blockIdx.y / oh, oy = blockIdx.y - n * oh;
+    const uint4* r0 = src + (static_cast<size_t>(n) * H + 2 * oy) * W * c8;
+    const uint4* r1 = r0 + static_cast<size_t>(W) * c8;
+    uint4* out = dst + (static_cast<size_t>(n) * oh + oy) * ow * c8;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < ow * c8; i += gridDim.x * 256) {
+        const int ox = i / c8, cg = i - ox * c8;
+        const uint4 a = __ldg(r0 + (2 * ox) * c8 + cg), b = __ldg(r0 + (2 * ox + 1) * c8 + cg);
+        const uint4 c = __ldg(r1 + (2 * ox) * c8 + cg), d = __ldg(r1 + (2 * ox + 1) * c8 + cg);
+        uint4 m;
+        m.x = bf16x2_max(bf16x2_max(a.x, b.x), bf16x2_max(c.x, d.x));
+        m.y = bf16x2_max(bf16x2_max(a.y, b.y), bf16x2_max(c.y, d.y));
+        m.z = bf16x2_max(bf16x2_max(a.z, b.z), bf16x2_max(c.z, d.z));
+        m.w = bf16x2_max(bf16x2_max(a.w, b.w), bf16x2_max(c.w, d.w));
+        out[i] = m;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ pack / post
 // out[n, k, :, :] = 2*(f[n, k mod C]/255) - 1 with f = f0 for k < C else f1: 16 pixels (one 128-bit load) per thread.
 __global__ void __launch_bounds__(256)
@@ -358,6 +381,16 @@ const char* upsample2x_launch(const void* src, void* dst, int N, int h, int w, i
                                                                 static_cast<uint4*>(dst), h, w, C / 8,
                                                                 static_cast<const uint4*>(src_lo),
                                                                 static_cast<uint4*>(dst_lo));
+    return last_launch_error();
+}
+
+const char* maxpool2x2_launch(const void* src, void* dst, int N, int H, int W, int C, cudaStream_t stream) {
+    if (C % 8) return "maxpool: channels must be a multiple of 8";
+    if (N <= 0 || H < 2 || W < 2) return "maxpool: needs at least a 2x2 image";
+    if (static_cast<long long>(N) * (H / 2) > 65535) return "maxpool: N*(H/2) must be <= 65535 (grid.y)";
+    const int items = (W / 2) * (C / 8);
+    maxpool2x2_kernel<<<dim3((items + 1023) / 1024, N * (H / 2)), 256, 0, stream>>>(
+        static_cast<const uint4*>(src), static_cast<uint4*>(dst), H, W, C / 8);
     return last_launch_error();
 }
 

@@ -32,6 +32,9 @@ void stem_pack_weights(const float* w /*[64][cin][3][3]*/, int cin, uint16_t* ou
 const char* upsample2x_launch(const void* src, void* dst, int N, int h, int w, int C, cudaStream_t stream,
                               const void* src_lo = nullptr, void* dst_lo = nullptr);  // lo halves: precise mode
 
+// nn.MaxPool2d(2) on bf16 NHWC [N,H,W,C] -> [N,H/2,W/2,C] (stand-alone Down module; fused elsewhere).
+const char* maxpool2x2_launch(const void* src, void* dst, int N, int H, int W, int C, cudaStream_t stream);
+
 // Frame-pair packing + normalisation: two u8 planar frame batches [N,C,H,W] -> fp32 NCHW [N,2C,H,W] = cat(2*f/255-1).
 const char* pack_pair_launch(const uint8_t* f0, const uint8_t* f1, float* out, int N, int C, int H, int W,
                              cudaStream_t stream);

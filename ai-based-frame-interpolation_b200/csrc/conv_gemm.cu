@@ -398,8 +398,6 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     p.tiles_x = (d.W + tile_w - 1) / tile_w;
     p.tiles_y = (d.H + tile_h - 1) / tile_h;
     {
-        const char* dm = getenv("FI_HALO_DESC_MODE");
-        p.desc_mode = dm ? atoi(dm) : 0;
         const char* pf = getenv("FI_HALO_PREFETCH");
         p.prefetch_dist = pf ? atoi(pf) : 2;
     }

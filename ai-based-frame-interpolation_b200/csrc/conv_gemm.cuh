@@ -65,7 +65,6 @@ struct ConvKernelParams {
     int H, W;
     int n_classes;
     int prefetch_dist;  // halo kernel: L2-prefetch the halo boxes of the tile this many grid strides ahead (0 = off)
-    int desc_mode;  // halo kernel: 0 = swizzle phase from absolute smem address bits, 1 = descriptor base-offset field
     const float* bias;
     const float* head_w;
     const float* head_b;

@@ -8,7 +8,7 @@
 //     -> smem descriptor start = stage + (dy*24 + dx + 8t)*128 B, stride-byte-offset = 24*128 = 3072 B.
 // The start address is no longer 1024 B aligned when dx != 0; the 128B-swizzle XOR is a function of the absolute smem
 // address bits [7,10), which is also what TMA used when it wrote the box, so the shifted view reads the right chunks
-// (validated on B200 against the oracle; p.desc_mode keeps the descriptor's base-offset alternative selectable).
+// (validated on B200 against the oracle; putting the row phase into the descriptor's base-offset field instead is wrong).
 // Weights stream per (tap, slab) through their own ring. Warp roles (224 threads): 0 = A producer, 1 = TMEM owner +
 // MMA issuer, 2 = B producer, 3..6 = epilogue. TMEM: 2 accumulator sets x 2 halves x Cout columns.
 #include "conv_epilogue.cuh"
@@ -44,13 +44,12 @@ __host__ __device__ constexpr int halo_smem_bytes(int cout, bool resident) {
            4 * (H_STAGING_PER_WARP + H_POOL_PER_WARP) + H_BAR_BYTES;
 }
 
-__device__ __forceinline__ uint64_t halo_desc(uint32_t smem_addr, uint32_t base_offset) {
+__device__ __forceinline__ uint64_t halo_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
     d |= static_cast<uint64_t>(1) << 16;
     d |= static_cast<uint64_t>((HALO_W * 128) >> 4) << 32;  // 3072 B between consecutive tile rows (8-row groups)
     d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(base_offset & 7) << 49;
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
@@ -226,7 +225,7 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
                         const int dy = tap / 3, dx = tap - 3 * dy;
                         const uint64_t db =
                             umma_desc_sw128(smem_b + (RESIDENT ? tap : b_stage) * B_STAGE_BYTES);
-                        const uint64_t da0 = halo_desc(a_base + (dy * HALO_W + dx) * 128, p.desc_mode ? dx : 0);
+                        const uint64_t da0 = halo_desc(a_base + (dy * HALO_W + dx) * 128);
                         if (elect_one()) {
                             // The two column halves are independent accumulators: alternating them keeps back-to-back
                             // tcgen05.mma from serialising on the same TMEM tile.

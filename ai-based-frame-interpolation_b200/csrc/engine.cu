@@ -1028,6 +1028,13 @@ int fiUpsample2x(const void* src, void* dst, int N, int h, int w, int C, void* s
     return FI_OK;
 }
 
+int fiMaxPool2x2(const void* src, void* dst, int N, int H, int W, int C, void* stream) {
+    if (!src || !dst) return fail(FI_ERR_INVALID, "null argument");
+    const char* e = fi::maxpool2x2_launch(src, dst, N, H, W, C, static_cast<cudaStream_t>(stream));
+    if (e) return fail(FI_ERR_INVALID, "%s", e);
+    return FI_OK;
+}
+
 int fiPackPairU8(const uint8_t* frame1, const uint8_t* frame2, float* out, int N, int C, int H, int W, void* stream) {
     if (!frame1 || !frame2 || !out) return fail(FI_ERR_INVALID, "null argument");
     const char* e = fi::pack_pair_launch(frame1, frame2, out, N, C, H, W, static_cast<cudaStream_t>(stream));

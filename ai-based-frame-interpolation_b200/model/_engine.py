@@ -66,6 +66,7 @@ _SIGNATURES = {
     "fiStemPackWeights": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "fiStemConv": (C.c_int, [C.POINTER(Planes), C.POINTER(Planes), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fiMaxPool2x2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fiUpsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fiPackPairU8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fiHeadPostU8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -24,9 +24,102 @@ def _conv_bn_relu_slots(cin, cout):
     return [nn.Conv2d(cin, cout, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True)]
 
 
-def _fused_only(name):
-    raise _E.FiError(f"{name} runs as part of the fused UNet schedule: call UNet / FrameInterpolationUNet (its kernel "
-                     "is reachable on its own through fiConvGemm / fiStemConv / fiUpsample2x of the C ABI)")
+# ----------------------------------------------------------------------------------------------------------------------
+# Stand-alone use of the building blocks (DoubleConv / Down / Up / OutConv called on their own, as the reference allows).
+# Inside UNet.forward none of this runs: the whole schedule is one fiNetForward call. Here each block is a handful of
+# single-layer C-ABI calls (fiStemConv / fiConvGemm / fiMaxPool2x2 / fiUpsample2x); torch only converts the caller's
+# NCHW fp32 tensors to the kernels' NHWC bf16 layout and back, and folds the (tiny) BatchNorm vectors.
+# ----------------------------------------------------------------------------------------------------------------------
+import ctypes as _C
+
+
+def _to_nhwc(x):
+    return x.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _to_nchw(y):
+    return y.permute(0, 3, 1, 2).contiguous().to(torch.float32)
+
+
+def _fold_bn(conv, bn):
+    """Eval-mode BatchNorm folded into the conv (reference model/unet.py:12-17): W*s, beta - mean*s."""
+    scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    w = conv.weight.detach().double() * scale[:, None, None, None]
+    b = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+    return w.float(), b.float().contiguous()
+
+
+def _run_conv(x, w, bias, *, x1=None, off=(0, 0), taps=9, mode=_E.EPI_STORE, relu=True):
+    """x (and x1): NHWC bf16 CUDA tensors; w: folded fp32 weight [cout, cin, k, k] (or packed rows for ConvT)."""
+    n, h, wd, c0 = x.shape
+    d = _E.ConvDesc()
+    d.src0, d.c0, d.N, d.H, d.W = x.data_ptr(), c0, n, h, wd
+    keep = [x]
+    if x1 is not None:
+        d.src1, d.c1, d.h1, d.w1 = x1.data_ptr(), x1.shape[3], x1.shape[1], x1.shape[2]
+        d.off_y, d.off_x = off
+        keep.append(x1)
+    if mode == _E.EPI_CONVT:   # w: [cin, cout, 2, 2] -> rows (ky, kx, co), K = ci
+        cout = w.shape[1]
+        wp = w.permute(2, 3, 1, 0).reshape(4 * cout, w.shape[0])
+        b = bias.repeat(4)
+        n_total, out_shape = 4 * cout, (n, 2 * h, 2 * wd, cout)
+    else:                      # w: [cout, cin, k, k] -> [cout, tap*cin + ci]
+        wp = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+        b = bias
+        n_total, out_shape = w.shape[0], (n, h, wd, w.shape[0])
+    wp = wp.contiguous().to(torch.bfloat16)
+    b = b.contiguous().float()
+    dst = torch.empty(out_shape, dtype=torch.bfloat16, device=x.device)
+    keep += [wp, b]
+    d.wpack, d.bias, d.n_total, d.taps, d.mode, d.relu, d.dst = (wp.data_ptr(), b.data_ptr(), n_total, taps, mode,
+                                                                 int(relu), dst.data_ptr())
+    with torch.cuda.device(x.device):
+        _E.check(_E.lib().fiConvGemm(_C.byref(d), _E.current_stream()))
+    return dst
+
+
+def _check_standalone(x, module):
+    _E.require_cuda(x.device)
+    if module.training:
+        raise _E.FiError("training-mode forward is not part of the B200 inference path; call .eval() first")
+    if x.dtype != torch.float32 or x.dim() != 4:
+        raise _E.FiError("expected an fp32 NCHW tensor")
+
+
+def _double_conv_nhwc(dc, x_nchw=None, x_nhwc=None, x1_nhwc=None, off=(0, 0)):
+    """The two conv+BN+ReLU stages of a DoubleConv. Input either NCHW fp32 with <= 8 channels (stem kernel) or NHWC
+    bf16 with a multiple of 64 channels (optionally a second, padded source = the fused concat of Up)."""
+    seq = dc.double_conv
+    w1, b1 = _fold_bn(seq[0], seq[1])
+    w2, b2 = _fold_bn(seq[3], seq[4])
+    if w1.shape[0] % 64 or w2.shape[0] % 64:
+        raise _E.FiError("stand-alone blocks need output channel counts that are multiples of 64")
+    if x_nchw is not None:
+        n, cin, h, w = x_nchw.shape
+        if cin > 8 or w1.shape[0] != 64:
+            raise _E.FiError("a raw-input DoubleConv needs <= 8 input channels and 64 mid channels (the stem kernel); "
+                             "other inputs must have a multiple of 64 channels")
+        kp = _E.lib().fiStemPackedK(cin)
+        packed = torch.empty((64, kp), dtype=torch.int16)
+        wc = w1.cpu().contiguous()
+        _E.check(_E.lib().fiStemPackWeights(wc.data_ptr(), cin, packed.data_ptr()))
+        packed = packed.to(x_nchw.device)
+        mid = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=x_nchw.device)
+        p0 = _E.planes_of(x_nchw)
+        with torch.cuda.device(x_nchw.device):
+            _E.check(_E.lib().fiStemConv(_C.byref(p0), None, _E.FI_IN_F32, packed.data_ptr(), b1.data_ptr(),
+                                         mid.data_ptr(), n, h, w, _E.current_stream()))
+    else:
+        mid = _run_conv(x_nhwc, w1, b1, x1=x1_nhwc, off=off)
+    return _run_conv(mid, w2, b2)
+
+
+def _entry_nhwc(x, dc):
+    """NCHW fp32 -> what _double_conv_nhwc wants for this channel count."""
+    if x.shape[1] % 64 == 0:
+        return dict(x_nhwc=_to_nhwc(x))
+    return dict(x_nchw=x.detach().contiguous())
 
 
 class _EngineBacked(nn.Module):
@@ -78,7 +171,8 @@ class DoubleConv(nn.Module):
         self.double_conv = nn.Sequential(*(_conv_bn_relu_slots(in_channels, mid) + _conv_bn_relu_slots(mid, out_channels)))
 
     def forward(self, x):
-        _fused_only("DoubleConv")
+        _check_standalone(x, self)
+        return _to_nchw(_double_conv_nhwc(self, **_entry_nhwc(x, self)))
 
 
 class Down(nn.Module):
@@ -89,7 +183,18 @@ class Down(nn.Module):
         self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), DoubleConv(in_channels, out_channels))
 
     def forward(self, x):
-        _fused_only("Down")
+        _check_standalone(x, self)
+        if x.shape[1] % 8:
+            raise _E.FiError("stand-alone Down needs a multiple of 8 input channels")
+        xs = _to_nhwc(x)
+        n, h, w, c = xs.shape
+        pooled = torch.empty((n, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
+        with torch.cuda.device(x.device):
+            _E.check(_E.lib().fiMaxPool2x2(xs.data_ptr(), pooled.data_ptr(), n, h, w, c, _E.current_stream()))
+        dc = self.maxpool_conv[1]
+        if c % 64:
+            return _to_nchw(_double_conv_nhwc(dc, x_nchw=_to_nchw(pooled)))
+        return _to_nchw(_double_conv_nhwc(dc, x_nhwc=pooled))
 
 
 class Up(nn.Module):
@@ -105,7 +210,22 @@ class Up(nn.Module):
             self.conv = DoubleConv(in_channels, out_channels)
 
     def forward(self, x1, x2):
-        _fused_only("Up")
+        _check_standalone(x1, self)
+        _check_standalone(x2, self)
+        if x1.shape[1] % 64 or x2.shape[1] % 64:
+            raise _E.FiError("stand-alone Up needs channel counts that are multiples of 64")
+        lo = _to_nhwc(x1)
+        n, h, w, c = lo.shape
+        if isinstance(self.up, nn.ConvTranspose2d):
+            up = _run_conv(lo, self.up.weight.detach().float(), self.up.bias.detach().float(), taps=1,
+                           mode=_E.EPI_CONVT, relu=False)
+        else:
+            up = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x1.device)
+            with torch.cuda.device(x1.device):
+                _E.check(_E.lib().fiUpsample2x(lo.data_ptr(), up.data_ptr(), n, h, w, c, _E.current_stream()))
+        skip = _to_nhwc(x2)
+        off = ((skip.shape[1] - up.shape[1]) // 2, (skip.shape[2] - up.shape[2]) // 2)  # F.pad, unet.py:49-53
+        return _to_nchw(_double_conv_nhwc(self.conv, x_nhwc=skip, x1_nhwc=up, off=off))
 
 
 class OutConv(nn.Module):
@@ -116,7 +236,16 @@ class OutConv(nn.Module):
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
 
     def forward(self, x):
-        _fused_only("OutConv")
+        _check_standalone(x, self)
+        if x.shape[1] % 64:
+            raise _E.FiError("stand-alone OutConv needs a multiple of 64 input channels")
+        ncls = self.conv.out_channels
+        w = torch.zeros((64, x.shape[1], 1, 1), dtype=torch.float32, device=x.device)  # GEMM N is a multiple of 64
+        b = torch.zeros(64, dtype=torch.float32, device=x.device)
+        w[:ncls] = self.conv.weight.detach().float()
+        b[:ncls] = self.conv.bias.detach().float()
+        y = _run_conv(_to_nhwc(x), w, b, taps=1, relu=False)
+        return _to_nchw(y[..., :ncls])
 
 
 class UNet(_EngineBacked):

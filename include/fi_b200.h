@@ -160,6 +160,9 @@ int fiStemPackedK(int cin);
 int fiStemPackWeights(const float* w_host, int cin, uint16_t* out_host);
 int fiStemConv(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const void* wpack, const float* bias, void* dst,
                int N, int H, int W, void* stream);
+/* nn.MaxPool2d(2) (model/unet.py:28) on bf16 NHWC [N,H,W,C] -> [N,H/2,W/2,C]; inside fiNetForward the pool is fused into
+ * the producing convolution, this entry point serves the stand-alone Down module. */
+int fiMaxPool2x2(const void* src, void* dst, int N, int H, int W, int C, void* stream);
 /* nn.Upsample(scale_factor=2, bilinear, align_corners=True) (model/unet.py:40): bf16 NHWC [N,h,w,C] -> [N,2h,2w,C]. */
 int fiUpsample2x(const void* src, void* dst, int N, int h, int w, int C, void* stream);
 

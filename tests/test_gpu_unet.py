@@ -228,3 +228,54 @@ def test_random_shape_fuzz(cuda_device):
         deep = net.read_activation("down4", n)
         rel_deep = ((deep - taps["down4"]).norm() / (taps["down4"].norm() + 1e-12)).item()
         assert rel < 2e-2 and rel_deep < 2e-2, (bilinear, n, h, w, rel, rel_deep)
+
+
+def test_building_blocks_stand_alone(cuda_device):
+    """DoubleConv / Down / Up / OutConv called on their own (reference model/unet.py:5-63) against the same torch ops."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from model.unet import DoubleConv, Down, Up, OutConv
+    g = torch.Generator().manual_seed(3)
+
+    def randomise(m):
+        for mod in m.modules():
+            if isinstance(mod, nn.BatchNorm2d):
+                mod.weight.data = torch.rand(mod.num_features, generator=g) + 0.5
+                mod.bias.data = torch.randn(mod.num_features, generator=g) * 0.1
+                mod.running_mean.data = torch.randn(mod.num_features, generator=g) * 0.1
+                mod.running_var.data = torch.rand(mod.num_features, generator=g) + 0.5
+        return m.eval()
+
+    def ref_double(dc, x):
+        s = dc.double_conv
+        for conv, bn in ((s[0], s[1]), (s[3], s[4])):
+            x = F.relu(F.batch_norm(F.conv2d(x, conv.weight, None, padding=1), bn.running_mean, bn.running_var,
+                                    bn.weight, bn.bias, False, 0.0, bn.eps))
+        return x
+
+    def check(got, ref, what):
+        assert got.shape == ref.shape, what
+        rel = ((got.cpu() - ref).norm() / ref.norm()).item()
+        assert rel < 1.5e-2, f"{what}: relative L2 error {rel:.4f}"
+
+    with torch.no_grad():
+        dc = randomise(DoubleConv(2, 64))
+        x = torch.rand(2, 2, 21, 30, generator=g) * 2 - 1
+        check(dc.to(cuda_device)(x.to(cuda_device)), ref_double(dc.cpu(), x), "DoubleConv(2,64)")
+        dc = randomise(DoubleConv(64, 128))
+        x = torch.randn(1, 64, 18, 20, generator=g)
+        check(dc.to(cuda_device)(x.to(cuda_device)), ref_double(dc.cpu(), x), "DoubleConv(64,128)")
+        dn = randomise(Down(64, 128))
+        x = torch.randn(1, 64, 19, 26, generator=g)
+        check(dn.to(cuda_device)(x.to(cuda_device)), ref_double(dn.cpu().maxpool_conv[1], F.max_pool2d(x, 2)), "Down")
+        for bilinear in (False, True):
+            up = randomise(Up(128, 64, bilinear))
+            x1, x2 = torch.randn(1, 128 if not bilinear else 64, 9, 12, generator=g), torch.randn(1, 64, 19, 25, generator=g)
+            u = up.cpu().up(x1)
+            dy, dx = x2.shape[2] - u.shape[2], x2.shape[3] - u.shape[3]
+            cat = torch.cat([x2, F.pad(u, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])], 1)
+            ref = ref_double(up.conv, cat)
+            check(up.to(cuda_device)(x1.to(cuda_device), x2.to(cuda_device)), ref, f"Up(bilinear={bilinear})")
+        oc = OutConv(64, 3).eval()
+        x = torch.randn(2, 64, 10, 11, generator=g)
+        check(oc.to(cuda_device)(x.to(cuda_device)), oc.cpu().conv(x), "OutConv")
