@@ -279,3 +279,56 @@ def test_building_blocks_stand_alone(cuda_device):
         oc = OutConv(64, 3).eval()
         x = torch.randn(2, 64, 10, 11, generator=g)
         check(oc.to(cuda_device)(x.to(cuda_device)), oc.cpu().conv(x), "OutConv")
+
+
+@pytest.mark.parametrize("env", [{"FI_CTA2": "0"}, {"FI_CTA2": "0", "FI_NO_HALO": "1"}, {"FI_HALO_PREFETCH": "0"}])
+def test_kernel_selection_fallbacks_give_same_network(cuda_device, monkeypatch, env):
+    """The single-CTA kernels (FI_CTA2=0), the per-tap kernel for narrow layers (FI_NO_HALO=1) and the halo kernel
+    without L2 prefetch compute the same network as the default selection (CTA pairs + halo reuse): identical per-layer
+    inputs and fp32 accumulation orders differ only in how K is walked, so outputs agree to bf16 noise."""
+    from model import _engine as E
+    sd = O.init_state_dict(0, 2, 1, False)
+    f1, f2 = frames(31, 2, 1, 70, 118).to(cuda_device), frames(32, 2, 1, 70, 118).to(cuda_device)
+    base = E.Net(cuda_device, 2, 1, False)
+    base.load_state_dict(sd)
+    ref = base.forward(f1, f2, want_f32=True)[0].clone()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    alt = E.Net(cuda_device, 2, 1, False)
+    alt.load_state_dict(sd)
+    got = alt.forward(f1, f2, want_f32=True)[0]
+    assert ((got - ref).norm() / ref.norm()).item() < 5e-3
+    oracle = O.unet_forward(sd, torch.cat([O.preprocess_u8(f1.cpu().numpy()), O.preprocess_u8(f2.cpu().numpy())], 1))
+    assert ((got.cpu() - oracle).norm() / oracle.norm()).item() < 2e-2
+
+
+def test_c_abi_error_paths(cuda_device):
+    """Errors come back as negative codes + message, never as a crash (SURVEY.md §8b error convention)."""
+    import ctypes as C
+    from model import _engine as E
+    lib = E.lib()
+    net = E.Net(cuda_device, 2, 1, False)
+    x = torch.zeros(1, 1, 32, 32, device=cuda_device)
+    with pytest.raises(E.FiError, match="fiNetLoadWeights has not been called"):
+        net.forward(x, x)
+    sd = O.init_state_dict(0, 2, 1, False)
+    bad = {k: v for k, v in sd.items() if "up2.up.weight" not in k}
+    with pytest.raises(E.FiError, match="missing state-dict entry 'up2.up.weight'"):
+        net.load_state_dict(bad)
+    bilinear_sd = O.init_state_dict(0, 2, 1, True)     # what the reference's load_model would reject as well
+    with pytest.raises(E.FiError, match="size mismatch|missing"):
+        net.load_state_dict(bilinear_sd)
+    net.load_state_dict(sd)
+    with pytest.raises(E.FiError, match="provide 3 channels"):
+        net.forward(torch.zeros(1, 2, 32, 32, device=cuda_device), x)
+    with pytest.raises(E.FiError, match="smaller than 16x16"):
+        net.forward(x[:, :, :8, :8], x[:, :, :8, :8])
+    with pytest.raises(E.FiError):
+        net.forward(x.double(), x.double())
+    d = E.ConvDesc()
+    assert lib.fiConvGemm(C.byref(d), None) == -1 and b"conv:" in lib.fiLastError()
+    assert lib.fiSsimPsnrU8(None, None, 1, 8, 8, None, None, None) == -1
+    with pytest.raises(E.FiError, match="precision"):
+        E.Net(cuda_device, 2, 1, False, "fp64")
+    out = net.forward(x, x)[0]  # the handle is still usable after the failed calls
+    assert torch.isfinite(out).all()
