@@ -11,7 +11,8 @@ struct EpiTile {
     int nb, img, y0, x0;
 };
 
-template <int BLOCK_N, int MODE, bool SPLIT>
+// DOUBLE_BUF as in epilogue_chunk_halo below: two alternating staging tiles per warp, or a single one.
+template <int BLOCK_N, int MODE, bool SPLIT, bool DOUBLE_BUF = true>
 __device__ __forceinline__ void epilogue_chunk_8x16(const ConvMaps& maps, const ConvKernelParams& p, const EpiTile& tc,
                                                     uint32_t taddr, int c, int q, int lane, uint32_t my_stage,
                                                     uint32_t my_pool, int& buf, bool store_enabled) {
@@ -76,9 +77,12 @@ __device__ __forceinline__ void epilogue_chunk_8x16(const ConvMaps& maps, const 
 #pragma unroll
         for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
         // The staging buffer used two chunks ago must have been read by its TMA store.
-        if (elect_one()) tma_store_wait_read<1>();
+        if (elect_one()) {
+            if (DOUBLE_BUF) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+        }
         __syncwarp();
-        const uint32_t sbuf = my_stage + buf * 4096;
+        const uint32_t sbuf = my_stage + (DOUBLE_BUF ? buf * 4096 : 0);
         const uint32_t row = sbuf + lane * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -97,7 +101,7 @@ __device__ __forceinline__ void epilogue_chunk_8x16(const ConvMaps& maps, const 
         }
         if constexpr (MODE == EPI_STORE_POOL) {
             // 2x2 max over (rows 2q,2q+1) x (cols 2p,2p+1): bf16 max commutes with the rounding above.
-            const uint32_t pbuf = my_pool + buf * 1024;
+            const uint32_t pbuf = my_pool + (DOUBLE_BUF ? buf * 1024 : 0);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int pp = lane >> 2;

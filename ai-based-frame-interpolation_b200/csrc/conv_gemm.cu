@@ -26,7 +26,8 @@ namespace fi {
 
 namespace {
 
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 192;    // 2 role warps + 4 epilogue warps (precise mode, head)
+constexpr int NUM_THREADS_8 = 320;  // 2 role warps + 8 epilogue warps: two sets split the 64-column chunks of a tile
 constexpr int A_STAGE_BYTES = BLOCK_M * 128;             // 16 KB
 constexpr int STAGING_BYTES_PER_WARP = 2 * 4096;         // 2 x (32 rows x 128 B)
 constexpr int POOL_BYTES_PER_WARP = 2 * 1024;            // 2 x (8 rows x 128 B)
@@ -62,8 +63,12 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const ConvKernelParams& 
     return c;
 }
 
+__host__ __device__ constexpr bool eight_epilogue_warps(int block_n, int mode, bool split) {
+    return !split && mode != EPI_HEAD && block_n >= 128;  // needs >= 2 chunks per tile and single staging tiles
+}
+
 template <int BLOCK_N, int MODE, bool SPLIT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(eight_epilogue_warps(BLOCK_N, MODE, SPLIT) ? NUM_THREADS_8 : NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p) {
     constexpr int STAGES = num_stages(BLOCK_N);
     constexpr int B_STAGE_BYTES = b_stage_bytes(BLOCK_N);
@@ -71,6 +76,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
     constexpr int TMEM_COLS = tmem_cols(BLOCK_N);
     constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, BLOCK_N);
     static_assert(MODE != EPI_HEAD || BLOCK_N == 64, "head epilogue consumes exactly 64 channels");
+    constexpr bool EIGHT = eight_epilogue_warps(BLOCK_N, MODE, SPLIT);
+    constexpr int EPI_SETS = EIGHT ? 2 : 1;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -101,7 +108,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
-            mbar_init(bar_tempty + 8 * a, 4);  // one arrive per epilogue warp
+            mbar_init(bar_tempty + 8 * a, 4 * EPI_SETS);  // one arrive per epilogue warp
         }
         fence_mbar_init();
     }
@@ -187,8 +194,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
     } else {
         // ------------------------------------------------------------ epilogue warps 2..5
         const int q = warp & 3;  // TMEM lanes [32q, 32q+32) <-> tile rows 2q, 2q+1
-        const uint32_t my_stage = smem_stage + q * STAGING_BYTES_PER_WARP;
-        const uint32_t my_pool = smem_pool + q * POOL_BYTES_PER_WARP;
+        const int ew = warp - 2;   // 0..3, or 0..7 with two epilogue sets
+        const int set = ew >> 2;
+        const uint32_t my_stage = smem_stage + ew * (EIGHT ? 4096 : STAGING_BYTES_PER_WARP);
+        const uint32_t my_pool = smem_pool + ew * (EIGHT ? 1024 : POOL_BYTES_PER_WARP);
         int buf = 0;
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -199,9 +208,9 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 64; ++c) {
-                epilogue_chunk_8x16<BLOCK_N, MODE, SPLIT>(maps, p, EpiTile{tc.nb, tc.img, tc.y0, tc.x0}, taddr, c, q, lane,
-                                                           my_stage, my_pool, buf, true);
+            for (int c = set; c < BLOCK_N / 64; c += EPI_SETS) {
+                epilogue_chunk_8x16<BLOCK_N, MODE, SPLIT, !EIGHT>(maps, p, EpiTile{tc.nb, tc.img, tc.y0, tc.x0}, taddr, c,
+                                                                   q, lane, my_stage, my_pool, buf, true);
             }
             // All TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back to the MMA warp.
             tc_fence_before();
@@ -287,7 +296,7 @@ const char* launch_inst(const ConvLaunch& l, cudaStream_t stream) {
             return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
         configured = true;
     }
-    kfn<<<l.grid, NUM_THREADS, smem, stream>>>(l.maps, l.p);
+    kfn<<<l.grid, eight_epilogue_warps(BLOCK_N, MODE, SPLIT) ? NUM_THREADS_8 : NUM_THREADS, smem, stream>>>(l.maps, l.p);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
