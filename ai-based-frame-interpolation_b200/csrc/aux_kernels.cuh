@@ -23,6 +23,7 @@ struct StemDesc {
     const float* bias;   // fp32 [64]
     void* dst;           // bf16 NHWC [N,H,W,64]
     void* dst_lo;        // precise mode: lo halves (value = dst + dst_lo), else null
+    int linear;          // 1: no ReLU (training forward keeps the pre-BatchNorm conv output)
 };
 const char* stem_conv_launch(const StemDesc& d, cudaStream_t stream);  // stem_mma.cu
 int stem_packed_k(int cin);                                               // packed K length (multiple of 64)

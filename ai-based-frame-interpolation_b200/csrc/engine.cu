@@ -3,6 +3,7 @@
 #include "../../include/fi_b200.h"
 #include "aux_kernels.cuh"
 #include "conv_gemm.cuh"
+#include "train_kernels.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -1001,8 +1002,21 @@ int fiStemPackWeights(const float* w_host, int cin, uint16_t* out_host) {
     return FI_OK;
 }
 
+static int stem_conv_impl(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const void* wpack, const float* bias,
+                          void* dst, int N, int H, int W, void* stream, int linear);
+
 int fiStemConv(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const void* wpack, const float* bias, void* dst,
                int N, int H, int W, void* stream) {
+    return stem_conv_impl(in0, in1, in_dtype, wpack, bias, dst, N, H, W, stream, 0);
+}
+
+int fiStemConvLinear(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const void* wpack, const float* bias,
+                     void* dst, int N, int H, int W, void* stream) {
+    return stem_conv_impl(in0, in1, in_dtype, wpack, bias, dst, N, H, W, stream, 1);
+}
+
+static int stem_conv_impl(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const void* wpack, const float* bias,
+                          void* dst, int N, int H, int W, void* stream, int linear) {
     if (!in0 || !wpack || !bias || !dst) return fail(FI_ERR_INVALID, "null argument");
     fi::StemDesc d;
     memset(&d, 0, sizeof d);
@@ -1014,6 +1028,7 @@ int fiStemConv(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const voi
     d.H = H;
     d.W = W;
     d.wpack = wpack;
+    d.linear = linear;
     d.bias = bias;
     d.dst = dst;
     const char* e = fi::stem_conv_launch(d, static_cast<cudaStream_t>(stream));
@@ -1060,5 +1075,71 @@ int fiSsimPsnrU8(const uint8_t* pred, const uint8_t* target, int N, int H, int W
     if (e) return fail(FI_ERR_INVALID, "%s", e);
     return FI_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------- training-step kernels
+#define TRAIN_CALL(expr)                                        \
+    do {                                                        \
+        const char* _m = (expr);                                \
+        if (_m) return fail(FI_ERR_INVALID, "%s", _m);          \
+        return FI_OK;                                           \
+    } while (0)
+#define ST static_cast<cudaStream_t>(stream)
+
+int fiBnStats(const void* z, int64_t P, int C, float* sum, float* sumsq, void* stream) {
+    TRAIN_CALL(fi::bn_stats_launch(z, P, C, sum, sumsq, ST));
+}
+int fiBnApplyRelu(const void* z, int64_t P, int C, const float* scale, const float* shift, void* a, void* stream) {
+    TRAIN_CALL(fi::bn_apply_relu_launch(z, P, C, scale, shift, a, ST));
+}
+int fiHeadForward(const void* a, int N, int64_t HW, const float* w, const float* b, int n_classes, float* y, void* stream) {
+    TRAIN_CALL(fi::head_forward_launch(a, N, HW, w, b, n_classes, y, ST));
+}
+int fiMseLossGrad(const float* y, const float* target, int64_t n, float* loss, float* dy, void* stream) {
+    TRAIN_CALL(fi::mse_launch(y, target, n, loss, dy, ST));
+}
+int fiHeadBackward(const void* a, const float* dy, int N, int64_t HW, const float* w, int n_classes, void* da, float* dw,
+                   float* db, void* stream) {
+    TRAIN_CALL(fi::head_backward_launch(a, dy, N, HW, w, n_classes, da, dw, db, ST));
+}
+int fiBnReluBackwardReduce(const void* dA, const void* a, const void* z, int64_t P, int C, const float* mean,
+                           const float* rstd, float* dbeta, float* dgamma, void* stream) {
+    TRAIN_CALL(fi::bn_relu_bwd_reduce_launch(dA, a, z, P, C, mean, rstd, dbeta, dgamma, ST));
+}
+int fiBnReluBackwardApply(const void* dA, const void* a, const void* z, int64_t P, int C, const float* mean,
+                          const float* rstd, const float* gamma, const float* dbeta, const float* dgamma, void* dz,
+                          void* stream) {
+    TRAIN_CALL(fi::bn_relu_bwd_apply_launch(dA, a, z, P, C, mean, rstd, gamma, dbeta, dgamma, dz, ST));
+}
+int fiMaxPoolBackwardAdd(const void* a_full, const void* a_pool, const void* d_pool, const void* d_skip, void* d_full,
+                         int N, int H, int W, int C, void* stream) {
+    TRAIN_CALL(fi::maxpool_bwd_add_launch(a_full, a_pool, d_pool, d_skip, d_full, N, H, W, C, ST));
+}
+int fiUpsample2xBackward(const void* d_up, void* d_lo, int N, int h, int w, int C, void* stream) {
+    TRAIN_CALL(fi::upsample2x_bwd_launch(d_up, d_lo, N, h, w, C, ST));
+}
+int64_t fiTransposePadK(int N, int H, int W) { return fi::transpose_pad_k(N, H, W); }
+int fiTransposePadRow(int W) { return fi::transpose_pad_row(W); }
+int fiTransposePad(const void* x, void* xT, int N, int H, int W, int C, int copies, void* stream) {
+    TRAIN_CALL(fi::transpose_pad_launch(x, xT, N, H, W, C, copies, ST));
+}
+int fiStemWgrad(const void* dz, const float* x, int N, int H, int W, int cin, float* dW, void* stream) {
+    TRAIN_CALL(fi::stem_wgrad_launch(dz, x, N, H, W, cin, dW, ST));
+}
+int fiWgrad(const void* dzT, const void* xT, int cout, int cin, int64_t Kp, int Wp, float* dW, void* stream) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    TRAIN_CALL(fi::wgrad_launch(dzT, xT, cout, cin, Kp, Wp, dW, sms, ST));
+}
+int fiAdamStep(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+               int step, void* stream) {
+    TRAIN_CALL(fi::adam_launch(p, g, m, v, n, lr, beta1, beta2, eps, step, ST));
+}
+int fiPackConvWeights(const float* w, int cout, int cin, void* fwd, void* bwd, void* stream) {
+    TRAIN_CALL(fi::pack_conv_launch(w, cout, cin, fwd, bwd, ST));
+}
+#undef ST
+#undef TRAIN_CALL
 
 }  // extern "C"

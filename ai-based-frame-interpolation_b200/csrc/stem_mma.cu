@@ -29,6 +29,7 @@ struct StemParams {
     PlaneSrc src[2];
     int N, H, W, tiles_x, tiles_y;
     int split;  // precise mode: also store lo = bf16(value - hi)
+    int linear; // no ReLU
     const float* bias;
 };
 
@@ -261,6 +262,7 @@ stem_mma_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
             __syncwarp();
             if (elect_one()) mbar_arrive(bar_tempty + 8 * acc);  // accumulator is in registers: release it early
             const float4* bias4 = reinterpret_cast<const float4*>(p.bias);
+            const float lo_clamp = p.linear ? -3.0e38f : 0.f;  // ReLU, or (training forward) none
             // split: buffer 0 = hi tile, buffer 1 = lo tile (both must be free); else the two buffers alternate
             if (elect_one()) {
                 if (p.split) tma_store_wait_read<0>();
@@ -275,14 +277,14 @@ stem_mma_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                 const uint32_t* v = j < 4 ? v0 : v1;
                 const int o = (j & 3) * 8;
                 float f[8];
-                f[0] = fmaxf(__uint_as_float(v[o + 0]) + b0.x, 0.f);
-                f[1] = fmaxf(__uint_as_float(v[o + 1]) + b0.y, 0.f);
-                f[2] = fmaxf(__uint_as_float(v[o + 2]) + b0.z, 0.f);
-                f[3] = fmaxf(__uint_as_float(v[o + 3]) + b0.w, 0.f);
-                f[4] = fmaxf(__uint_as_float(v[o + 4]) + b1.x, 0.f);
-                f[5] = fmaxf(__uint_as_float(v[o + 5]) + b1.y, 0.f);
-                f[6] = fmaxf(__uint_as_float(v[o + 6]) + b1.z, 0.f);
-                f[7] = fmaxf(__uint_as_float(v[o + 7]) + b1.w, 0.f);
+                f[0] = fmaxf(__uint_as_float(v[o + 0]) + b0.x, lo_clamp);
+                f[1] = fmaxf(__uint_as_float(v[o + 1]) + b0.y, lo_clamp);
+                f[2] = fmaxf(__uint_as_float(v[o + 2]) + b0.z, lo_clamp);
+                f[3] = fmaxf(__uint_as_float(v[o + 3]) + b0.w, lo_clamp);
+                f[4] = fmaxf(__uint_as_float(v[o + 4]) + b1.x, lo_clamp);
+                f[5] = fmaxf(__uint_as_float(v[o + 5]) + b1.y, lo_clamp);
+                f[6] = fmaxf(__uint_as_float(v[o + 6]) + b1.z, lo_clamp);
+                f[7] = fmaxf(__uint_as_float(v[o + 7]) + b1.w, lo_clamp);
                 uint32_t hw[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) hw[k] = pack_bf16x2(f[2 * k], f[2 * k + 1]);
@@ -395,6 +397,7 @@ const char* stem_conv_launch(const StemDesc& d, cudaStream_t stream) {
     p.tiles_y = (d.H + TILE_H - 1) / TILE_H;
     p.bias = d.bias;
     p.split = d.dst_lo != nullptr;
+    p.linear = d.linear;
     const long long tiles = static_cast<long long>(d.N) * p.tiles_x * p.tiles_y;
     if (tiles > 0x7fffffffLL) return "stem: too many tiles";
     alignas(64) CUtensorMap map_b, map_out, map_out_lo;

@@ -1,0 +1,511 @@
+// Training-step kernels around the tensor-core convolutions (reference model/train.py:153-249: forward with
+// batch-statistics BatchNorm, MSE loss, backward, Adam). Activations and activation gradients are bf16 NHWC,
+// statistics / weight gradients / optimizer state are fp32. The conv forward and the data gradient (a conv with the
+// flipped, transposed weights) reuse conv_gemm*.cu / conv_halo*.cu; the weight gradient is wgrad_gemm.cu.
+#include "ptx.cuh"
+#include "train_kernels.cuh"
+
+namespace fi {
+
+namespace {
+
+__device__ __forceinline__ float2 unpack2(uint32_t v) { return make_float2(bf16lo_f(v), bf16hi_f(v)); }
+
+const char* last_error() {
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+int blocks_for(long long items, int threads, int cap = 148 * 8) {
+    long long b = (items + threads - 1) / threads;
+    return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ------------------------------------------------------------------------------------------------ BN statistics
+// z: bf16 [P][C]. Thread = channel pair, a block walks a contiguous range of pixels: coalesced 4-byte loads across the
+// warp, fp32 partial sums, one atomicAdd per (block, channel).
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const uint32_t* __restrict__ z, long long P, int c2, float* __restrict__ sum, float* __restrict__ sumsq) {
+    // c2 (channel pairs per pixel) divides 256 or is a multiple of it: 256/c2 pixel rows per block pass, or 1
+    const int rows_par = c2 <= 256 ? 256 / c2 : 1;
+    const int r0 = c2 <= 256 ? threadIdx.x / c2 : 0;
+    for (int col = c2 <= 256 ? threadIdx.x % c2 : threadIdx.x; col < c2; col += 256) {
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        for (long long p = static_cast<long long>(blockIdx.x) * rows_par + r0; p < P;
+             p += static_cast<long long>(gridDim.x) * rows_par) {
+            const float2 v = unpack2(__ldg(z + p * c2 + col));
+            s0 += v.x; s1 += v.y; q0 += v.x * v.x; q1 += v.y * v.y;
+        }
+        atomicAdd(sum + 2 * col, s0); atomicAdd(sum + 2 * col + 1, s1);
+        atomicAdd(sumsq + 2 * col, q0); atomicAdd(sumsq + 2 * col + 1, q1);
+    }
+}
+
+// a = relu(z * scale[c] + shift[c]) (scale = gamma * rstd, shift = beta - mean * scale); 8 channels per thread.
+__global__ void __launch_bounds__(256)
+bn_apply_relu_kernel(const uint4* __restrict__ z, long long n8, int c8, const float* __restrict__ scale,
+                     const float* __restrict__ shift, uint4* __restrict__ a) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % c8) * 8;
+        const uint4 v = __ldg(z + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = unpack2(w[k]);
+            o[k] = pack_bf16x2(fmaxf(fmaf(f.x, scale[c + 2 * k], shift[c + 2 * k]), 0.f),
+                               fmaxf(fmaf(f.y, scale[c + 2 * k + 1], shift[c + 2 * k + 1]), 0.f));
+        }
+        a[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ head + loss
+// y[n][k][pix] = b[k] + sum_c a[n][pix][c] * w[k][c]   (a: bf16 [N*HW][64])
+__global__ void __launch_bounds__(256)
+head_forward_kernel(const uint4* __restrict__ a, long long P, long long HW, const float* __restrict__ w,
+                    const float* __restrict__ b, int ncls, float* __restrict__ y) {
+    __shared__ float ws[4 * 64];
+    for (int i = threadIdx.x; i < ncls * 64; i += blockDim.x) ws[i] = w[i];
+    __syncthreads();
+    for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < P;
+         p += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 v = __ldg(a + p * 8 + j);
+            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack2(wv[k]);
+                for (int cls = 0; cls < ncls; ++cls)
+                    acc[cls] = fmaf(f.y, ws[cls * 64 + j * 8 + 2 * k + 1], fmaf(f.x, ws[cls * 64 + j * 8 + 2 * k], acc[cls]));
+            }
+        }
+        const long long n = p / HW, pix = p - n * HW;
+        for (int cls = 0; cls < ncls; ++cls) y[(n * ncls + cls) * HW + pix] = acc[cls] + b[cls];
+    }
+}
+
+// loss += sum (y-t)^2 / n ; dy = 2 (y - t) / n
+__global__ void __launch_bounds__(256)
+mse_kernel(const float* __restrict__ y, const float* __restrict__ t, long long n, float inv_n, float* __restrict__ loss,
+           float* __restrict__ dy) {
+    float part = 0.f;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float d = y[i] - t[i];
+        part += d * d;
+        dy[i] = 2.f * d * inv_n;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss, part * inv_n);
+}
+
+// da[n][pix][c] = sum_k dy[n][k][pix] w[k][c];  dw[k][c] += sum dy * a;  db[k] += sum dy
+__global__ void __launch_bounds__(256)
+head_backward_kernel(const uint4* __restrict__ a, const float* __restrict__ dy, long long P, long long HW,
+                     const float* __restrict__ w, int ncls, uint4* __restrict__ da, float* __restrict__ dw,
+                     float* __restrict__ db) {
+    __shared__ float ws[4 * 64];
+    __shared__ float acc_w[4 * 64];
+    __shared__ float acc_b[4];
+    for (int i = threadIdx.x; i < ncls * 64; i += blockDim.x) { ws[i] = w[i]; acc_w[i] = 0.f; }
+    if (threadIdx.x < 4) acc_b[threadIdx.x] = 0.f;
+    __syncthreads();
+    // thread = (pixel, 8-channel group): 8 consecutive threads share a pixel
+    const int cg = threadIdx.x & 7;
+    float lw[4][8];
+    float lb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lw[k][j] = 0.f;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < P * 8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long p = i >> 3;
+        const long long n = p / HW, pix = p - n * HW;
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < ncls; ++k) g[k] = dy[(n * ncls + k) * HW + pix];
+        const uint4 v = __ldg(a + i);
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        float av[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = unpack2(wv[k]); av[2 * k] = f.x; av[2 * k + 1] = f.y; }
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float s = 0.f;
+            for (int k = 0; k < ncls; ++k) { s = fmaf(g[k], ws[k * 64 + cg * 8 + j], s); lw[k][j] = fmaf(g[k], av[j], lw[k][j]); }
+            o[j] = s;
+        }
+        if (cg == 0) for (int k = 0; k < ncls; ++k) lb[k] += g[k];
+        da[i] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+    for (int k = 0; k < ncls; ++k) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&acc_w[k * 64 + cg * 8 + j], lw[k][j]);
+        if (cg == 0) atomicAdd(&acc_b[k], lb[k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ncls * 64; i += blockDim.x) atomicAdd(dw + i, acc_w[i]);
+    if (threadIdx.x < ncls) atomicAdd(db + threadIdx.x, acc_b[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------ BN + ReLU backward
+// dy = dA * (a > 0); dbeta[c] += sum dy; dgamma[c] += sum dy * zhat, zhat = (z - mean) * rstd.   (same walk as bn_stats)
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_reduce_kernel(const uint32_t* __restrict__ dA, const uint32_t* __restrict__ a, const uint32_t* __restrict__ z,
+                          long long P, int c2, const float* __restrict__ mean, const float* __restrict__ rstd,
+                          float* __restrict__ dbeta, float* __restrict__ dgamma) {
+    const int rows_par = c2 <= 256 ? 256 / c2 : 1;
+    const int r0 = c2 <= 256 ? threadIdx.x / c2 : 0;
+    for (int c = c2 <= 256 ? threadIdx.x % c2 : threadIdx.x; c < c2; c += 256) {
+        const float m0 = mean[2 * c], m1 = mean[2 * c + 1], r_0 = rstd[2 * c], r_1 = rstd[2 * c + 1];
+        float b0 = 0.f, b1 = 0.f, g0 = 0.f, g1 = 0.f;
+        for (long long p = static_cast<long long>(blockIdx.x) * rows_par + r0; p < P;
+             p += static_cast<long long>(gridDim.x) * rows_par) {
+            const long long i = p * c2 + c;
+            const float2 d = unpack2(__ldg(dA + i)), av = unpack2(__ldg(a + i)), zv = unpack2(__ldg(z + i));
+            const float d0 = av.x > 0.f ? d.x : 0.f, d1 = av.y > 0.f ? d.y : 0.f;
+            b0 += d0; b1 += d1;
+            g0 += d0 * (zv.x - m0) * r_0; g1 += d1 * (zv.y - m1) * r_1;
+        }
+        atomicAdd(dbeta + 2 * c, b0); atomicAdd(dbeta + 2 * c + 1, b1);
+        atomicAdd(dgamma + 2 * c, g0); atomicAdd(dgamma + 2 * c + 1, g1);
+    }
+}
+
+// dz = gamma * rstd * (dy - dbeta/P - zhat * dgamma/P)
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_apply_kernel(const uint4* __restrict__ dA, const uint4* __restrict__ a, const uint4* __restrict__ z,
+                         long long n8, int c8, float inv_p, const float* __restrict__ mean, const float* __restrict__ rstd,
+                         const float* __restrict__ gamma, const float* __restrict__ dbeta, const float* __restrict__ dgamma,
+                         uint4* __restrict__ dz) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % c8) * 8;
+        const uint4 dv = __ldg(dA + i), av = __ldg(a + i), zv = __ldg(z + i);
+        const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, aw[4] = {av.x, av.y, av.z, av.w}, zw[4] = {zv.x, zv.y, zv.z, zv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 d = unpack2(dw[k]), af = unpack2(aw[k]), zf = unpack2(zw[k]);
+            float r[2];
+            const float dd[2] = {af.x > 0.f ? d.x : 0.f, af.y > 0.f ? d.y : 0.f};
+            const float zz[2] = {zf.x, zf.y};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int ch = c + 2 * k + h;
+                const float zhat = (zz[h] - mean[ch]) * rstd[ch];
+                r[h] = gamma[ch] * rstd[ch] * (dd[h] - dbeta[ch] * inv_p - zhat * dgamma[ch] * inv_p);
+            }
+            o[k] = pack_bf16x2(r[0], r[1]);
+        }
+        dz[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pool / upsample backward
+// d_full[n,y,x,c] = (d_skip ? d_skip : 0) + (a_full == a_pool[y/2,x/2] and first such position in the 2x2 window ? d_pool : 0)
+__global__ void __launch_bounds__(256)
+maxpool_bwd_add_kernel(const uint4* __restrict__ a_full, const uint4* __restrict__ a_pool, const uint4* __restrict__ d_pool,
+                       const uint4* __restrict__ d_skip, uint4* __restrict__ d_full, int N, int H, int W, int c8) {
+    const int oh = H / 2, ow = W / 2;
+    const long long total = static_cast<long long>(N) * oh * ow * c8;  // one thread per pooled element group
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int cg = static_cast<int>(i % c8);
+        long long r = i / c8;
+        const int ox = static_cast<int>(r % ow);
+        r /= ow;
+        const int oy = static_cast<int>(r % oh);
+        const int n = static_cast<int>(r / oh);
+        const uint4 pv = __ldg(a_pool + i), gv = __ldg(d_pool + i);
+        const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+        uint32_t taken[4] = {0, 0, 0, 0};  // per half-word: gradient already routed (ties go to the first position)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int y = 2 * oy + (q >> 1), x = 2 * ox + (q & 1);
+            const long long idx = ((static_cast<long long>(n) * H + y) * W + x) * c8 + cg;
+            const uint4 fv = __ldg(a_full + idx);
+            const uint32_t fw[4] = {fv.x, fv.y, fv.z, fv.w};
+            uint4 sk = make_uint4(0, 0, 0, 0);
+            if (d_skip) sk = __ldg(d_skip + idx);
+            const uint32_t sw[4] = {sk.x, sk.y, sk.z, sk.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 s = unpack2(sw[k]), g = unpack2(gw[k]);
+                const bool lo = ((fw[k] & 0xffffu) == (pw[k] & 0xffffu)) && !(taken[k] & 1u);
+                const bool hi = ((fw[k] >> 16) == (pw[k] >> 16)) && !(taken[k] & 2u);
+                taken[k] |= (lo ? 1u : 0u) | (hi ? 2u : 0u);
+                o[k] = pack_bf16x2(s.x + (lo ? g.x : 0.f), s.y + (hi ? g.y : 0.f));
+            }
+            d_full[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    // odd trailing row / column (dropped by the floor pooling) only carries the skip gradient
+    if ((H & 1) || (W & 1)) {
+        const long long edge = static_cast<long long>(N) * H * W * c8;
+        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < edge;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            long long r = i / c8;
+            const int x = static_cast<int>(r % W);
+            const int y = static_cast<int>((r / W) % H);
+            if (y >= 2 * oh || x >= 2 * ow) d_full[i] = d_skip ? __ldg(d_skip + i) : make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
+// Backward of bilinear x2 (align_corners=True) with the F.pad offset of Up: d_lo[n,y,x,c] = sum over the output pixels
+// whose taps include (y,x) of weight * d_up_padded. Gather form (deterministic): an input pixel can only be referenced
+// by output rows in [2y-2, 2y+2] / columns likewise.
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const uint4* __restrict__ d_up, uint4* __restrict__ d_lo, int N, int h, int w, int c8) {
+    const int oh = 2 * h, ow = 2 * w;
+    const float rh = oh > 1 ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.f;
+    const float rw = ow > 1 ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) : 0.f;
+    const long long total = static_cast<long long>(N) * h * w * c8;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int cg = static_cast<int>(i % c8);
+        long long r = i / c8;
+        const int x = static_cast<int>(r % w);
+        r /= w;
+        const int y = static_cast<int>(r % h);
+        const int n = static_cast<int>(r / h);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int oy = max(0, 2 * y - 3); oy <= min(oh - 1, 2 * y + 3); ++oy) {
+            const float fy = rh * oy;
+            const int y0 = static_cast<int>(fy);
+            const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+            const float ly = fy - y0;
+            const float wy = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
+            if (wy == 0.f) continue;
+            for (int ox = max(0, 2 * x - 3); ox <= min(ow - 1, 2 * x + 3); ++ox) {
+                const float fx = rw * ox;
+                const int x0 = static_cast<int>(fx);
+                const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+                const float lx = fx - x0;
+                const float wx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
+                if (wx == 0.f) continue;
+                const uint4 g = __ldg(d_up + ((static_cast<long long>(n) * oh + oy) * ow + ox) * c8 + cg);
+                const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+                const float wt = wy * wx;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = unpack2(gw[k]);
+                    acc[2 * k] = fmaf(wt, f.x, acc[2 * k]);
+                    acc[2 * k + 1] = fmaf(wt, f.y, acc[2 * k + 1]);
+                }
+            }
+        }
+        d_lo[i] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                             pack_bf16x2(acc[6], acc[7]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ layouts for wgrad
+// x: bf16 NHWC [N,H,W,C] -> channel-major, zero-padded rows xT[copy][c][q]: padded images of (H+2) x Wp8 pixels
+// (Wp8 = W+2 rounded up to 8), pixel (n,y,x) at q = n*(H+2)*Wp8 + (y+1)*Wp8 + (x+1); row length Kp (multiple of 64).
+// TMA needs 16-byte aligned box starts along the contiguous dimension, so the +-1 column shift of a tap cannot be a
+// coordinate offset: copy `s` (blockIdx.z) holds the row shifted by (s-1) elements, xT[s][c][q] = padded(q + s - 1),
+// and the row shift of a tap, (dy-1)*Wp8, is a multiple of 8 elements.
+__global__ void __launch_bounds__(256)
+transpose_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xT, int N, int H, int W, int C,
+                     int Wp8, long long Kp, int first_shift) {
+    __shared__ __nv_bfloat16 tile[32][34];
+    const int Hp = H + 2;
+    const int shift = first_shift + static_cast<int>(blockIdx.z);
+    const long long q0 = static_cast<long long>(blockIdx.x) * 32;  // output index base
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const long long q = q0 + r + shift;                        // padded source index
+        __nv_bfloat16 v = __float2bfloat16(0.f);
+        if (q >= 0 && q < static_cast<long long>(N) * Hp * Wp8 && c0 + tx < C) {
+            const int n = static_cast<int>(q / (static_cast<long long>(Hp) * Wp8));
+            const int rem = static_cast<int>(q - static_cast<long long>(n) * Hp * Wp8);
+            const int yp = rem / Wp8, xp = rem - yp * Wp8;
+            if (yp >= 1 && yp <= H && xp >= 1 && xp <= W)
+                v = x[((static_cast<long long>(n) * H + (yp - 1)) * W + (xp - 1)) * C + c0 + tx];
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    __nv_bfloat16* out = xT + static_cast<long long>(blockIdx.z) * C * Kp;
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r;
+        const long long q = q0 + tx;
+        if (c < C && q < Kp) out[static_cast<long long>(c) * Kp + q] = tile[tx][r];
+    }
+}
+
+// Stem weight gradient (C_in <= 8, K = 9*C_in): dW[co][ci][tap] += sum_px dz[px,co] * x[px+tap, ci]; x in NCHW fp32.
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(const uint32_t* __restrict__ dz, const float* __restrict__ x, int N, int H, int W, int cin,
+                  float* __restrict__ dW) {
+    // thread = (channel pair of dz) ; block walks pixels; 32 channel pairs x 8 pixel lanes
+    const int cp = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    float acc[2][72];
+    for (int k = 0; k < 9 * cin; ++k) acc[0][k] = acc[1][k] = 0.f;
+    const long long P = static_cast<long long>(N) * H * W;
+    for (long long p = static_cast<long long>(blockIdx.x) * 8 + pl; p < P; p += static_cast<long long>(gridDim.x) * 8) {
+        const int n = static_cast<int>(p / (static_cast<long long>(H) * W));
+        const int rem = static_cast<int>(p - static_cast<long long>(n) * H * W);
+        const int y = rem / W, xx = rem - y * W;
+        const float2 g = unpack2(__ldg(dz + p * 32 + cp));
+        for (int ci = 0; ci < cin; ++ci)
+            for (int t = 0; t < 9; ++t) {
+                const int yy = y + t / 3 - 1, xq = xx + t % 3 - 1;
+                const float v = (yy >= 0 && yy < H && xq >= 0 && xq < W)
+                                    ? __ldg(x + ((static_cast<long long>(n) * cin + ci) * H + yy) * W + xq) : 0.f;
+                acc[0][ci * 9 + t] = fmaf(g.x, v, acc[0][ci * 9 + t]);
+                acc[1][ci * 9 + t] = fmaf(g.y, v, acc[1][ci * 9 + t]);
+            }
+    }
+    for (int k = 0; k < 9 * cin; ++k) {
+        atomicAdd(dW + static_cast<long long>(2 * cp) * 9 * cin + k, acc[0][k]);
+        atomicAdd(dW + static_cast<long long>(2 * cp + 1) * 9 * cin + k, acc[1][k]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ optimizer / packing
+// torch.optim.Adam defaults (reference model/train.py:160): p -= lr * mhat / (sqrt(vhat) + eps)
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+            float lr, float b1, float b2, float eps, float bc1, float bc2) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    }
+}
+
+// w fp32 [co][ci][3][3] -> fwd bf16 [co][tap*ci_tot + ci] and bwd bf16 [ci][(8-tap)*co_tot... ] (data-gradient weights:
+// dX = conv3x3(dz, Wb) with Wb[ci][tap'][co] = w[co][ci][8 - tap'])
+__global__ void __launch_bounds__(256)
+pack_conv_kernel(const float* __restrict__ w, int co, int ci, __nv_bfloat16* __restrict__ fwd,
+                 __nv_bfloat16* __restrict__ bwd) {
+    const long long total = static_cast<long long>(co) * ci * 9;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int t = static_cast<int>(i % 9);
+        const int c = static_cast<int>((i / 9) % ci);
+        const int o = static_cast<int>(i / (9LL * ci));
+        const __nv_bfloat16 v = __float2bfloat16(w[i]);
+        if (fwd) fwd[(static_cast<long long>(o) * 9 + t) * ci + c] = v;
+        if (bwd) bwd[(static_cast<long long>(c) * 9 + (8 - t)) * co + o] = v;
+    }
+}
+
+}  // namespace
+
+#define FI_REQUIRE(cond, msg) do { if (!(cond)) return msg; } while (0)
+
+const char* bn_stats_launch(const void* z, long long P, int C, float* sum, float* sumsq, cudaStream_t st) {
+    FI_REQUIRE(z && sum && sumsq && P > 0 && C > 0 && C % 2 == 0, "bn_stats: bad arguments");
+    FI_REQUIRE((C / 2) <= 256 ? 256 % (C / 2) == 0 : (C / 2) % 256 == 0, "bn_stats: C/2 must divide 256 or be a multiple");
+    bn_stats_kernel<<<blocks_for(P, C / 2 <= 256 ? 256 / (C / 2) : 1, 148 * 4), 256, 0, st>>>(
+        static_cast<const uint32_t*>(z), P, C / 2, sum, sumsq);
+    return last_error();
+}
+const char* bn_apply_relu_launch(const void* z, long long P, int C, const float* scale, const float* shift, void* a,
+                                 cudaStream_t st) {
+    FI_REQUIRE(z && a && scale && shift && P > 0 && C % 8 == 0, "bn_apply: bad arguments");
+    const long long n8 = P * (C / 8);
+    bn_apply_relu_kernel<<<blocks_for(n8, 256), 256, 0, st>>>(static_cast<const uint4*>(z), n8, C / 8, scale, shift,
+                                                              static_cast<uint4*>(a));
+    return last_error();
+}
+const char* head_forward_launch(const void* a, int N, long long HW, const float* w, const float* b, int ncls, float* y,
+                                cudaStream_t st) {
+    FI_REQUIRE(a && w && b && y && ncls >= 1 && ncls <= 4 && N > 0 && HW > 0, "head_forward: bad arguments");
+    head_forward_kernel<<<blocks_for(N * HW, 256), 256, 0, st>>>(static_cast<const uint4*>(a), N * HW, HW, w, b, ncls, y);
+    return last_error();
+}
+const char* mse_launch(const float* y, const float* t, long long n, float* loss, float* dy, cudaStream_t st) {
+    FI_REQUIRE(y && t && loss && dy && n > 0, "mse: bad arguments");
+    mse_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, t, n, 1.0f / static_cast<float>(n), loss, dy);
+    return last_error();
+}
+const char* head_backward_launch(const void* a, const float* dy, int N, long long HW, const float* w, int ncls, void* da,
+                                 float* dw, float* db, cudaStream_t st) {
+    FI_REQUIRE(a && dy && w && da && dw && db && ncls >= 1 && ncls <= 4, "head_backward: bad arguments");
+    head_backward_kernel<<<blocks_for(N * HW * 8, 256, 148 * 4), 256, 0, st>>>(
+        static_cast<const uint4*>(a), dy, N * HW, HW, w, ncls, static_cast<uint4*>(da), dw, db);
+    return last_error();
+}
+const char* bn_relu_bwd_reduce_launch(const void* dA, const void* a, const void* z, long long P, int C, const float* mean,
+                                      const float* rstd, float* dbeta, float* dgamma, cudaStream_t st) {
+    FI_REQUIRE(dA && a && z && mean && rstd && dbeta && dgamma && C % 2 == 0, "bn_bwd_reduce: bad arguments");
+    FI_REQUIRE((C / 2) <= 256 ? 256 % (C / 2) == 0 : (C / 2) % 256 == 0, "bn_bwd_reduce: C/2 must divide 256 or be a multiple");
+    bn_relu_bwd_reduce_kernel<<<blocks_for(P, C / 2 <= 256 ? 256 / (C / 2) : 1, 148 * 4), 256, 0, st>>>(
+        static_cast<const uint32_t*>(dA), static_cast<const uint32_t*>(a), static_cast<const uint32_t*>(z), P, C / 2,
+        mean, rstd, dbeta, dgamma);
+    return last_error();
+}
+const char* bn_relu_bwd_apply_launch(const void* dA, const void* a, const void* z, long long P, int C, const float* mean,
+                                     const float* rstd, const float* gamma, const float* dbeta, const float* dgamma,
+                                     void* dz, cudaStream_t st) {
+    FI_REQUIRE(dA && a && z && dz && C % 8 == 0, "bn_bwd_apply: bad arguments");
+    const long long n8 = P * (C / 8);
+    bn_relu_bwd_apply_kernel<<<blocks_for(n8, 256), 256, 0, st>>>(
+        static_cast<const uint4*>(dA), static_cast<const uint4*>(a), static_cast<const uint4*>(z), n8, C / 8,
+        1.0f / static_cast<float>(P), mean, rstd, gamma, dbeta, dgamma, static_cast<uint4*>(dz));
+    return last_error();
+}
+const char* maxpool_bwd_add_launch(const void* a_full, const void* a_pool, const void* d_pool, const void* d_skip,
+                                   void* d_full, int N, int H, int W, int C, cudaStream_t st) {
+    FI_REQUIRE(a_full && a_pool && d_pool && d_full && C % 8 == 0 && H >= 2 && W >= 2, "maxpool_bwd: bad arguments");
+    maxpool_bwd_add_kernel<<<blocks_for(static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, st>>>(
+        static_cast<const uint4*>(a_full), static_cast<const uint4*>(a_pool), static_cast<const uint4*>(d_pool),
+        static_cast<const uint4*>(d_skip), static_cast<uint4*>(d_full), N, H, W, C / 8);
+    return last_error();
+}
+const char* upsample2x_bwd_launch(const void* d_up, void* d_lo, int N, int h, int w, int C, cudaStream_t st) {
+    FI_REQUIRE(d_up && d_lo && C % 8 == 0, "upsample_bwd: bad arguments");
+    upsample2x_bwd_kernel<<<blocks_for(static_cast<long long>(N) * h * w * (C / 8), 256), 256, 0, st>>>(
+        static_cast<const uint4*>(d_up), static_cast<uint4*>(d_lo), N, h, w, C / 8);
+    return last_error();
+}
+int transpose_pad_row(int W) { return (W + 2 + 7) / 8 * 8; }
+long long transpose_pad_k(int N, int H, int W) {
+    const long long k = static_cast<long long>(N) * (H + 2) * transpose_pad_row(W);
+    return (k + 63) / 64 * 64;
+}
+const char* transpose_pad_launch(const void* x, void* xT, int N, int H, int W, int C, int copies, cudaStream_t st) {
+    FI_REQUIRE(x && xT && N > 0 && C > 0 && (copies == 1 || copies == 3), "transpose_pad: bad arguments");
+    const long long Kp = transpose_pad_k(N, H, W);
+    transpose_pad_kernel<<<dim3(static_cast<unsigned>(Kp / 32), (C + 31) / 32, copies), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(xT), N, H, W, C, transpose_pad_row(W), Kp,
+        copies == 3 ? -1 : 0);
+    return last_error();
+}
+const char* stem_wgrad_launch(const void* dz, const float* x, int N, int H, int W, int cin, float* dW, cudaStream_t st) {
+    FI_REQUIRE(dz && x && dW && cin >= 1 && cin <= 8, "stem_wgrad: bad arguments");
+    stem_wgrad_kernel<<<blocks_for(static_cast<long long>(N) * H * W, 8, 148 * 2), 256, 0, st>>>(
+        static_cast<const uint32_t*>(dz), x, N, H, W, cin, dW);
+    return last_error();
+}
+const char* adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                        int step, cudaStream_t st) {
+    FI_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adam: bad arguments");
+    adam_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, 1.f - powf(b1, static_cast<float>(step)),
+                                                   1.f - powf(b2, static_cast<float>(step)));
+    return last_error();
+}
+const char* pack_conv_launch(const float* w, int co, int ci, void* fwd, void* bwd, cudaStream_t st) {
+    FI_REQUIRE(w && (fwd || bwd) && co > 0 && ci > 0, "pack_conv: bad arguments");
+    pack_conv_kernel<<<blocks_for(static_cast<long long>(co) * ci * 9, 256), 256, 0, st>>>(
+        w, co, ci, static_cast<__nv_bfloat16*>(fwd), static_cast<__nv_bfloat16*>(bwd));
+    return last_error();
+}
+
+}  // namespace fi

@@ -1,0 +1,39 @@
+// Launchers of the training-step kernels (train_kernels.cu, wgrad_gemm.cu). Device pointers; nullptr return = ok.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace fi {
+
+const char* bn_stats_launch(const void* z, long long P, int C, float* sum, float* sumsq, cudaStream_t st);
+const char* bn_apply_relu_launch(const void* z, long long P, int C, const float* scale, const float* shift, void* a,
+                                 cudaStream_t st);
+const char* head_forward_launch(const void* a, int N, long long HW, const float* w, const float* b, int ncls, float* y,
+                                cudaStream_t st);
+const char* mse_launch(const float* y, const float* t, long long n, float* loss, float* dy, cudaStream_t st);
+const char* head_backward_launch(const void* a, const float* dy, int N, long long HW, const float* w, int ncls, void* da,
+                                 float* dw, float* db, cudaStream_t st);
+const char* bn_relu_bwd_reduce_launch(const void* dA, const void* a, const void* z, long long P, int C, const float* mean,
+                                      const float* rstd, float* dbeta, float* dgamma, cudaStream_t st);
+const char* bn_relu_bwd_apply_launch(const void* dA, const void* a, const void* z, long long P, int C, const float* mean,
+                                     const float* rstd, const float* gamma, const float* dbeta, const float* dgamma,
+                                     void* dz, cudaStream_t st);
+const char* maxpool_bwd_add_launch(const void* a_full, const void* a_pool, const void* d_pool, const void* d_skip,
+                                   void* d_full, int N, int H, int W, int C, cudaStream_t st);
+const char* upsample2x_bwd_launch(const void* d_up, void* d_lo, int N, int h, int w, int C, cudaStream_t st);
+int transpose_pad_row(int W);                    // padded image row pitch: W + 2 rounded up to 8
+long long transpose_pad_k(int N, int H, int W);  // padded K length of the transposed layout (multiple of 64)
+// copies = 1: xT[c][q]; copies = 3: xT[s][c][q] = row shifted by s-1 elements (the three column taps)
+const char* transpose_pad_launch(const void* x, void* xT, int N, int H, int W, int C, int copies, cudaStream_t st);
+const char* stem_wgrad_launch(const void* dz, const float* x, int N, int H, int W, int cin, float* dW, cudaStream_t st);
+const char* adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                        int step, cudaStream_t st);
+const char* pack_conv_launch(const float* w, int co, int ci, void* fwd, void* bwd, cudaStream_t st);
+
+// wgrad_gemm.cu: dW[tap][co][ci] += sum_q dzT[co][q] * xT3[dx][ci][q + (dy-1)*Wp8]   (tcgen05, split-K, fp32 atomics)
+const char* wgrad_launch(const void* dzT, const void* xT3, int cout, int cin, long long Kp, int Wp8, float* dW,
+                         int num_sms, cudaStream_t st);
+
+}  // namespace fi

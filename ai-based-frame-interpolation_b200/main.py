@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """CLI with the reference main.py's sub-commands and flags (reference main.py:40-72): train / infer / video / serve /
-info. `infer` and `video` drive model.inference.FrameInterpolator, i.e. the B200 path; `train` is not part of the
-inference hot path and says so."""
+info. `infer` and `video` drive model.inference.FrameInterpolator, `train` drives model.train.main (the B200
+training step)."""
 import argparse
 import os
 import sys
@@ -47,9 +47,10 @@ def main(argv=None):
     device = "cuda" if device == "auto" else device
     try:
         if args.command == "train":
-            print("train: the training step (train-mode BatchNorm, backward, Adam) is not part of the B200 inference "
-                  "path yet; use the reference's model/train.py and load its checkpoint here.")
-            return 2
+            from model.train import main as train_main
+            train_main(["--data-dir", args.data_dir, "--epochs", str(args.epochs), "--batch-size", str(args.batch_size),
+                        "--lr", str(args.lr), "--device", args.device])
+            return 0
         if args.command == "infer":
             import cv2
             from model.inference import FrameInterpolator

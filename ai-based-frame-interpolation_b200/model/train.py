@@ -1,0 +1,480 @@
+"""Training step of the reference's model/train.py (train_model's inner loop, :183-199: forward in training mode,
+loss, backward, Adam) on the B200 kernels — SURVEY.md §8f row 2 / BASELINE config "MSE + Adam, batch 16 at 256x256".
+
+What runs where
+  conv3x3 forward, conv3x3 data gradient   tcgen05 implicit-GEMM kernels (fiConvGemm; dgrad = conv with flipped weights)
+  conv3x3 weight gradient                  tcgen05 split-K GEMM over the pixel dimension (fiWgrad) on transposed operands
+  BatchNorm (batch statistics) fwd / bwd, ReLU, max-pool / bilinear-upsample backward, 1x1 head, MSE, Adam: CUDA-core
+                                           kernels in csrc/train_kernels.cu
+  gradient all-reduce                      torch.distributed (NCCL) on one flat fp32 gradient buffer
+PyTorch holds the fp32 master parameters (the module's own nn.Parameters), the flat gradient / Adam buffers and does
+per-channel vector arithmetic of BatchNorm (C-sized tensors); every per-pixel FLOP is in the library.
+
+Scope: FrameInterpolationUNet / UNet with bilinear=True (what the reference's train.py builds, model/train.py:299),
+H and W multiples of 16 (the reference trains at 256x256, model/train.py:138), bf16 activations and activation
+gradients, fp32 master parameters / gradients / Adam state. Loss: criterion=None is the fused MSE kernel (BASELINE
+config 5); any torch callable on the [N,1,H,W] fp32 network output (e.g. CombinedLoss below, the reference's
+0.5*MSE + 0.5*(1-SSIM), model/train.py:75-87) is differentiated by torch autograd on that one tensor and its
+gradient enters the library backward — the loss touches 1/1000 of the step's bytes.
+
+Also here, mirroring the reference file: SSIMLoss / CombinedLoss, FrameTripletDataset, train_model (same checkpoint
+keys, ReduceLROnPlateau(factor 0.5, patience 10) schedule) and main().
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import math
+import os
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+try:
+    from . import _engine as E
+    from .unet import FrameInterpolationUNet, UNet
+except ImportError:  # model/ on sys.path, like the reference's scripts
+    import _engine as E
+    from unet import FrameInterpolationUNet, UNet
+
+BN_MOMENTUM = 0.1
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _Layer:
+    """One conv3x3 + BatchNorm + ReLU stage: parameters, packed weights and what the backward needs."""
+
+    def __init__(self, name, conv, bn, src, src1=None):
+        self.name, self.conv, self.bn, self.src, self.src1 = name, conv, bn, src, src1
+        self.cout, self.cin = conv.weight.shape[0], conv.weight.shape[1]
+
+
+class TrainStep:
+    """loss = TrainStep(model, lr=1e-4)(frame1, frame2, target) — one optimisation step in place on `model`."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, criterion=None):
+        self.criterion = criterion
+        unet = model.unet if isinstance(model, FrameInterpolationUNet) else model
+        if not isinstance(unet, UNet) or not unet.bilinear:
+            raise E.FiError("the B200 training step covers the bilinear UNet (what reference train.py builds)")
+        self.model, self.unet = model, unet
+        self.lr, self.betas, self.eps, self.step_count = lr, betas, eps, 0
+        p0 = next(model.parameters())
+        self.device = E.require_cuda(p0.device)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.flat_param = torch.empty(n, dtype=torch.float32, device=self.device)
+        self.m = torch.zeros_like(self.flat_grad)
+        self.v = torch.zeros_like(self.flat_grad)
+        off = 0
+        self.grad_view = {}
+        with torch.no_grad():  # parameters become views of one flat buffer: Adam and the all-reduce see one vector
+            for p in self.params:
+                k = p.numel()
+                self.flat_param[off:off + k] = p.detach().reshape(-1)
+                p.data = self.flat_param[off:off + k].view_as(p)
+                self.grad_view[p] = self.flat_grad[off:off + k].view_as(p)
+                off += k
+        u = unet
+        dc = lambda m: m.double_conv  # noqa: E731
+        L = []
+        L.append(_Layer("inc.0", dc(u.inc)[0], dc(u.inc)[1], "input"))
+        L.append(_Layer("inc.3", dc(u.inc)[3], dc(u.inc)[4], "inc.0"))
+        for i, d in enumerate((u.down1, u.down2, u.down3, u.down4), 1):
+            blk = dc(d.maxpool_conv[1])
+            L.append(_Layer(f"down{i}.0", blk[0], blk[1], f"pool{i}"))
+            L.append(_Layer(f"down{i}.3", blk[3], blk[4], f"down{i}.0"))
+        skips = ["down3.3", "down2.3", "down1.3", "inc.3"]
+        for i, up in enumerate((u.up1, u.up2, u.up3, u.up4), 1):
+            blk = dc(up.conv)
+            L.append(_Layer(f"up{i}.0", blk[0], blk[1], skips[i - 1], f"up{i}.up"))
+            L.append(_Layer(f"up{i}.3", blk[3], blk[4], f"up{i}.0"))
+        self.layers = L
+        self.lib = E.lib()
+
+    def state_dict(self):
+        """torch.optim.Adam-shaped state: per-parameter step / exp_avg / exp_avg_sq plus the param group."""
+        state, off = {}, 0
+        for i, p in enumerate(self.params):
+            k = p.numel()
+            state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.m[off:off + k].view_as(p).clone(),
+                        "exp_avg_sq": self.v[off:off + k].view_as(p).clone()}
+            off += k
+        return {"state": state, "param_groups": [{"lr": self.lr, "betas": self.betas, "eps": self.eps,
+                                                  "weight_decay": 0, "amsgrad": False,
+                                                  "params": list(range(len(self.params)))}]}
+
+    def load_state_dict(self, sd):
+        off = 0
+        for i, p in enumerate(self.params):
+            k = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                self.m[off:off + k] = st["exp_avg"].reshape(-1).to(self.device)
+                self.v[off:off + k] = st["exp_avg_sq"].reshape(-1).to(self.device)
+                self.step_count = int(st["step"])
+            off += k
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps = g["lr"], tuple(g["betas"]), g["eps"]
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def _conv(self, src, wpack, n_total, src1=None):
+        """bf16 NHWC conv3x3 (no bias, no ReLU) through the tcgen05 kernels."""
+        n, h, w, c0 = src.shape
+        d = E.ConvDesc()
+        d.src0, d.c0, d.N, d.H, d.W = src.data_ptr(), c0, n, h, w
+        if src1 is not None:
+            d.src1, d.c1, d.h1, d.w1 = src1.data_ptr(), src1.shape[3], src1.shape[1], src1.shape[2]
+        dst = torch.empty((n, h, w, n_total), dtype=torch.bfloat16, device=self.device)
+        zero = self._zero_bias(n_total)
+        d.wpack, d.bias, d.n_total, d.taps, d.mode, d.relu, d.dst = (wpack.data_ptr(), zero.data_ptr(), n_total, 9,
+                                                                     E.EPI_STORE, 0, dst.data_ptr())
+        E.check(self.lib.fiConvGemm(C.byref(d), E.current_stream()))
+        return dst
+
+    def _zero_bias(self, n):
+        z = getattr(self, "_zeros", None)
+        if z is None or z.numel() < n:
+            z = self._zeros = torch.zeros(max(n, 1024), dtype=torch.float32, device=self.device)
+        return z
+
+    def _bn_forward(self, layer, z):
+        """Batch statistics -> a = relu(bn(z)); returns (a, mean, rstd) and updates the running statistics."""
+        n, h, w, c = z.shape
+        P = n * h * w
+        stats = torch.zeros(2, c, dtype=torch.float32, device=self.device)
+        E.check(self.lib.fiBnStats(_ptr(z), P, c, _ptr(stats[0]), _ptr(stats[1]), E.current_stream()))
+        mean = stats[0] / P
+        var = (stats[1] / P - mean * mean).clamp_min_(0.0)
+        rstd = torch.rsqrt(var + layer.bn.eps)
+        scale = layer.bn.weight.detach() * rstd
+        shift = layer.bn.bias.detach() - mean * scale
+        a = torch.empty_like(z)
+        E.check(self.lib.fiBnApplyRelu(_ptr(z), P, c, _ptr(scale), _ptr(shift), _ptr(a), E.current_stream()))
+        with torch.no_grad():  # nn.BatchNorm2d bookkeeping (unbiased variance for the running estimate)
+            layer.bn.running_mean.mul_(1 - BN_MOMENTUM).add_(mean, alpha=BN_MOMENTUM)
+            layer.bn.running_var.mul_(1 - BN_MOMENTUM).add_(var * (P / max(P - 1, 1)), alpha=BN_MOMENTUM)
+            layer.bn.num_batches_tracked += 1
+        return a, mean, rstd
+
+    def _transposed(self, tensors, n, h, w, copies):
+        """Channel-major zero-padded copies of the (concatenated) NHWC tensors: operand layouts of fiWgrad
+        ([copies][C_total][Kp]; 3 copies = the rows shifted by -1/0/+1 for the three column taps)."""
+        kp = self.lib.fiTransposePadK(n, h, w)
+        ctot = sum(t.shape[3] for t in tensors)
+        out = torch.empty((copies, ctot, kp), dtype=torch.bfloat16, device=self.device)
+        row = 0
+        for t in tensors:
+            c = t.shape[3]
+            if copies == 1 or len(tensors) == 1:
+                E.check(self.lib.fiTransposePad(_ptr(t), _ptr(out[0, row:]), n, h, w, c, copies, E.current_stream()))
+            else:  # concatenated sources: each copy's rows are [skip | up], so place the copies one by one
+                tmp = torch.empty((copies, c, kp), dtype=torch.bfloat16, device=self.device)
+                E.check(self.lib.fiTransposePad(_ptr(t), _ptr(tmp), n, h, w, c, copies, E.current_stream()))
+                out[:, row:row + c] = tmp
+            row += c
+        return out, kp
+
+    # ------------------------------------------------------------------------------------------------ one step
+    @torch.no_grad()
+    def __call__(self, frame1, frame2, target):
+        lib, st = self.lib, E.current_stream
+        x = torch.cat([frame1, frame2], 1).contiguous().float() if frame2 is not None else frame1.contiguous().float()
+        n, cin0, h, w = x.shape
+        if h % 16 or w % 16:
+            raise E.FiError("the training step needs H and W to be multiples of 16 (the reference trains at 256x256)")
+        with torch.cuda.device(self.device):
+            self.flat_grad.zero_()
+            acts, zs, stats, packs = {}, {}, {}, {}
+            # ---- pack weights (bf16 forward rows, flipped/transposed rows for the data gradient)
+            for l in self.layers:
+                wt = l.conv.weight.detach()
+                if l.name == "inc.0":
+                    kp = lib.fiStemPackedK(l.cin)
+                    packed = torch.empty((64, kp), dtype=torch.int16)
+                    wc = wt.cpu().contiguous()
+                    E.check(lib.fiStemPackWeights(wc.data_ptr(), l.cin, packed.data_ptr()))
+                    packs[l.name] = (packed.to(self.device), None)
+                else:
+                    fwd = torch.empty((l.cout, 9 * l.cin), dtype=torch.bfloat16, device=self.device)
+                    bwd = torch.empty((l.cin, 9 * l.cout), dtype=torch.bfloat16, device=self.device)
+                    E.check(lib.fiPackConvWeights(_ptr(wt), l.cout, l.cin, _ptr(fwd), _ptr(bwd), st()))
+                    packs[l.name] = (fwd, bwd)
+            # ---- forward (training-mode BatchNorm)
+            for l in self.layers:
+                if l.name == "inc.0":
+                    z = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=self.device)
+                    p0 = E.planes_of(x)
+                    E.check(lib.fiStemConvLinear(C.byref(p0), None, E.FI_IN_F32, _ptr(packs[l.name][0]),
+                                                 _ptr(self._zero_bias(64)), _ptr(z), n, h, w, st()))
+                else:
+                    if l.src.startswith("pool"):
+                        full = acts[self.layers[self.layers.index(l) - 1].name]
+                        fn, fh, fw, fc = full.shape
+                        pooled = torch.empty((fn, fh // 2, fw // 2, fc), dtype=torch.bfloat16, device=self.device)
+                        E.check(lib.fiMaxPool2x2(_ptr(full), _ptr(pooled), fn, fh, fw, fc, st()))
+                        acts[l.src] = pooled
+                    if l.src1 is not None:
+                        lo = acts[self.layers[self.layers.index(l) - 1].name]
+                        ln, lh, lw, lc = lo.shape
+                        up = torch.empty((ln, 2 * lh, 2 * lw, lc), dtype=torch.bfloat16, device=self.device)
+                        E.check(lib.fiUpsample2x(_ptr(lo), _ptr(up), ln, lh, lw, lc, st()))
+                        acts[l.src1] = up
+                    z = self._conv(acts[l.src], packs[l.name][0], l.cout, acts.get(l.src1) if l.src1 else None)
+                zs[l.name] = z
+                acts[l.name], mean, rstd = self._bn_forward(l, z)
+                stats[l.name] = (mean, rstd)
+            last = acts["up4.3"]
+            hw_, hb = self.unet.outc.conv.weight.detach().reshape(-1, 64).contiguous(), self.unet.outc.conv.bias.detach()
+            ncls = hw_.shape[0]
+            y = torch.empty((n, ncls, h, w), dtype=torch.float32, device=self.device)
+            E.check(lib.fiHeadForward(_ptr(last), n, h * w, _ptr(hw_), _ptr(hb), ncls, _ptr(y), st()))
+            tgt = target.contiguous().float()
+            if self.criterion is None:
+                loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+                dy = torch.empty_like(y)
+                E.check(lib.fiMseLossGrad(_ptr(y), _ptr(tgt), y.numel(), _ptr(loss), _ptr(dy), st()))
+            else:  # a torch loss on the network output: autograd on this one [N,ncls,H,W] tensor only
+                with torch.enable_grad():
+                    y_req = y.detach().requires_grad_(True)
+                    loss_t = self.criterion(y_req, tgt)
+                    dy, = torch.autograd.grad(loss_t, y_req)
+                loss, dy = loss_t.detach().reshape(1), dy.contiguous().float()
+            # ---- backward
+            grads = {}  # gradient w.r.t. the activation named by the key
+            dA = torch.empty_like(last)
+            gw = self.grad_view[self.unet.outc.conv.weight].view(ncls, 64)
+            gb = self.grad_view[self.unet.outc.conv.bias]
+            E.check(lib.fiHeadBackward(_ptr(last), _ptr(dy), n, h * w, _ptr(hw_), ncls, _ptr(dA), _ptr(gw), _ptr(gb), st()))
+            grads["up4.3"] = dA
+            for l in reversed(self.layers):
+                a, z = acts[l.name], zs[l.name]
+                ln, lh, lw, lc = z.shape
+                P = ln * lh * lw
+                mean, rstd = stats[l.name]
+                dA = grads.pop(l.name)
+                red = torch.zeros(2, lc, dtype=torch.float32, device=self.device)  # dbeta, dgamma
+                E.check(lib.fiBnReluBackwardReduce(_ptr(dA), _ptr(a), _ptr(z), P, lc, _ptr(mean), _ptr(rstd), _ptr(red[0]),
+                                                   _ptr(red[1]), st()))
+                gamma = l.bn.weight.detach()
+                dz = torch.empty_like(z)
+                E.check(lib.fiBnReluBackwardApply(_ptr(dA), _ptr(a), _ptr(z), P, lc, _ptr(mean), _ptr(rstd), _ptr(gamma),
+                                                  _ptr(red[0]), _ptr(red[1]), _ptr(dz), st()))
+                self.grad_view[l.bn.bias].add_(red[0])
+                self.grad_view[l.bn.weight].add_(red[1])
+                # weight gradient
+                if l.name == "inc.0":
+                    E.check(lib.fiStemWgrad(_ptr(dz), _ptr(x), n, h, w, l.cin, _ptr(self.grad_view[l.conv.weight]), st()))
+                    continue
+                srcs = [acts[l.src]] + ([acts[l.src1]] if l.src1 else [])
+                dzT, kp = self._transposed([dz], ln, lh, lw, 1)
+                xT, _ = self._transposed(srcs, ln, lh, lw, 3)
+                dW = torch.zeros((9, l.cout, l.cin), dtype=torch.float32, device=self.device)
+                E.check(lib.fiWgrad(_ptr(dzT), _ptr(xT), l.cout, l.cin, kp, lib.fiTransposePadRow(lw), _ptr(dW), st()))
+                self.grad_view[l.conv.weight].add_(dW.permute(1, 2, 0).reshape(l.cout, l.cin, 3, 3))
+                # data gradient(s): conv3x3 of dz with the flipped, transposed weights
+                bwd = packs[l.name][1]
+                c0 = srcs[0].shape[3]
+                d_src = self._conv(dz, bwd[:c0], c0)
+                if l.src1:
+                    d_up = self._conv(dz, bwd[c0:], l.cin - c0)
+                    below = self.layers[self.layers.index(l) - 1].name   # the tensor that was upsampled
+                    bn_, bh, bw_, bc = acts[below].shape
+                    d_lo = torch.empty_like(acts[below])
+                    E.check(lib.fiUpsample2xBackward(_ptr(d_up), _ptr(d_lo), bn_, bh, bw_, bc, st()))
+                    grads[below] = d_lo
+                    grads["skip:" + l.src] = d_src       # joins the encoder-side gradient at the pool backward
+                elif l.src.startswith("pool"):
+                    full_name = self.layers[self.layers.index(l) - 1].name
+                    full = acts[full_name]
+                    fn, fh, fw, fc = full.shape
+                    d_full = torch.empty_like(full)
+                    skip = grads.pop("skip:" + full_name, None)
+                    E.check(lib.fiMaxPoolBackwardAdd(_ptr(full), _ptr(acts[l.src]), _ptr(d_src), _ptr(skip), _ptr(d_full),
+                                                     fn, fh, fw, fc, st()))
+                    grads[full_name] = d_full
+                else:
+                    grads[l.src] = d_src
+            # ---- gradient all-reduce across data-parallel replicas (NCCL over NVLink), then Adam
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(self.flat_grad)
+                self.flat_grad.div_(dist.get_world_size())
+            self.step_count += 1
+            E.check(lib.fiAdamStep(_ptr(self.flat_param), _ptr(self.flat_grad), _ptr(self.m), _ptr(self.v),
+                                   self.flat_param.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                   self.step_count, st()))
+            # the inference engine mirrors the parameters lazily: force a re-upload on the next eval forward
+            for mod in (self.model, self.unet):
+                mod.__dict__["_fi_print"] = None
+        self.last_output, self.last_activations = y, acts
+        return loss
+
+
+# ---------------------------------------------------------------------------------------------------- reference surface
+class SSIMLoss(nn.Module):
+    """1 - SSIM with an 11x11 Gaussian window (sigma 1.5), zero-padded 'same' filtering, C1 = 0.01^2, C2 = 0.03^2 —
+    the loss of reference model/train.py:18-73 (torch ops on the network output; see the module docstring)."""
+
+    def __init__(self, window_size=11, size_average=True, channel=1):
+        super().__init__()
+        self.window_size, self.size_average, self.channel = window_size, size_average, channel
+        self.window = self._create_window(window_size, channel)
+
+    @staticmethod
+    def _gaussian(window_size, sigma):
+        x = torch.arange(window_size, dtype=torch.float64) - window_size // 2
+        g = torch.exp(-x * x / (2.0 * sigma * sigma))
+        return (g / g.sum()).float()
+
+    def _create_window(self, window_size, channel):
+        g = self._gaussian(window_size, 1.5)
+        return torch.outer(g, g).expand(channel, 1, window_size, window_size).contiguous()
+
+    def forward(self, img1, img2):
+        c = img1.shape[1]
+        if c != self.channel or self.window.device != img1.device or self.window.dtype != img1.dtype:
+            self.window, self.channel = self._create_window(self.window_size, c).to(img1), c
+        win, pad = self.window, self.window_size // 2
+        blur = lambda t: F.conv2d(t, win, padding=pad, groups=c)  # noqa: E731
+        mu1, mu2 = blur(img1), blur(img2)
+        s11, s22, s12 = blur(img1 * img1) - mu1 * mu1, blur(img2 * img2) - mu2 * mu2, blur(img1 * img2) - mu1 * mu2
+        c1, c2 = 0.01 ** 2, 0.03 ** 2
+        ssim = ((2 * mu1 * mu2 + c1) * (2 * s12 + c2)) / ((mu1 * mu1 + mu2 * mu2 + c1) * (s11 + s22 + c2))
+        return 1 - (ssim.mean() if self.size_average else ssim.mean((1, 2, 3)))
+
+
+class CombinedLoss(nn.Module):
+    """mse_weight * MSE + ssim_weight * (1 - SSIM) (reference model/train.py:75-87)."""
+
+    def __init__(self, mse_weight=0.5, ssim_weight=0.5):
+        super().__init__()
+        self.mse_weight, self.ssim_weight = mse_weight, ssim_weight
+        self.mse_loss, self.ssim_loss = nn.MSELoss(), SSIMLoss()
+
+    def forward(self, pred, target):
+        return self.mse_weight * self.mse_loss(pred, target) + self.ssim_weight * self.ssim_loss(pred, target)
+
+
+class FrameTripletDataset(torch.utils.data.Dataset):
+    """(frame_t0, frame_t1, ground_truth_mid) from <data_dir>/<video>/<sorted frames>: frames i and i+2 are the inputs,
+    i+1 the target; grayscale, resized to 256x256, [0,1] fp32 [1,H,W] (reference model/train.py:89-151)."""
+
+    EXTENSIONS = (".jpg", ".png", ".bmp")
+
+    def __init__(self, data_dir, sequence_length=3):
+        self.data_dir, self.sequence_length = data_dir, sequence_length
+        self.triplets = []
+        for video in os.listdir(data_dir):
+            path = os.path.join(data_dir, video)
+            if not os.path.isdir(path):
+                continue
+            frames = sorted(f for f in os.listdir(path) if f.endswith(self.EXTENSIONS))
+            for i in range(len(frames) - 2):
+                self.triplets.append({"video_dir": path, "frame_t0": frames[i], "frame_t1": frames[i + 2],
+                                      "ground_truth": frames[i + 1]})
+
+    def __len__(self):
+        return len(self.triplets)
+
+    def __getitem__(self, idx):
+        import cv2
+        import numpy as np
+        t = self.triplets[idx]
+        out = []
+        for key in ("frame_t0", "frame_t1", "ground_truth"):
+            img = cv2.imread(os.path.join(t["video_dir"], t[key]), cv2.IMREAD_GRAYSCALE)
+            img = cv2.resize(img, (256, 256)).astype(np.float32) / 255.0
+            out.append(torch.from_numpy(img).unsqueeze(0))
+        return tuple(out)
+
+
+class _PlateauSchedule:
+    """optim.lr_scheduler.ReduceLROnPlateau(mode='min', factor=0.5, patience=10) with torch's default relative
+    threshold 1e-4 (reference model/train.py:163-165), acting on TrainStep.lr."""
+
+    def __init__(self, step, factor=0.5, patience=10, threshold=1e-4):
+        self.step_obj, self.factor, self.patience, self.threshold = step, factor, patience, threshold
+        self.best, self.bad = math.inf, 0
+
+    def step(self, metric):
+        if metric < self.best * (1 - self.threshold):
+            self.best, self.bad = metric, 0
+        else:
+            self.bad += 1
+        if self.bad > self.patience:
+            self.step_obj.lr *= self.factor
+            self.bad = 0
+
+
+def train_model(model, train_loader, val_loader, num_epochs=100, device="cuda", criterion="combined", lr=1e-4,
+                checkpoint_path="best_model.pth"):
+    """The reference's train_model (model/train.py:153-249): Adam(lr=1e-4), CombinedLoss, plateau schedule, best
+    checkpoint by validation loss with the same dictionary keys. The optimisation step is TrainStep (B200 kernels);
+    validation runs the eval-mode inference path. criterion: "combined" | "mse" | a torch callable."""
+    crit = CombinedLoss() if criterion == "combined" else (None if criterion == "mse" else criterion)
+    val_crit = crit if crit is not None else nn.MSELoss()
+    step = TrainStep(model, lr=lr, criterion=crit)
+    sched = _PlateauSchedule(step)
+    train_losses, val_losses, best = [], [], math.inf
+    print(f"Starting training for {num_epochs} epochs...")
+    print(f"Using device: {device}")
+    for epoch in range(num_epochs):
+        model.train()
+        total = 0.0
+        for f0, f1, gt in train_loader:
+            total += step(f0.to(device), f1.to(device), gt.to(device)).item()
+        train_losses.append(total / max(len(train_loader), 1))
+        model.eval()
+        total = 0.0
+        with torch.no_grad():
+            for f0, f1, gt in val_loader:
+                total += val_crit(model(f0.to(device), f1.to(device)), gt.to(device)).item()
+        val_losses.append(total / max(len(val_loader), 1))
+        sched.step(val_losses[-1])
+        print(f"Epoch {epoch + 1}/{num_epochs}:\n  Train Loss: {train_losses[-1]:.6f}\n  Val Loss: {val_losses[-1]:.6f}\n"
+              f"  Learning Rate: {step.lr:.2e}")
+        if val_losses[-1] < best:
+            best = val_losses[-1]
+            torch.save({"epoch": epoch, "model_state_dict": model.state_dict(),
+                        "optimizer_state_dict": step.state_dict(), "train_loss": train_losses[-1],
+                        "val_loss": val_losses[-1], "train_losses": train_losses, "val_losses": val_losses},
+                       checkpoint_path)
+            print(f"  New best model saved! (Val Loss: {best:.6f})")
+        print("-" * 50)
+    print(f"Training completed! Best validation loss: {best:.6f}")
+    return train_losses, val_losses
+
+
+def main(argv=None):
+    """python model/train.py --data-dir D [--epochs 100 --batch-size 8 --device auto --val-split 0.2]
+    (reference model/train.py:251-313)."""
+    ap = argparse.ArgumentParser(description="Train Frame Interpolation UNet (B200 training step)")
+    ap.add_argument("--data-dir", required=True)
+    ap.add_argument("--epochs", type=int, default=100)
+    ap.add_argument("--batch-size", type=int, default=8)
+    ap.add_argument("--device", default="auto")
+    ap.add_argument("--val-split", type=float, default=0.2)
+    ap.add_argument("--lr", type=float, default=1e-4)
+    args = ap.parse_args(argv)
+    device = torch.device("cuda" if args.device == "auto" else args.device)
+    E.require_cuda(device)
+    data = FrameTripletDataset(args.data_dir)
+    n_val = int(len(data) * args.val_split)
+    train_set, val_set = torch.utils.data.random_split(data, [len(data) - n_val, n_val])
+    print(f"Dataset split: {len(train_set)} train, {len(val_set)} validation")
+    mk = lambda d, sh: torch.utils.data.DataLoader(d, batch_size=args.batch_size, shuffle=sh, num_workers=4,  # noqa: E731
+                                                   pin_memory=True)
+    model = FrameInterpolationUNet(bilinear=True).to(device)
+    print(f"Model parameters: {sum(p.numel() for p in model.parameters()):,} total")
+    train_model(model, mk(train_set, True), mk(val_set, False), num_epochs=args.epochs, device=device, lr=args.lr)
+    print("Training completed successfully!")
+
+
+if __name__ == "__main__":
+    main()

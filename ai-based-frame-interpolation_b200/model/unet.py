@@ -6,7 +6,8 @@ The nn.Module objects below are parameter containers only: they exist so that `.
 (state-dict schema: SURVEY.md A.5 / reference model/unet.py:5-112). The arithmetic lives in csrc/:
   DoubleConv / Down / Up / OutConv   -> conv_gemm.cu (tcgen05 implicit GEMM, BN folded, pool / concat / head fused)
   first conv of `inc`                -> aux_kernels.cu stem kernel (frame-pair cat + normalisation fused)
-There is no CPU fallback and no training-mode forward (train-mode BatchNorm is a later row of the scope table).
+There is no CPU fallback. forward() is the inference path (eval mode); the training-mode forward + backward + Adam
+of the reference's train.py is model/train.py:TrainStep, which works on these same modules' parameters.
 """
 from __future__ import annotations
 
@@ -82,7 +83,7 @@ def _run_conv(x, w, bias, *, x1=None, off=(0, 0), taps=9, mode=_E.EPI_STORE, rel
 def _check_standalone(x, module):
     _E.require_cuda(x.device)
     if module.training:
-        raise _E.FiError("training-mode forward is not part of the B200 inference path; call .eval() first")
+        raise _E.FiError("forward() is the inference path: call .eval() first (training: model.train.TrainStep)")
     if x.dtype != torch.float32 or x.dim() != 4:
         raise _E.FiError("expected an fp32 NCHW tensor")
 
@@ -138,8 +139,8 @@ class _EngineBacked(nn.Module):
 
     def _engine(self, device):
         if self.training:
-            raise _E.FiError("training-mode forward (batch-statistics BatchNorm) is not part of the B200 inference "
-                             "path; call .eval() first")
+            raise _E.FiError("forward() is the inference path: call .eval() first; the training-mode forward, "
+                             "backward and Adam step are model.train.TrainStep")
         net = self.__dict__.get("_fi_net")
         if net is None or net.device != device or net.precision != self.precision:
             if net is not None:

@@ -160,6 +160,9 @@ int fiStemPackedK(int cin);
 int fiStemPackWeights(const float* w_host, int cin, uint16_t* out_host);
 int fiStemConv(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const void* wpack, const float* bias, void* dst,
                int N, int H, int W, void* stream);
+/* Same without the ReLU: the training forward keeps the pre-BatchNorm conv output. */
+int fiStemConvLinear(const fiPlanes* in0, const fiPlanes* in1, int in_dtype, const void* wpack, const float* bias,
+                     void* dst, int N, int H, int W, void* stream);
 /* nn.MaxPool2d(2) (model/unet.py:28) on bf16 NHWC [N,H,W,C] -> [N,H/2,W/2,C]; inside fiNetForward the pool is fused into
  * the producing convolution, this entry point serves the stand-alone Down module. */
 int fiMaxPool2x2(const void* src, void* dst, int N, int H, int W, int C, void* stream);
@@ -179,6 +182,53 @@ int fiHeadPostU8(const float* logits, uint8_t* out, size_t n, void* stream);
 size_t fiSsimPsnrWorkspaceBytes(int N, int H, int W);
 int fiSsimPsnrU8(const uint8_t* pred, const uint8_t* target, int N, int H, int W, double* out, void* workspace,
                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training step (model/train.py:153-249): the kernels around the tensor-core convolutions.
+ * Activations / activation gradients: bf16 NHWC [P = N*H*W][C]; statistics, weight gradients, optimizer state: fp32.
+ * Conv forward and the data gradient reuse fiConvGemm (the latter with the flipped/transposed weights that
+ * fiPackConvWeights writes); the host side of one step is model/train.py:TrainStep.
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* nn.BatchNorm2d in training mode (model/unet.py:13,16): per-channel sum / sum of squares (accumulated into sum, sumsq). */
+int fiBnStats(const void* z, int64_t P, int C, float* sum, float* sumsq, void* stream);
+/* a = relu(z*scale[c] + shift[c]) with scale = gamma*rstd, shift = beta - mean*scale. */
+int fiBnApplyRelu(const void* z, int64_t P, int C, const float* scale, const float* shift, void* a, void* stream);
+/* OutConv (model/unet.py:57-63) on bf16 [N*HW][64] -> fp32 NCHW [N,n_classes,H,W]. */
+int fiHeadForward(const void* a, int N, int64_t HW, const float* w, const float* b, int n_classes, float* y, void* stream);
+/* nn.MSELoss (model/train.py:81): loss += mean((y-t)^2); dy = 2(y-t)/n. */
+int fiMseLossGrad(const float* y, const float* target, int64_t n, float* loss, float* dy, void* stream);
+int fiHeadBackward(const void* a, const float* dy, int N, int64_t HW, const float* w, int n_classes, void* da, float* dw,
+                   float* db, void* stream);
+/* ReLU + BatchNorm backward: dbeta += sum dy, dgamma += sum dy*zhat (dy = dA masked by a > 0); then
+ * dz = gamma*rstd*(dy - dbeta/P - zhat*dgamma/P). */
+int fiBnReluBackwardReduce(const void* dA, const void* a, const void* z, int64_t P, int C, const float* mean,
+                           const float* rstd, float* dbeta, float* dgamma, void* stream);
+int fiBnReluBackwardApply(const void* dA, const void* a, const void* z, int64_t P, int C, const float* mean,
+                          const float* rstd, const float* gamma, const float* dbeta, const float* dgamma, void* dz,
+                          void* stream);
+/* MaxPool2d(2) backward (gradient to the first maximum of each window) plus the skip-connection gradient. */
+int fiMaxPoolBackwardAdd(const void* a_full, const void* a_pool, const void* d_pool, const void* d_skip, void* d_full,
+                         int N, int H, int W, int C, void* stream);
+/* Backward of nn.Upsample(scale_factor=2, bilinear, align_corners=True): [N,2h,2w,C] -> [N,h,w,C]. */
+int fiUpsample2xBackward(const void* d_up, void* d_lo, int N, int h, int w, int C, void* stream);
+/* bf16 NHWC [N,H,W,C] -> channel-major zero-padded rows xT[copy][C][Kp], Kp = fiTransposePadK, padded image rows of
+ * Wp8 = fiTransposePadRow(W) pixels, pixel (n,y,x) at n*(H+2)*Wp8 + (y+1)*Wp8 + x+1. copies = 1: the plain row;
+ * copies = 3: rows shifted by -1, 0, +1 elements (the three column taps; TMA box starts must be 16-byte aligned, so
+ * only the row part of a tap can be a coordinate offset). Operand layouts of fiWgrad: dzT 1 copy, xT 3 copies. */
+int64_t fiTransposePadK(int N, int H, int W);
+int fiTransposePadRow(int W);
+int fiTransposePad(const void* x, void* xT, int N, int H, int W, int C, int copies, void* stream);
+/* Weight gradient of conv3x3: dW[tap][cout][cin] (fp32, accumulated) from the transposed operands; tcgen05 GEMM over
+ * the pixel dimension, split-K with fp32 atomics. Wp8 = fiTransposePadRow(W). fiStemWgrad: the <= 8 input-channel first
+ * conv (x fp32 NCHW), dW[64][cin][9]. */
+int fiWgrad(const void* dzT, const void* xT3, int cout, int cin, int64_t Kp, int Wp8, float* dW, void* stream);
+int fiStemWgrad(const void* dz, const float* x, int N, int H, int W, int cin, float* dW, void* stream);
+/* torch.optim.Adam (model/train.py:160) on one flat fp32 parameter vector; step counts from 1. */
+int fiAdamStep(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+               int step, void* stream);
+/* fp32 [cout][cin][3][3] -> bf16 forward rows [cout][tap*cin+ci] and data-gradient rows [cin][(8-tap)*cout+co]
+ * (either may be NULL). */
+int fiPackConvWeights(const float* w, int cout, int cin, void* fwd, void* bwd, void* stream);
 
 #ifdef __cplusplus
 }
