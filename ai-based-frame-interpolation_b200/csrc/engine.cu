@@ -1118,19 +1118,15 @@ int fiMaxPoolBackwardAdd(const void* a_full, const void* a_pool, const void* d_p
 int fiUpsample2xBackward(const void* d_up, void* d_lo, int N, int h, int w, int C, void* stream) {
     TRAIN_CALL(fi::upsample2x_bwd_launch(d_up, d_lo, N, h, w, C, ST));
 }
-int64_t fiTransposePadK(int N, int H, int W) { return fi::transpose_pad_k(N, H, W); }
-int fiTransposePadRow(int W) { return fi::transpose_pad_row(W); }
-int fiTransposePad(const void* x, void* xT, int N, int H, int W, int C, int copies, void* stream) {
-    TRAIN_CALL(fi::transpose_pad_launch(x, xT, N, H, W, C, copies, ST));
-}
 int fiStemWgrad(const void* dz, const float* x, int N, int H, int W, int cin, float* dW, void* stream) {
     TRAIN_CALL(fi::stem_wgrad_launch(dz, x, N, H, W, cin, dW, ST));
 }
-int fiWgrad(const void* dzT, const void* xT, int cout, int cin, int64_t Kp, int Wp, float* dW, void* stream) {
+int fiWgrad(const void* dz, const void* x0, int c0, const void* x1, int c1, int N, int H, int W, int cout, float* dW,
+            void* stream) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    TRAIN_CALL(fi::wgrad_launch(dzT, xT, cout, cin, Kp, Wp, dW, sms, ST));
+    TRAIN_CALL(fi::wgrad_launch(dz, x0, c0, x1, c1, N, H, W, cout, dW, sms, ST));
 }
 int fiAdamStep(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                int step, void* stream) {

@@ -307,69 +307,47 @@ upsample2x_bwd_kernel(const uint4* __restrict__ d_up, uint4* __restrict__ d_lo, 
     }
 }
 
-// ------------------------------------------------------------------------------------------------ layouts for wgrad
-// x: bf16 NHWC [N,H,W,C] -> channel-major, zero-padded rows xT[copy][c][q]: padded images of (H+2) x Wp8 pixels
-// (Wp8 = W+2 rounded up to 8), pixel (n,y,x) at q = n*(H+2)*Wp8 + (y+1)*Wp8 + (x+1); row length Kp (multiple of 64).
-// TMA needs 16-byte aligned box starts along the contiguous dimension, so the +-1 column shift of a tap cannot be a
-// coordinate offset: copy `s` (blockIdx.z) holds the row shifted by (s-1) elements, xT[s][c][q] = padded(q + s - 1),
-// and the row shift of a tap, (dy-1)*Wp8, is a multiple of 8 elements.
-__global__ void __launch_bounds__(256)
-transpose_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xT, int N, int H, int W, int C,
-                     int Wp8, long long Kp, int first_shift) {
-    __shared__ __nv_bfloat16 tile[32][34];
-    const int Hp = H + 2;
-    const int shift = first_shift + static_cast<int>(blockIdx.z);
-    const long long q0 = static_cast<long long>(blockIdx.x) * 32;  // output index base
-    const int c0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8
-    for (int r = ty; r < 32; r += 8) {
-        const long long q = q0 + r + shift;                        // padded source index
-        __nv_bfloat16 v = __float2bfloat16(0.f);
-        if (q >= 0 && q < static_cast<long long>(N) * Hp * Wp8 && c0 + tx < C) {
-            const int n = static_cast<int>(q / (static_cast<long long>(Hp) * Wp8));
-            const int rem = static_cast<int>(q - static_cast<long long>(n) * Hp * Wp8);
-            const int yp = rem / Wp8, xp = rem - yp * Wp8;
-            if (yp >= 1 && yp <= H && xp >= 1 && xp <= W)
-                v = x[((static_cast<long long>(n) * H + (yp - 1)) * W + (xp - 1)) * C + c0 + tx];
-        }
-        tile[r][tx] = v;
-    }
-    __syncthreads();
-    __nv_bfloat16* out = xT + static_cast<long long>(blockIdx.z) * C * Kp;
-    for (int r = ty; r < 32; r += 8) {
-        const int c = c0 + r;
-        const long long q = q0 + tx;
-        if (c < C && q < Kp) out[static_cast<long long>(c) * Kp + q] = tile[tx][r];
-    }
-}
-
 // Stem weight gradient (C_in <= 8, K = 9*C_in): dW[co][ci][tap] += sum_px dz[px,co] * x[px+tap, ci]; x in NCHW fp32.
+// thread = one channel pair of dz, 8 pixel lanes per block; the 2 x 9*CIN partial sums live in registers (CIN is a
+// template parameter so that the accumulator array is never indexed dynamically), are reduced over the 8 pixel lanes
+// with shared-memory atomics and leave the block as one global atomic per weight.
+template <int CIN>
 __global__ void __launch_bounds__(256)
-stem_wgrad_kernel(const uint32_t* __restrict__ dz, const float* __restrict__ x, int N, int H, int W, int cin,
+stem_wgrad_kernel(const uint32_t* __restrict__ dz, const float* __restrict__ x, int N, int H, int W,
                   float* __restrict__ dW) {
-    // thread = (channel pair of dz) ; block walks pixels; 32 channel pairs x 8 pixel lanes
+    constexpr int K = 9 * CIN;
+    __shared__ float part[64 * K];
+    for (int i = threadIdx.x; i < 64 * K; i += 256) part[i] = 0.f;
+    __syncthreads();
     const int cp = threadIdx.x & 31, pl = threadIdx.x >> 5;
-    float acc[2][72];
-    for (int k = 0; k < 9 * cin; ++k) acc[0][k] = acc[1][k] = 0.f;
+    float acc[2][K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[0][k] = acc[1][k] = 0.f;
     const long long P = static_cast<long long>(N) * H * W;
     for (long long p = static_cast<long long>(blockIdx.x) * 8 + pl; p < P; p += static_cast<long long>(gridDim.x) * 8) {
         const int n = static_cast<int>(p / (static_cast<long long>(H) * W));
         const int rem = static_cast<int>(p - static_cast<long long>(n) * H * W);
         const int y = rem / W, xx = rem - y * W;
         const float2 g = unpack2(__ldg(dz + p * 32 + cp));
-        for (int ci = 0; ci < cin; ++ci)
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float* plane = x + (static_cast<long long>(n) * CIN + ci) * H * W;
+#pragma unroll
             for (int t = 0; t < 9; ++t) {
                 const int yy = y + t / 3 - 1, xq = xx + t % 3 - 1;
-                const float v = (yy >= 0 && yy < H && xq >= 0 && xq < W)
-                                    ? __ldg(x + ((static_cast<long long>(n) * cin + ci) * H + yy) * W + xq) : 0.f;
+                const float v = (yy >= 0 && yy < H && xq >= 0 && xq < W) ? __ldg(plane + static_cast<long long>(yy) * W + xq) : 0.f;
                 acc[0][ci * 9 + t] = fmaf(g.x, v, acc[0][ci * 9 + t]);
                 acc[1][ci * 9 + t] = fmaf(g.y, v, acc[1][ci * 9 + t]);
             }
+        }
     }
-    for (int k = 0; k < 9 * cin; ++k) {
-        atomicAdd(dW + static_cast<long long>(2 * cp) * 9 * cin + k, acc[0][k]);
-        atomicAdd(dW + static_cast<long long>(2 * cp + 1) * 9 * cin + k, acc[1][k]);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {   // 8-way contention at most (the 8 pixel lanes)
+        atomicAdd(&part[(2 * cp) * K + k], acc[0][k]);
+        atomicAdd(&part[(2 * cp + 1) * K + k], acc[1][k]);
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * K; i += 256) atomicAdd(dW + i, part[i]);
 }
 
 // ------------------------------------------------------------------------------------------------ optimizer / packing
@@ -475,23 +453,18 @@ const char* upsample2x_bwd_launch(const void* d_up, void* d_lo, int N, int h, in
         static_cast<const uint4*>(d_up), static_cast<uint4*>(d_lo), N, h, w, C / 8);
     return last_error();
 }
-int transpose_pad_row(int W) { return (W + 2 + 7) / 8 * 8; }
-long long transpose_pad_k(int N, int H, int W) {
-    const long long k = static_cast<long long>(N) * (H + 2) * transpose_pad_row(W);
-    return (k + 63) / 64 * 64;
-}
-const char* transpose_pad_launch(const void* x, void* xT, int N, int H, int W, int C, int copies, cudaStream_t st) {
-    FI_REQUIRE(x && xT && N > 0 && C > 0 && (copies == 1 || copies == 3), "transpose_pad: bad arguments");
-    const long long Kp = transpose_pad_k(N, H, W);
-    transpose_pad_kernel<<<dim3(static_cast<unsigned>(Kp / 32), (C + 31) / 32, copies), 256, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(xT), N, H, W, C, transpose_pad_row(W), Kp,
-        copies == 3 ? -1 : 0);
-    return last_error();
-}
 const char* stem_wgrad_launch(const void* dz, const float* x, int N, int H, int W, int cin, float* dW, cudaStream_t st) {
-    FI_REQUIRE(dz && x && dW && cin >= 1 && cin <= 8, "stem_wgrad: bad arguments");
-    stem_wgrad_kernel<<<blocks_for(static_cast<long long>(N) * H * W, 8, 148 * 2), 256, 0, st>>>(
-        static_cast<const uint32_t*>(dz), x, N, H, W, cin, dW);
+    FI_REQUIRE(dz && x && dW && cin >= 1 && cin <= 6, "stem_wgrad: bad arguments");
+    const int grid = blocks_for(static_cast<long long>(N) * H * W, 8, 148 * 2);
+    const uint32_t* g = static_cast<const uint32_t*>(dz);
+    switch (cin) {
+        case 1: stem_wgrad_kernel<1><<<grid, 256, 0, st>>>(g, x, N, H, W, dW); break;
+        case 2: stem_wgrad_kernel<2><<<grid, 256, 0, st>>>(g, x, N, H, W, dW); break;   // grayscale frame pair
+        case 3: stem_wgrad_kernel<3><<<grid, 256, 0, st>>>(g, x, N, H, W, dW); break;
+        case 4: stem_wgrad_kernel<4><<<grid, 256, 0, st>>>(g, x, N, H, W, dW); break;
+        case 6: stem_wgrad_kernel<6><<<grid, 256, 0, st>>>(g, x, N, H, W, dW); break;   // RGB frame pair
+        default: return "stem_wgrad: built for 1, 2, 3, 4 or 6 input channels";
+    }
     return last_error();
 }
 const char* adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,

@@ -23,17 +23,14 @@ const char* bn_relu_bwd_apply_launch(const void* dA, const void* a, const void* 
 const char* maxpool_bwd_add_launch(const void* a_full, const void* a_pool, const void* d_pool, const void* d_skip,
                                    void* d_full, int N, int H, int W, int C, cudaStream_t st);
 const char* upsample2x_bwd_launch(const void* d_up, void* d_lo, int N, int h, int w, int C, cudaStream_t st);
-int transpose_pad_row(int W);                    // padded image row pitch: W + 2 rounded up to 8
-long long transpose_pad_k(int N, int H, int W);  // padded K length of the transposed layout (multiple of 64)
-// copies = 1: xT[c][q]; copies = 3: xT[s][c][q] = row shifted by s-1 elements (the three column taps)
-const char* transpose_pad_launch(const void* x, void* xT, int N, int H, int W, int C, int copies, cudaStream_t st);
 const char* stem_wgrad_launch(const void* dz, const float* x, int N, int H, int W, int cin, float* dW, cudaStream_t st);
 const char* adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                         int step, cudaStream_t st);
 const char* pack_conv_launch(const float* w, int co, int ci, void* fwd, void* bwd, cudaStream_t st);
 
-// wgrad_gemm.cu: dW[tap][co][ci] += sum_q dzT[co][q] * xT3[dx][ci][q + (dy-1)*Wp8]   (tcgen05, split-K, fp32 atomics)
-const char* wgrad_launch(const void* dzT, const void* xT3, int cout, int cin, long long Kp, int Wp8, float* dW,
-                         int num_sms, cudaStream_t st);
+// wgrad_gemm.cu: dW[tap][co][ci] += sum_q dz[q][co] * x[q + tap][ci], x = channel concat of x0 | x1, all bf16 NHWC
+// (tcgen05 GEMM over the pixel dimension with MN-major operands straight from NHWC, split-K, fp32 atomics)
+const char* wgrad_launch(const void* dz, const void* x0, int c0, const void* x1, int c1, int N, int H, int W, int cout,
+                         float* dW, int num_sms, cudaStream_t st);
 
 }  // namespace fi

@@ -2,13 +2,13 @@
 //
 //   dW[tap][co][ci] = sum over pixels q of dz[q][co] * x[q + tap][ci]
 //
-// is a GEMM whose reduction dimension is the pixel index. Both operands are first transposed to channel-major,
-// zero-padded layouts (transpose_pad_kernel): dzT [Cout][Kp], xT [Cin][Kp] with Kp = N*(H+2)*(W+2) rounded up. In that
-// layout the row part of a tap is a plain offset (dy-1)*Wp8 along K (a multiple of 16 bytes, as TMA box starts must be)
-// and the column part selects one of three pre-shifted copies of xT; the zero border of dzT kills the products that
-// would wrap around an image row — so the mainloop is an ordinary K-major tcgen05 GEMM (the descriptors validated in
-// conv_gemm.cu): A = dzT rows [128 co] x 64 K, B = xT rows [N_TILE ci] x 64 K shifted by the tap, D = [128 x N_TILE]
-// fp32 in TMEM. K is split over CTAs; partial tiles are added to dW with fp32 vector atomics.
+// is a GEMM whose reduction dimension is the pixel index. In NHWC both operands have that dimension as the slow one, i.e.
+// they are "MN-major" tcgen05 operands as they lie in HBM: a TMA box {64 channels, bw, bh, 1 image} with bw*bh = 64 lands
+// in shared memory as 64 pixel rows of 128 swizzled bytes — the canonical MN-major SWIZZLE_128B atom (8 K-rows x 128 B,
+// atoms 1024 B apart along K, 64-channel blocks LBO apart along M/N). The tap is a coordinate shift of the x box and the
+// zero fill of out-of-bounds TMA reads is the convolution's padding, so nothing is transposed, padded or copied. The
+// reduction is split over CTAs; partial tiles are added to dW with fp32 atomics. When the layer has fewer than 128 output
+// channels but at least 128 input channels the operand roles are swapped (M = input channels) to fill the 128 MMA rows.
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
 #include "train_kernels.cuh"
@@ -20,10 +20,15 @@ namespace fi {
 namespace {
 
 constexpr int WG_THREADS = 192;
-constexpr int WG_A_BYTES = 128 * 128;
+constexpr int WG_BLOCK_BYTES = 64 * 128;      // one 64-channel x 64-pixel block
+constexpr int WG_A_BYTES = 2 * WG_BLOCK_BYTES;  // M = 128 channels
 
 struct WgradParams {
-    int cout, cin, m_tiles, n_tiles, k_chunks, chunk_slabs, total_slabs, wp;
+    int cout, cin, c0;                          // c0 = channels of the first x source (concat layers have two)
+    int m_total, m_tiles, n_tiles;              // GEMM rows / tiles (rows = cout, or cin when swapped)
+    int k_chunks, chunk_slabs, total_slabs;     // split of the pixel slabs over work items
+    int tiles_w, tiles_h, bw, bh;               // a slab is a bw x bh pixel box of one image
+    int swap;                                   // 1: A = x (M = cin), B = dz (N = cout)
     float* dW;
 };
 
@@ -32,12 +37,25 @@ __host__ __device__ constexpr int wg_smem(int n_tile) {
     return 1024 + wg_stages(n_tile) * (WG_A_BYTES + n_tile * 128) + 256;
 }
 
+// MN-major SWIZZLE_128B operand: 8 K-rows of 128 B per atom, atoms 1024 B apart along K, 64-element blocks `lbo` apart.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
 template <int N_TILE>
 __global__ void __launch_bounds__(WG_THREADS, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const WgradParams p) {
+wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_x0,
+             const __grid_constant__ CUtensorMap map_x1, const WgradParams p) {
     constexpr int STAGES = wg_stages(N_TILE);
     constexpr int B_BYTES = N_TILE * 128;
-    constexpr uint32_t IDESC = umma_idesc_bf16(128, N_TILE);
+    constexpr int N_BLOCKS = N_TILE / 64;
+    constexpr uint32_t IDESC = umma_idesc_bf16(128, N_TILE) | (1u << 15) | (1u << 16);  // A and B MN-major
     constexpr int TMEM_COLS = 2 * N_TILE < 32 ? 32 : 2 * N_TILE;
 
     extern __shared__ uint8_t smem_raw[];
@@ -50,8 +68,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&map_a);
-        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_dz);
+        tma_prefetch_desc(&map_x0);
+        tma_prefetch_desc(&map_x1);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
@@ -84,18 +103,37 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     if (warp == 0) {
         int stage = 0;
         uint32_t phase = 0;
+        const int m_blocks = (p.m_total + 63) / 64;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             int tap, mt, nt, s0, s1;
             decode(t, tap, mt, nt, s0, s1);
-            const int off = (tap / 3 - 1) * p.wp;   // row shift: a multiple of 8 elements (16 B), as TMA requires
-            const int brow = (tap % 3) * p.cin;      // column shift: the pre-shifted copy of xT
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            const int a_blocks = m_blocks - 2 * mt < 2 ? m_blocks - 2 * mt : 2;  // rows past m_total are never stored
             for (int s = s0; s < s1; ++s) {
+                const int tw = s % p.tiles_w;
+                const int r = s / p.tiles_w;
+                const int th = r % p.tiles_h, img = r / p.tiles_h;
+                const int w0 = tw * p.bw, h0 = th * p.bh;
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 const uint32_t full = bar_full + 8 * stage;
                 if (elect_one()) {
-                    mbar_expect_tx(full, WG_A_BYTES + B_BYTES);
-                    tma_load_2d(smem_a + stage * WG_A_BYTES, &map_a, full, s * 64, mt * 128);
-                    tma_load_2d(smem_b + stage * B_BYTES, &map_b, full, s * 64 + off, brow + nt * N_TILE);
+                    mbar_expect_tx(full, (a_blocks + N_BLOCKS) * WG_BLOCK_BYTES);
+                    auto load_dz = [&](uint32_t dst, int cb) { tma_load_4d(dst, &map_dz, full, cb * 64, w0, h0, img); };
+                    auto load_x = [&](uint32_t dst, int cb) {
+                        const int c = cb * 64;
+                        if (c < p.c0) tma_load_4d(dst, &map_x0, full, c, w0 + dx, h0 + dy, img);
+                        else tma_load_4d(dst, &map_x1, full, c - p.c0, w0 + dx, h0 + dy, img);
+                    };
+                    const uint32_t sa = smem_a + stage * WG_A_BYTES, sb = smem_b + stage * B_BYTES;
+                    for (int b = 0; b < a_blocks; ++b) {
+                        if (p.swap) load_x(sa + b * WG_BLOCK_BYTES, 2 * mt + b);
+                        else load_dz(sa + b * WG_BLOCK_BYTES, 2 * mt + b);
+                    }
+#pragma unroll
+                    for (int b = 0; b < N_BLOCKS; ++b) {
+                        if (p.swap) load_dz(sb + b * WG_BLOCK_BYTES, nt * N_BLOCKS + b);
+                        else load_x(sb + b * WG_BLOCK_BYTES, nt * N_BLOCKS + b);
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) {
@@ -118,12 +156,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             for (int s = s0; s < s1; ++s) {
                 mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
-                const uint64_t da = umma_desc_sw128(smem_a + stage * WG_A_BYTES);
-                const uint64_t db = umma_desc_sw128(smem_b + stage * B_BYTES);
+                const uint64_t da = umma_desc_mn_sw128(smem_a + stage * WG_A_BYTES, WG_BLOCK_BYTES);
+                const uint64_t db = umma_desc_mn_sw128(smem_b + stage * B_BYTES, WG_BLOCK_BYTES);
                 if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, IDESC, (s > s0) || (k > 0));
+                    for (int k = 0; k < 4; ++k)  // 16 pixel rows (2048 B) per MMA
+                        umma_bf16_ss(d_tmem, da + 128 * k, db + 128 * k, IDESC, (s > s0) || (k > 0));
                     umma_commit(bar_empty + 8 * stage);
                     if (s == s1 - 1) umma_commit(bar_tfull + 8 * acc);
                 }
@@ -144,19 +182,27 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * N_TILE;
-            const int co = mt * 128 + q * 32 + lane;
-            float* row = p.dW + (static_cast<size_t>(tap) * p.cout + co) * p.cin + nt * N_TILE;
+            const int m = mt * 128 + q * 32 + lane;
+            float* tap_base = p.dW + static_cast<size_t>(tap) * p.cout * p.cin;
 #pragma unroll 1
             for (int c = 0; c < N_TILE / 32; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + c * 32, v);
                 tmem_ld_wait();
-                if (co < p.cout) {
+                if (m < p.m_total) {
+                    const int n0 = nt * N_TILE + c * 32;
+                    if (!p.swap) {  // row = co, columns = ci: contiguous in dW
+                        float* row = tap_base + static_cast<size_t>(m) * p.cin + n0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        atomicAdd(reinterpret_cast<float4*>(row + c * 32 + 4 * j),
-                                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                        for (int j = 0; j < 8; ++j) {
+                            atomicAdd(reinterpret_cast<float4*>(row + 4 * j),
+                                      make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                        }
+                    } else {        // row = ci, columns = co: lanes cover consecutive ci of one co row
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            atomicAdd(tap_base + static_cast<size_t>(n0 + j) * p.cin + m, __uint_as_float(v[j]));
                     }
                 }
             }
@@ -174,7 +220,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 }
 
 template <int N_TILE>
-const char* launch_wgrad(const CUtensorMap& ma, const CUtensorMap& mb, const WgradParams& p, int grid, cudaStream_t st) {
+const char* launch_wgrad(const CUtensorMap* maps, const WgradParams& p, int grid, cudaStream_t st) {
     auto k = wgrad_kernel<N_TILE>;
     static bool configured = false;
     if (!configured) {
@@ -182,54 +228,73 @@ const char* launch_wgrad(const CUtensorMap& ma, const CUtensorMap& mb, const Wgr
             return "wgrad: cudaFuncSetAttribute failed";
         configured = true;
     }
-    k<<<grid, WG_THREADS, wg_smem(N_TILE), st>>>(ma, mb, p);
+    k<<<grid, WG_THREADS, wg_smem(N_TILE), st>>>(maps[0], maps[1], maps[2], p);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
+const char* encode_pixels(CUtensorMap* map, const void* base, int N, int H, int W, int C, int bw, int bh) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(N)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W) * C,
+                                 static_cast<uint64_t>(H) * W * C};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), 1};
+    return encode_bf16_map_public(map, base, 4, dims, strides, box);
+}
+
 }  // namespace
 
-const char* wgrad_launch(const void* dzT, const void* xT, int cout, int cin, long long Kp, int Wp, float* dW,
-                         int num_sms, cudaStream_t st) {
-    if (!dzT || !xT || !dW) return "wgrad: null operand";
-    if (cin % 64 || cout % 8 || Kp % 64 || Kp <= 0 || Wp % 8) return "wgrad: cin % 64, Kp % 64 and row pitch % 8 must be 0";
-    const int n_tile = cin % 256 == 0 ? 256 : (cin % 128 == 0 ? 128 : 64);
+const char* wgrad_launch(const void* dz, const void* x0, int c0, const void* x1, int c1, int N, int H, int W, int cout,
+                         float* dW, int num_sms, cudaStream_t st) {
+    if (!dz || !x0 || !dW || (c1 > 0 && !x1)) return "wgrad: null operand";
+    if (N <= 0 || H <= 0 || W <= 0) return "wgrad: empty shape";
+    if (c0 <= 0 || c0 % 64 || c1 < 0 || c1 % 64 || cout <= 0 || cout % 64)
+        return "wgrad: channel counts must be multiples of 64";
+    const int cin = c0 + c1;
     WgradParams p;
     memset(&p, 0, sizeof p);
     p.cout = cout;
     p.cin = cin;
-    p.m_tiles = (cout + 127) / 128;
-    p.n_tiles = cin / n_tile;
-    p.total_slabs = static_cast<int>(Kp / 64);
-    p.wp = Wp;
+    p.c0 = c0;
     p.dW = dW;
-    // split K so that there are a few work items per SM
+    p.swap = (cout % 128 != 0 && cin % 128 == 0) ? 1 : 0;
+    p.m_total = p.swap ? cin : cout;
+    const int n_total = p.swap ? cout : cin;
+    const int n_tile = n_total % 256 == 0 ? 256 : (n_total % 128 == 0 ? 128 : 64);
+    p.m_tiles = (p.m_total + 127) / 128;
+    p.n_tiles = n_total / n_tile;
+    // pixel slab: the 64-pixel box shape that wastes the fewest out-of-bounds pixels
+    long long best = -1;
+    for (int bw = 16; bw >= 1; bw >>= 1) {
+        const int bh = 64 / bw;
+        const long long covered = static_cast<long long>((W + bw - 1) / bw) * ((H + bh - 1) / bh);
+        if (best < 0 || covered < best) {
+            best = covered;
+            p.bw = bw;
+            p.bh = bh;
+        }
+    }
+    p.tiles_w = (W + p.bw - 1) / p.bw;
+    p.tiles_h = (H + p.bh - 1) / p.bh;
+    p.total_slabs = N * p.tiles_w * p.tiles_h;
+    // split the reduction so that there are a few work items per SM
     const int base_items = 9 * p.m_tiles * p.n_tiles;
     int chunks = (4 * num_sms + base_items - 1) / base_items;
     if (chunks > p.total_slabs) chunks = p.total_slabs;
     if (chunks < 1) chunks = 1;
     p.chunk_slabs = (p.total_slabs + chunks - 1) / chunks;
     p.k_chunks = (p.total_slabs + p.chunk_slabs - 1) / p.chunk_slabs;
-    alignas(64) CUtensorMap ma, mb;
+    alignas(64) CUtensorMap maps[3];
     const char* e;
-    {
-        const uint64_t dims[2] = {static_cast<uint64_t>(Kp), static_cast<uint64_t>(cout)};
-        const uint64_t strides[1] = {static_cast<uint64_t>(Kp)};
-        const uint32_t box[2] = {64, 128};
-        if ((e = encode_bf16_map_public(&ma, dzT, 2, dims, strides, box))) return e;
-    }
-    {
-        const uint64_t dims[2] = {static_cast<uint64_t>(Kp), static_cast<uint64_t>(3 * cin)};  // three shifted copies
-        const uint64_t strides[1] = {static_cast<uint64_t>(Kp)};
-        const uint32_t box[2] = {64, static_cast<uint32_t>(n_tile)};
-        if ((e = encode_bf16_map_public(&mb, xT, 2, dims, strides, box))) return e;
-    }
+    if ((e = encode_pixels(&maps[0], dz, N, H, W, cout, p.bw, p.bh))) return e;
+    if ((e = encode_pixels(&maps[1], x0, N, H, W, c0, p.bw, p.bh))) return e;
+    if ((e = encode_pixels(&maps[2], c1 > 0 ? x1 : x0, N, H, W, c1 > 0 ? c1 : c0, p.bw, p.bh))) return e;
     const long long total = 9LL * p.m_tiles * p.n_tiles * p.k_chunks;
     const int grid = static_cast<int>(total < num_sms ? total : num_sms);
     switch (n_tile) {
-        case 64: return launch_wgrad<64>(ma, mb, p, grid, st);
-        case 128: return launch_wgrad<128>(ma, mb, p, grid, st);
-        default: return launch_wgrad<256>(ma, mb, p, grid, st);
+        case 64: return launch_wgrad<64>(maps, p, grid, st);
+        case 128: return launch_wgrad<128>(maps, p, grid, st);
+        default: return launch_wgrad<256>(maps, p, grid, st);
     }
 }
 

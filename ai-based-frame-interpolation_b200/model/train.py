@@ -3,7 +3,7 @@ loss, backward, Adam) on the B200 kernels — SURVEY.md §8f row 2 / BASELINE co
 
 What runs where
   conv3x3 forward, conv3x3 data gradient   tcgen05 implicit-GEMM kernels (fiConvGemm; dgrad = conv with flipped weights)
-  conv3x3 weight gradient                  tcgen05 split-K GEMM over the pixel dimension (fiWgrad) on transposed operands
+  conv3x3 weight gradient                  tcgen05 split-K GEMM over the pixel dimension (fiWgrad), operands read as NHWC
   BatchNorm (batch statistics) fwd / bwd, ReLU, max-pool / bilinear-upsample backward, 1x1 head, MSE, Adam: CUDA-core
                                            kernels in csrc/train_kernels.cu
   gradient all-reduce                      torch.distributed (NCCL) on one flat fp32 gradient buffer
@@ -163,24 +163,6 @@ class TrainStep:
             layer.bn.num_batches_tracked += 1
         return a, mean, rstd
 
-    def _transposed(self, tensors, n, h, w, copies):
-        """Channel-major zero-padded copies of the (concatenated) NHWC tensors: operand layouts of fiWgrad
-        ([copies][C_total][Kp]; 3 copies = the rows shifted by -1/0/+1 for the three column taps)."""
-        kp = self.lib.fiTransposePadK(n, h, w)
-        ctot = sum(t.shape[3] for t in tensors)
-        out = torch.empty((copies, ctot, kp), dtype=torch.bfloat16, device=self.device)
-        row = 0
-        for t in tensors:
-            c = t.shape[3]
-            if copies == 1 or len(tensors) == 1:
-                E.check(self.lib.fiTransposePad(_ptr(t), _ptr(out[0, row:]), n, h, w, c, copies, E.current_stream()))
-            else:  # concatenated sources: each copy's rows are [skip | up], so place the copies one by one
-                tmp = torch.empty((copies, c, kp), dtype=torch.bfloat16, device=self.device)
-                E.check(self.lib.fiTransposePad(_ptr(t), _ptr(tmp), n, h, w, c, copies, E.current_stream()))
-                out[:, row:row + c] = tmp
-            row += c
-        return out, kp
-
     # ------------------------------------------------------------------------------------------------ one step
     @torch.no_grad()
     def __call__(self, frame1, frame2, target):
@@ -273,10 +255,10 @@ class TrainStep:
                     E.check(lib.fiStemWgrad(_ptr(dz), _ptr(x), n, h, w, l.cin, _ptr(self.grad_view[l.conv.weight]), st()))
                     continue
                 srcs = [acts[l.src]] + ([acts[l.src1]] if l.src1 else [])
-                dzT, kp = self._transposed([dz], ln, lh, lw, 1)
-                xT, _ = self._transposed(srcs, ln, lh, lw, 3)
                 dW = torch.zeros((9, l.cout, l.cin), dtype=torch.float32, device=self.device)
-                E.check(lib.fiWgrad(_ptr(dzT), _ptr(xT), l.cout, l.cin, kp, lib.fiTransposePadRow(lw), _ptr(dW), st()))
+                x1 = srcs[1] if len(srcs) > 1 else None
+                E.check(lib.fiWgrad(_ptr(dz), _ptr(srcs[0]), srcs[0].shape[3], _ptr(x1), x1.shape[3] if x1 is not None else 0,
+                                    ln, lh, lw, l.cout, _ptr(dW), st()))
                 self.grad_view[l.conv.weight].add_(dW.permute(1, 2, 0).reshape(l.cout, l.cin, 3, 3))
                 # data gradient(s): conv3x3 of dz with the flipped, transposed weights
                 bwd = packs[l.name][1]

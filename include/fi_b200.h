@@ -211,17 +211,12 @@ int fiMaxPoolBackwardAdd(const void* a_full, const void* a_pool, const void* d_p
                          int N, int H, int W, int C, void* stream);
 /* Backward of nn.Upsample(scale_factor=2, bilinear, align_corners=True): [N,2h,2w,C] -> [N,h,w,C]. */
 int fiUpsample2xBackward(const void* d_up, void* d_lo, int N, int h, int w, int C, void* stream);
-/* bf16 NHWC [N,H,W,C] -> channel-major zero-padded rows xT[copy][C][Kp], Kp = fiTransposePadK, padded image rows of
- * Wp8 = fiTransposePadRow(W) pixels, pixel (n,y,x) at n*(H+2)*Wp8 + (y+1)*Wp8 + x+1. copies = 1: the plain row;
- * copies = 3: rows shifted by -1, 0, +1 elements (the three column taps; TMA box starts must be 16-byte aligned, so
- * only the row part of a tap can be a coordinate offset). Operand layouts of fiWgrad: dzT 1 copy, xT 3 copies. */
-int64_t fiTransposePadK(int N, int H, int W);
-int fiTransposePadRow(int W);
-int fiTransposePad(const void* x, void* xT, int N, int H, int W, int C, int copies, void* stream);
-/* Weight gradient of conv3x3: dW[tap][cout][cin] (fp32, accumulated) from the transposed operands; tcgen05 GEMM over
- * the pixel dimension, split-K with fp32 atomics. Wp8 = fiTransposePadRow(W). fiStemWgrad: the <= 8 input-channel first
- * conv (x fp32 NCHW), dW[64][cin][9]. */
-int fiWgrad(const void* dzT, const void* xT3, int cout, int cin, int64_t Kp, int Wp8, float* dW, void* stream);
+/* Weight gradient of conv3x3 (padding 1): dW[tap][cout][cin] (fp32, ACCUMULATED into) from dz [N,H,W,cout] and the
+ * layer input x = channel concat of x0 [N,H,W,c0] | x1 [N,H,W,c1] (x1 NULL / c1 0 for single-source layers), all bf16
+ * NHWC, channel counts multiples of 64. tcgen05 GEMM over the pixel dimension reading both operands as they lie
+ * (MN-major), split-K with fp32 atomics. fiStemWgrad: the <= 8 input-channel first conv (x fp32 NCHW), dW[64][cin][9]. */
+int fiWgrad(const void* dz, const void* x0, int c0, const void* x1, int c1, int N, int H, int W, int cout, float* dW,
+            void* stream);
 int fiStemWgrad(const void* dz, const float* x, int N, int H, int W, int cin, float* dW, void* stream);
 /* torch.optim.Adam (model/train.py:160) on one flat fp32 parameter vector; step counts from 1. */
 int fiAdamStep(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

@@ -168,3 +168,20 @@ def test_data_gradient_is_a_conv_with_flipped_weights(cuda_device):
     torch.cuda.synchronize()
     ref = F.conv_transpose2d(dz.double(), wt.to(torch.bfloat16).double(), padding=1).float()
     assert (from_nhwc(dst) - ref).abs().max() <= 2.0 ** -7 * ref.abs().max() + 1e-3
+
+
+@pytest.mark.parametrize("n,cin,h,w", [(2, 2, 9, 12), (1, 6, 8, 8), (3, 1, 5, 7)])
+def test_stem_weight_gradient(cuda_device, n, cin, h, w):
+    lib, st = E.lib(), E.current_stream()
+    g = torch.Generator().manual_seed(cin * 10 + h)
+    x = torch.rand(n, cin, h, w, generator=g) * 2 - 1
+    dz = torch.randn(n, 64, h, w, generator=g).to(torch.bfloat16).float()
+    wt = torch.zeros(64, cin, 3, 3, requires_grad=True)
+    F.conv2d(x, wt, padding=1).backward(dz)
+    xd, dzd = x.to(cuda_device), nhwc(dz, cuda_device)
+    prior = torch.randn(64, cin, 3, 3, generator=g).to(cuda_device)
+    dW = prior.clone()
+    E.check(lib.fiStemWgrad(p(dzd), p(xd), n, h, w, cin, p(dW), st))
+    torch.cuda.synchronize()
+    assert torch.allclose((dW - prior).cpu(), wt.grad, rtol=1e-4, atol=1e-4)
+    assert lib.fiStemWgrad(p(dzd), p(xd), n, h, w, 5, p(dW), st) != 0
