@@ -1128,6 +1128,15 @@ int fiWgrad(const void* dz, const void* x0, int c0, const void* x1, int c1, int 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     TRAIN_CALL(fi::wgrad_launch(dz, x0, c0, x1, c1, N, H, W, cout, dW, sms, ST));
 }
+int fiBnFinalize(const float* sum, const float* sumsq, int C, int64_t P, float eps, float momentum, const float* gamma,
+                 const float* beta, float* mean, float* rstd, float* scale, float* shift, float* running_mean,
+                 float* running_var, void* stream) {
+    TRAIN_CALL(fi::bn_finalize_launch(sum, sumsq, C, P, eps, momentum, gamma, beta, mean, rstd, scale, shift, running_mean,
+                                      running_var, ST));
+}
+int fiUnpackConvGrad(const float* dW, int cout, int cin, float* grad, void* stream) {
+    TRAIN_CALL(fi::unpack_conv_grad_launch(dW, cout, cin, grad, ST));
+}
 int fiAdamStep(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                int step, void* stream) {
     TRAIN_CALL(fi::adam_launch(p, g, m, v, n, lr, beta1, beta2, eps, step, ST));

@@ -21,43 +21,122 @@ int blocks_for(long long items, int threads, int cap = 148 * 8) {
 }
 
 // ------------------------------------------------------------------------------------------------ BN statistics
-// z: bf16 [P][C]. Thread = channel pair, a block walks a contiguous range of pixels: coalesced 4-byte loads across the
-// warp, fp32 partial sums, one atomicAdd per (block, channel).
-__global__ void __launch_bounds__(256)
-bn_stats_kernel(const uint32_t* __restrict__ z, long long P, int c2, float* __restrict__ sum, float* __restrict__ sumsq) {
-    // c2 (channel pairs per pixel) divides 256 or is a multiple of it: 256/c2 pixel rows per block pass, or 1
-    const int rows_par = c2 <= 256 ? 256 / c2 : 1;
-    const int r0 = c2 <= 256 ? threadIdx.x / c2 : 0;
-    for (int col = c2 <= 256 ? threadIdx.x % c2 : threadIdx.x; col < c2; col += 256) {
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        for (long long p = static_cast<long long>(blockIdx.x) * rows_par + r0; p < P;
-             p += static_cast<long long>(gridDim.x) * rows_par) {
-            const float2 v = unpack2(__ldg(z + p * c2 + col));
-            s0 += v.x; s1 += v.y; q0 += v.x * v.x; q1 += v.y * v.y;
-        }
-        atomicAdd(sum + 2 * col, s0); atomicAdd(sum + 2 * col + 1, s1);
-        atomicAdd(sumsq + 2 * col, q0); atomicAdd(sumsq + 2 * col + 1, q1);
+// Per-channel reductions over z: bf16 [P][C]. A thread owns one 8-channel group (16-byte loads) and walks pixels with a
+// block-wide stride, four independent loads in flight; when C/8 divides 256 the 256/(C/8) pixel lanes of a block are
+// combined with shared-memory atomics so that a block issues one global atomic per channel and quantity.
+constexpr int RED_MAX_C = 2048;
+
+template <typename Acc>
+__device__ __forceinline__ void channel_reduce_walk(long long P, int c8, Acc&& per_group) {
+    const bool packed = c8 <= 256 && 256 % c8 == 0;
+    const int rows_par = packed ? 256 / c8 : 1;
+    const int r0 = packed ? threadIdx.x / c8 : 0;
+    for (int g = packed ? threadIdx.x % c8 : threadIdx.x; g < c8; g += 256)
+        per_group(g, static_cast<long long>(blockIdx.x) * rows_par + r0, static_cast<long long>(gridDim.x) * rows_par,
+                  packed && rows_par > 1);
+}
+
+// adds v[0..7] of channel group g to out[8g..8g+7]: through shared memory first when several pixel lanes share g
+__device__ __forceinline__ void flush_group(float* sh, float* out, int g, const float (&v)[8], bool via_smem) {
+    if (via_smem) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(sh + 8 * g + j, v[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(out + 8 * g + j, v[j]);
     }
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        f[2 * k] = bf16lo_f(w[k]);
+        f[2 * k + 1] = bf16hi_f(w[k]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const uint4* __restrict__ z, long long P, int c8, float* __restrict__ sum, float* __restrict__ sumsq) {
+    __shared__ float sh[2][RED_MAX_C];
+    const int C = 8 * c8;
+    for (int i = threadIdx.x; i < C; i += 256) sh[0][i] = sh[1][i] = 0.f;
+    __syncthreads();
+    bool any_smem = false;
+    channel_reduce_walk(P, c8, [&](int g, long long p, long long step, bool via_smem) {
+        float s[8], q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+        auto add = [&](const uint4& v) {
+            float f[8];
+            unpack8(v, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+        };
+        for (; p + 3 * step < P; p += 4 * step) {
+            const uint4 v0 = __ldg(z + p * c8 + g), v1 = __ldg(z + (p + step) * c8 + g);
+            const uint4 v2 = __ldg(z + (p + 2 * step) * c8 + g), v3 = __ldg(z + (p + 3 * step) * c8 + g);
+            add(v0); add(v1); add(v2); add(v3);
+        }
+        for (; p < P; p += step) add(__ldg(z + p * c8 + g));
+        flush_group(sh[0], sum, g, s, via_smem);
+        flush_group(sh[1], sumsq, g, q, via_smem);
+        any_smem = via_smem;
+    });
+    if (any_smem) {   // uniform across the block
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += 256) { atomicAdd(sum + i, sh[0][i]); atomicAdd(sumsq + i, sh[1][i]); }
+    }
+}
+
+// Batch statistics -> per-channel affine + the nn.BatchNorm2d running estimates (momentum update, unbiased variance).
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, int C, float inv_p, float unbias,
+                   float eps, float momentum, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ mean_out, float* __restrict__ rstd_out, float* __restrict__ scale,
+                   float* __restrict__ shift, float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float mean = sum[c] * inv_p;
+    const float var = fmaxf(sumsq[c] * inv_p - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float sc = gamma[c] * rstd;
+    mean_out[c] = mean;
+    rstd_out[c] = rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
 }
 
 // a = relu(z * scale[c] + shift[c]) (scale = gamma * rstd, shift = beta - mean * scale); 8 channels per thread.
 __global__ void __launch_bounds__(256)
 bn_apply_relu_kernel(const uint4* __restrict__ z, long long n8, int c8, const float* __restrict__ scale,
                      const float* __restrict__ shift, uint4* __restrict__ a) {
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % c8) * 8;
-        const uint4 v = __ldg(z + i);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    // the launcher makes gridDim.x * 256 a multiple of c8, so a thread keeps its channel group: parameters in registers
+    const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+    const int c = static_cast<int>(i0 % c8) * 8;
+    float sc[8], sf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[c + j]; sf[j] = shift[c + j]; }
+    auto one = [&](long long i, const uint4& v) {
+        float f[8];
+        unpack8(v, f);
         uint32_t o[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 f = unpack2(w[k]);
-            o[k] = pack_bf16x2(fmaxf(fmaf(f.x, scale[c + 2 * k], shift[c + 2 * k]), 0.f),
-                               fmaxf(fmaf(f.y, scale[c + 2 * k + 1], shift[c + 2 * k + 1]), 0.f));
-        }
+        for (int k = 0; k < 4; ++k)
+            o[k] = pack_bf16x2(fmaxf(fmaf(f[2 * k], sc[2 * k], sf[2 * k]), 0.f),
+                               fmaxf(fmaf(f[2 * k + 1], sc[2 * k + 1], sf[2 * k + 1]), 0.f));
         a[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    };
+    long long i = i0;
+    for (; i + step < n8; i += 2 * step) {
+        const uint4 v0 = __ldg(z + i), v1 = __ldg(z + i + step);
+        one(i, v0);
+        one(i + step, v1);
     }
+    if (i < n8) one(i, __ldg(z + i));
 }
 
 // ------------------------------------------------------------------------------------------------ head + loss
@@ -156,24 +235,45 @@ head_backward_kernel(const uint4* __restrict__ a, const float* __restrict__ dy, 
 // ------------------------------------------------------------------------------------------------ BN + ReLU backward
 // dy = dA * (a > 0); dbeta[c] += sum dy; dgamma[c] += sum dy * zhat, zhat = (z - mean) * rstd.   (same walk as bn_stats)
 __global__ void __launch_bounds__(256)
-bn_relu_bwd_reduce_kernel(const uint32_t* __restrict__ dA, const uint32_t* __restrict__ a, const uint32_t* __restrict__ z,
-                          long long P, int c2, const float* __restrict__ mean, const float* __restrict__ rstd,
+bn_relu_bwd_reduce_kernel(const uint4* __restrict__ dA, const uint4* __restrict__ a, const uint4* __restrict__ z,
+                          long long P, int c8, const float* __restrict__ mean, const float* __restrict__ rstd,
                           float* __restrict__ dbeta, float* __restrict__ dgamma) {
-    const int rows_par = c2 <= 256 ? 256 / c2 : 1;
-    const int r0 = c2 <= 256 ? threadIdx.x / c2 : 0;
-    for (int c = c2 <= 256 ? threadIdx.x % c2 : threadIdx.x; c < c2; c += 256) {
-        const float m0 = mean[2 * c], m1 = mean[2 * c + 1], r_0 = rstd[2 * c], r_1 = rstd[2 * c + 1];
-        float b0 = 0.f, b1 = 0.f, g0 = 0.f, g1 = 0.f;
-        for (long long p = static_cast<long long>(blockIdx.x) * rows_par + r0; p < P;
-             p += static_cast<long long>(gridDim.x) * rows_par) {
-            const long long i = p * c2 + c;
-            const float2 d = unpack2(__ldg(dA + i)), av = unpack2(__ldg(a + i)), zv = unpack2(__ldg(z + i));
-            const float d0 = av.x > 0.f ? d.x : 0.f, d1 = av.y > 0.f ? d.y : 0.f;
-            b0 += d0; b1 += d1;
-            g0 += d0 * (zv.x - m0) * r_0; g1 += d1 * (zv.y - m1) * r_1;
+    __shared__ float sh[2][RED_MAX_C];
+    const int C = 8 * c8;
+    for (int i = threadIdx.x; i < C; i += 256) sh[0][i] = sh[1][i] = 0.f;
+    __syncthreads();
+    bool any_smem = false;
+    channel_reduce_walk(P, c8, [&](int g, long long p, long long step, bool via_smem) {
+        float m[8], b[8], gsum[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { m[j] = mean[8 * g + j]; b[j] = gsum[j] = 0.f; }
+        auto add = [&](const uint4& dv, const uint4& av, const uint4& zv) {
+            float d[8], af[8], zf[8];
+            unpack8(dv, d); unpack8(av, af); unpack8(zv, zf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float dd = af[j] > 0.f ? d[j] : 0.f;
+                b[j] += dd;
+                gsum[j] = fmaf(dd, zf[j] - m[j], gsum[j]);
+            }
+        };
+        for (; p + step < P; p += 2 * step) {
+            const long long i0 = p * c8 + g, i1 = (p + step) * c8 + g;
+            const uint4 d0 = __ldg(dA + i0), a0 = __ldg(a + i0), z0 = __ldg(z + i0);
+            const uint4 d1 = __ldg(dA + i1), a1 = __ldg(a + i1), z1 = __ldg(z + i1);
+            add(d0, a0, z0);
+            add(d1, a1, z1);
         }
-        atomicAdd(dbeta + 2 * c, b0); atomicAdd(dbeta + 2 * c + 1, b1);
-        atomicAdd(dgamma + 2 * c, g0); atomicAdd(dgamma + 2 * c + 1, g1);
+        if (p < P) { const long long i0 = p * c8 + g; add(__ldg(dA + i0), __ldg(a + i0), __ldg(z + i0)); }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gsum[j] *= rstd[8 * g + j];
+        flush_group(sh[0], dbeta, g, b, via_smem);
+        flush_group(sh[1], dgamma, g, gsum, via_smem);
+        any_smem = via_smem;
+    });
+    if (any_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += 256) { atomicAdd(dbeta + i, sh[0][i]); atomicAdd(dgamma + i, sh[1][i]); }
     }
 }
 
@@ -183,28 +283,34 @@ bn_relu_bwd_apply_kernel(const uint4* __restrict__ dA, const uint4* __restrict__
                          long long n8, int c8, float inv_p, const float* __restrict__ mean, const float* __restrict__ rstd,
                          const float* __restrict__ gamma, const float* __restrict__ dbeta, const float* __restrict__ dgamma,
                          uint4* __restrict__ dz) {
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % c8) * 8;
-        const uint4 dv = __ldg(dA + i), av = __ldg(a + i), zv = __ldg(z + i);
-        const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, aw[4] = {av.x, av.y, av.z, av.w}, zw[4] = {zv.x, zv.y, zv.z, zv.w};
-        uint32_t o[4];
+    // gridDim.x * 256 is a multiple of c8 (launcher): per-channel constants live in registers
+    const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+    const int c = static_cast<int>(i0 % c8) * 8;
+    float k1[8], k2[8], k3[8], m[8];   // dz = k1 * (dy - k2 - (z - m) * k3)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 d = unpack2(dw[k]), af = unpack2(aw[k]), zf = unpack2(zw[k]);
-            float r[2];
-            const float dd[2] = {af.x > 0.f ? d.x : 0.f, af.y > 0.f ? d.y : 0.f};
-            const float zz[2] = {zf.x, zf.y};
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int ch = c + 2 * k + h;
-                const float zhat = (zz[h] - mean[ch]) * rstd[ch];
-                r[h] = gamma[ch] * rstd[ch] * (dd[h] - dbeta[ch] * inv_p - zhat * dgamma[ch] * inv_p);
-            }
-            o[k] = pack_bf16x2(r[0], r[1]);
-        }
-        dz[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    for (int j = 0; j < 8; ++j) {
+        const float r = rstd[c + j];
+        k1[j] = gamma[c + j] * r;
+        k2[j] = dbeta[c + j] * inv_p;
+        k3[j] = r * dgamma[c + j] * inv_p;
+        m[j] = mean[c + j];
     }
+    auto one = [&](long long i, const uint4& dv, const uint4& av, const uint4& zv) {
+        float d[8], af[8], zf[8], r[8];
+        unpack8(dv, d); unpack8(av, af); unpack8(zv, zf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = k1[j] * ((af[j] > 0.f ? d[j] : 0.f) - k2[j] - (zf[j] - m[j]) * k3[j]);
+        dz[i] = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+    };
+    long long i = i0;
+    for (; i + step < n8; i += 2 * step) {
+        const uint4 d0 = __ldg(dA + i), a0 = __ldg(a + i), z0 = __ldg(z + i);
+        const uint4 d1 = __ldg(dA + i + step), a1 = __ldg(a + i + step), z1 = __ldg(z + i + step);
+        one(i, d0, a0, z0);
+        one(i + step, d1, a1, z1);
+    }
+    if (i < n8) one(i, __ldg(dA + i), __ldg(a + i), __ldg(z + i));
 }
 
 // ------------------------------------------------------------------------------------------------ pool / upsample backward
@@ -323,12 +429,12 @@ stem_wgrad_kernel(const uint32_t* __restrict__ dz, const float* __restrict__ x, 
     float acc[2][K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[0][k] = acc[1][k] = 0.f;
-    const long long P = static_cast<long long>(N) * H * W;
-    for (long long p = static_cast<long long>(blockIdx.x) * 8 + pl; p < P; p += static_cast<long long>(gridDim.x) * 8) {
-        const int n = static_cast<int>(p / (static_cast<long long>(H) * W));
-        const int rem = static_cast<int>(p - static_cast<long long>(n) * H * W);
+    const int P = N * H * W, HW = H * W;   // launcher checks that the pixel count fits 31 bits
+    for (int p = blockIdx.x * 8 + pl; p < P; p += gridDim.x * 8) {
+        const int n = p / HW;
+        const int rem = p - n * HW;
         const int y = rem / W, xx = rem - y * W;
-        const float2 g = unpack2(__ldg(dz + p * 32 + cp));
+        const float2 g = unpack2(__ldg(dz + static_cast<long long>(p) * 32 + cp));
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
             const float* plane = x + (static_cast<long long>(n) * CIN + ci) * H * W;
@@ -348,6 +454,19 @@ stem_wgrad_kernel(const uint32_t* __restrict__ dz, const float* __restrict__ x, 
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 64 * K; i += 256) atomicAdd(dW + i, part[i]);
+}
+
+// fiWgrad's dW[tap][co][ci] -> the parameter layout grad[co][ci][tap] (accumulated): thread = one (co, ci)
+__global__ void __launch_bounds__(256)
+unpack_conv_grad_kernel(const float* __restrict__ dW, long long n, float* __restrict__ grad) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float v[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] = __ldg(dW + t * n + i);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) grad[i * 9 + t] += v[t];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ optimizer / packing
@@ -387,19 +506,43 @@ pack_conv_kernel(const float* __restrict__ w, int co, int ci, __nv_bfloat16* __r
 
 #define FI_REQUIRE(cond, msg) do { if (!(cond)) return msg; } while (0)
 
+namespace {
+// grid of a per-channel reduction: every block covers 256/c8 pixel lanes (or one when c8 does not divide 256)
+int reduce_blocks(long long P, int c8) {
+    const int rows_par = (c8 <= 256 && 256 % c8 == 0) ? 256 / c8 : 1;
+    return blocks_for(P, rows_par * 4, 148 * 4);
+}
+// grid of an elementwise per-channel kernel: gridDim * 256 must be a multiple of c8 so threads keep their channel group
+int apply_blocks(long long n8, int c8) {
+    int b = blocks_for(n8, 512, 148 * 8);
+    int unit = 1;                      // smallest block count with (unit * 256) % c8 == 0
+    while ((static_cast<long long>(unit) * 256) % c8) ++unit;
+    b = (b + unit - 1) / unit * unit;
+    return b;
+}
+}  // namespace
+
 const char* bn_stats_launch(const void* z, long long P, int C, float* sum, float* sumsq, cudaStream_t st) {
-    FI_REQUIRE(z && sum && sumsq && P > 0 && C > 0 && C % 2 == 0, "bn_stats: bad arguments");
-    FI_REQUIRE((C / 2) <= 256 ? 256 % (C / 2) == 0 : (C / 2) % 256 == 0, "bn_stats: C/2 must divide 256 or be a multiple");
-    bn_stats_kernel<<<blocks_for(P, C / 2 <= 256 ? 256 / (C / 2) : 1, 148 * 4), 256, 0, st>>>(
-        static_cast<const uint32_t*>(z), P, C / 2, sum, sumsq);
+    FI_REQUIRE(z && sum && sumsq && P > 0 && C > 0 && C % 8 == 0 && C <= RED_MAX_C, "bn_stats: bad arguments");
+    bn_stats_kernel<<<reduce_blocks(P, C / 8), 256, 0, st>>>(static_cast<const uint4*>(z), P, C / 8, sum, sumsq);
+    return last_error();
+}
+const char* bn_finalize_launch(const float* sum, const float* sumsq, int C, long long P, float eps, float momentum,
+                               const float* gamma, const float* beta, float* mean, float* rstd, float* scale, float* shift,
+                               float* running_mean, float* running_var, cudaStream_t st) {
+    FI_REQUIRE(sum && sumsq && gamma && beta && mean && rstd && scale && shift && C > 0 && P > 0, "bn_finalize: bad arguments");
+    bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(sum, sumsq, C, 1.0f / static_cast<float>(P),
+                                                        P > 1 ? static_cast<float>(P) / static_cast<float>(P - 1) : 1.f, eps,
+                                                        momentum, gamma, beta, mean, rstd, scale, shift, running_mean,
+                                                        running_var);
     return last_error();
 }
 const char* bn_apply_relu_launch(const void* z, long long P, int C, const float* scale, const float* shift, void* a,
                                  cudaStream_t st) {
     FI_REQUIRE(z && a && scale && shift && P > 0 && C % 8 == 0, "bn_apply: bad arguments");
     const long long n8 = P * (C / 8);
-    bn_apply_relu_kernel<<<blocks_for(n8, 256), 256, 0, st>>>(static_cast<const uint4*>(z), n8, C / 8, scale, shift,
-                                                              static_cast<uint4*>(a));
+    bn_apply_relu_kernel<<<apply_blocks(n8, C / 8), 256, 0, st>>>(static_cast<const uint4*>(z), n8, C / 8, scale, shift,
+                                                                  static_cast<uint4*>(a));
     return last_error();
 }
 const char* head_forward_launch(const void* a, int N, long long HW, const float* w, const float* b, int ncls, float* y,
@@ -422,11 +565,10 @@ const char* head_backward_launch(const void* a, const float* dy, int N, long lon
 }
 const char* bn_relu_bwd_reduce_launch(const void* dA, const void* a, const void* z, long long P, int C, const float* mean,
                                       const float* rstd, float* dbeta, float* dgamma, cudaStream_t st) {
-    FI_REQUIRE(dA && a && z && mean && rstd && dbeta && dgamma && C % 2 == 0, "bn_bwd_reduce: bad arguments");
-    FI_REQUIRE((C / 2) <= 256 ? 256 % (C / 2) == 0 : (C / 2) % 256 == 0, "bn_bwd_reduce: C/2 must divide 256 or be a multiple");
-    bn_relu_bwd_reduce_kernel<<<blocks_for(P, C / 2 <= 256 ? 256 / (C / 2) : 1, 148 * 4), 256, 0, st>>>(
-        static_cast<const uint32_t*>(dA), static_cast<const uint32_t*>(a), static_cast<const uint32_t*>(z), P, C / 2,
-        mean, rstd, dbeta, dgamma);
+    FI_REQUIRE(dA && a && z && mean && rstd && dbeta && dgamma && C % 8 == 0 && C <= RED_MAX_C, "bn_bwd_reduce: bad arguments");
+    bn_relu_bwd_reduce_kernel<<<reduce_blocks(P, C / 8), 256, 0, st>>>(
+        static_cast<const uint4*>(dA), static_cast<const uint4*>(a), static_cast<const uint4*>(z), P, C / 8, mean, rstd,
+        dbeta, dgamma);
     return last_error();
 }
 const char* bn_relu_bwd_apply_launch(const void* dA, const void* a, const void* z, long long P, int C, const float* mean,
@@ -434,7 +576,7 @@ const char* bn_relu_bwd_apply_launch(const void* dA, const void* a, const void* 
                                      void* dz, cudaStream_t st) {
     FI_REQUIRE(dA && a && z && dz && C % 8 == 0, "bn_bwd_apply: bad arguments");
     const long long n8 = P * (C / 8);
-    bn_relu_bwd_apply_kernel<<<blocks_for(n8, 256), 256, 0, st>>>(
+    bn_relu_bwd_apply_kernel<<<apply_blocks(n8, C / 8), 256, 0, st>>>(
         static_cast<const uint4*>(dA), static_cast<const uint4*>(a), static_cast<const uint4*>(z), n8, C / 8,
         1.0f / static_cast<float>(P), mean, rstd, gamma, dbeta, dgamma, static_cast<uint4*>(dz));
     return last_error();
@@ -454,8 +596,8 @@ const char* upsample2x_bwd_launch(const void* d_up, void* d_lo, int N, int h, in
     return last_error();
 }
 const char* stem_wgrad_launch(const void* dz, const float* x, int N, int H, int W, int cin, float* dW, cudaStream_t st) {
-    FI_REQUIRE(dz && x && dW && cin >= 1 && cin <= 6, "stem_wgrad: bad arguments");
-    const int grid = blocks_for(static_cast<long long>(N) * H * W, 8, 148 * 2);
+    FI_REQUIRE(dz && x && dW && cin >= 1 && cin <= 6 && static_cast<long long>(N) * H * W < (1LL << 31), "stem_wgrad: bad arguments");
+    const int grid = blocks_for(static_cast<long long>(N) * H * W, 8 * 16, 148 * 4);
     const uint32_t* g = static_cast<const uint32_t*>(dz);
     switch (cin) {
         case 1: stem_wgrad_kernel<1><<<grid, 256, 0, st>>>(g, x, N, H, W, dW); break;
@@ -465,6 +607,12 @@ const char* stem_wgrad_launch(const void* dz, const float* x, int N, int H, int 
         case 6: stem_wgrad_kernel<6><<<grid, 256, 0, st>>>(g, x, N, H, W, dW); break;   // RGB frame pair
         default: return "stem_wgrad: built for 1, 2, 3, 4 or 6 input channels";
     }
+    return last_error();
+}
+const char* unpack_conv_grad_launch(const float* dW, int cout, int cin, float* grad, cudaStream_t st) {
+    FI_REQUIRE(dW && grad && cout > 0 && cin > 0, "unpack_conv_grad: bad arguments");
+    const long long n = static_cast<long long>(cout) * cin;
+    unpack_conv_grad_kernel<<<blocks_for(n, 256), 256, 0, st>>>(dW, n, grad);
     return last_error();
 }
 const char* adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,

@@ -8,6 +8,9 @@
 namespace fi {
 
 const char* bn_stats_launch(const void* z, long long P, int C, float* sum, float* sumsq, cudaStream_t st);
+const char* bn_finalize_launch(const float* sum, const float* sumsq, int C, long long P, float eps, float momentum,
+                               const float* gamma, const float* beta, float* mean, float* rstd, float* scale, float* shift,
+                               float* running_mean, float* running_var, cudaStream_t st);
 const char* bn_apply_relu_launch(const void* z, long long P, int C, const float* scale, const float* shift, void* a,
                                  cudaStream_t st);
 const char* head_forward_launch(const void* a, int N, long long HW, const float* w, const float* b, int ncls, float* y,
@@ -24,6 +27,7 @@ const char* maxpool_bwd_add_launch(const void* a_full, const void* a_pool, const
                                    void* d_full, int N, int H, int W, int C, cudaStream_t st);
 const char* upsample2x_bwd_launch(const void* d_up, void* d_lo, int N, int h, int w, int C, cudaStream_t st);
 const char* stem_wgrad_launch(const void* dz, const float* x, int N, int H, int W, int cin, float* dW, cudaStream_t st);
+const char* unpack_conv_grad_launch(const float* dW, int cout, int cin, float* grad, cudaStream_t st);
 const char* adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                         int step, cudaStream_t st);
 const char* pack_conv_launch(const float* w, int co, int ci, void* fwd, void* bwd, cudaStream_t st);

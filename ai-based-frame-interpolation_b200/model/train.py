@@ -144,24 +144,20 @@ class TrainStep:
             z = self._zeros = torch.zeros(max(n, 1024), dtype=torch.float32, device=self.device)
         return z
 
-    def _bn_forward(self, layer, z):
-        """Batch statistics -> a = relu(bn(z)); returns (a, mean, rstd) and updates the running statistics."""
+    def _bn_forward(self, layer, z, work):
+        """Batch statistics -> a = relu(bn(z)); returns (a, mean, rstd) and updates the running statistics.
+        work: zeroed fp32 [6, C] scratch (sum, sumsq, mean, rstd, scale, shift)."""
         n, h, w, c = z.shape
         P = n * h * w
-        stats = torch.zeros(2, c, dtype=torch.float32, device=self.device)
-        E.check(self.lib.fiBnStats(_ptr(z), P, c, _ptr(stats[0]), _ptr(stats[1]), E.current_stream()))
-        mean = stats[0] / P
-        var = (stats[1] / P - mean * mean).clamp_min_(0.0)
-        rstd = torch.rsqrt(var + layer.bn.eps)
-        scale = layer.bn.weight.detach() * rstd
-        shift = layer.bn.bias.detach() - mean * scale
+        st = E.current_stream()
+        E.check(self.lib.fiBnStats(_ptr(z), P, c, _ptr(work[0]), _ptr(work[1]), st))
+        bn = layer.bn
+        E.check(self.lib.fiBnFinalize(_ptr(work[0]), _ptr(work[1]), c, P, bn.eps, BN_MOMENTUM, _ptr(bn.weight),
+                                      _ptr(bn.bias), _ptr(work[2]), _ptr(work[3]), _ptr(work[4]), _ptr(work[5]),
+                                      _ptr(bn.running_mean), _ptr(bn.running_var), st))
         a = torch.empty_like(z)
-        E.check(self.lib.fiBnApplyRelu(_ptr(z), P, c, _ptr(scale), _ptr(shift), _ptr(a), E.current_stream()))
-        with torch.no_grad():  # nn.BatchNorm2d bookkeeping (unbiased variance for the running estimate)
-            layer.bn.running_mean.mul_(1 - BN_MOMENTUM).add_(mean, alpha=BN_MOMENTUM)
-            layer.bn.running_var.mul_(1 - BN_MOMENTUM).add_(var * (P / max(P - 1, 1)), alpha=BN_MOMENTUM)
-            layer.bn.num_batches_tracked += 1
-        return a, mean, rstd
+        E.check(self.lib.fiBnApplyRelu(_ptr(z), P, c, _ptr(work[4]), _ptr(work[5]), _ptr(a), st))
+        return a, work[2], work[3]
 
     # ------------------------------------------------------------------------------------------------ one step
     @torch.no_grad()
@@ -174,6 +170,17 @@ class TrainStep:
         with torch.cuda.device(self.device):
             self.flat_grad.zero_()
             acts, zs, stats, packs = {}, {}, {}, {}
+            # one zeroed scratch for every layer's BatchNorm reductions / affine and weight-gradient accumulators
+            bn_total = sum(6 * l.cout for l in self.layers)
+            dw_total = sum(9 * l.cout * l.cin for l in self.layers[1:])
+            scratch = torch.zeros(bn_total + dw_total, dtype=torch.float32, device=self.device)
+            bn_work, dw_work, off = {}, {}, 0
+            for l in self.layers:
+                bn_work[l.name] = scratch[off:off + 6 * l.cout].view(6, l.cout)
+                off += 6 * l.cout
+            for l in self.layers[1:]:
+                dw_work[l.name] = scratch[off:off + 9 * l.cout * l.cin]
+                off += 9 * l.cout * l.cin
             # ---- pack weights (bf16 forward rows, flipped/transposed rows for the data gradient)
             for l in self.layers:
                 wt = l.conv.weight.detach()
@@ -210,7 +217,7 @@ class TrainStep:
                         acts[l.src1] = up
                     z = self._conv(acts[l.src], packs[l.name][0], l.cout, acts.get(l.src1) if l.src1 else None)
                 zs[l.name] = z
-                acts[l.name], mean, rstd = self._bn_forward(l, z)
+                acts[l.name], mean, rstd = self._bn_forward(l, z, bn_work[l.name])
                 stats[l.name] = (mean, rstd)
             last = acts["up4.3"]
             hw_, hb = self.unet.outc.conv.weight.detach().reshape(-1, 64).contiguous(), self.unet.outc.conv.bias.detach()
@@ -241,25 +248,22 @@ class TrainStep:
                 P = ln * lh * lw
                 mean, rstd = stats[l.name]
                 dA = grads.pop(l.name)
-                red = torch.zeros(2, lc, dtype=torch.float32, device=self.device)  # dbeta, dgamma
-                E.check(lib.fiBnReluBackwardReduce(_ptr(dA), _ptr(a), _ptr(z), P, lc, _ptr(mean), _ptr(rstd), _ptr(red[0]),
-                                                   _ptr(red[1]), st()))
-                gamma = l.bn.weight.detach()
+                dbeta, dgamma = self.grad_view[l.bn.bias], self.grad_view[l.bn.weight]   # zeroed with flat_grad
+                E.check(lib.fiBnReluBackwardReduce(_ptr(dA), _ptr(a), _ptr(z), P, lc, _ptr(mean), _ptr(rstd), _ptr(dbeta),
+                                                   _ptr(dgamma), st()))
                 dz = torch.empty_like(z)
-                E.check(lib.fiBnReluBackwardApply(_ptr(dA), _ptr(a), _ptr(z), P, lc, _ptr(mean), _ptr(rstd), _ptr(gamma),
-                                                  _ptr(red[0]), _ptr(red[1]), _ptr(dz), st()))
-                self.grad_view[l.bn.bias].add_(red[0])
-                self.grad_view[l.bn.weight].add_(red[1])
+                E.check(lib.fiBnReluBackwardApply(_ptr(dA), _ptr(a), _ptr(z), P, lc, _ptr(mean), _ptr(rstd),
+                                                  _ptr(l.bn.weight), _ptr(dbeta), _ptr(dgamma), _ptr(dz), st()))
                 # weight gradient
                 if l.name == "inc.0":
                     E.check(lib.fiStemWgrad(_ptr(dz), _ptr(x), n, h, w, l.cin, _ptr(self.grad_view[l.conv.weight]), st()))
                     continue
                 srcs = [acts[l.src]] + ([acts[l.src1]] if l.src1 else [])
-                dW = torch.zeros((9, l.cout, l.cin), dtype=torch.float32, device=self.device)
+                dW = dw_work[l.name]
                 x1 = srcs[1] if len(srcs) > 1 else None
                 E.check(lib.fiWgrad(_ptr(dz), _ptr(srcs[0]), srcs[0].shape[3], _ptr(x1), x1.shape[3] if x1 is not None else 0,
                                     ln, lh, lw, l.cout, _ptr(dW), st()))
-                self.grad_view[l.conv.weight].add_(dW.permute(1, 2, 0).reshape(l.cout, l.cin, 3, 3))
+                E.check(lib.fiUnpackConvGrad(_ptr(dW), l.cout, l.cin, _ptr(self.grad_view[l.conv.weight]), st()))
                 # data gradient(s): conv3x3 of dz with the flipped, transposed weights
                 bwd = packs[l.name][1]
                 c0 = srcs[0].shape[3]
@@ -287,6 +291,7 @@ class TrainStep:
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                 dist.all_reduce(self.flat_grad)
                 self.flat_grad.div_(dist.get_world_size())
+            torch._foreach_add_([l.bn.num_batches_tracked for l in self.layers], 1)
             self.step_count += 1
             E.check(lib.fiAdamStep(_ptr(self.flat_param), _ptr(self.flat_grad), _ptr(self.m), _ptr(self.v),
                                    self.flat_param.numel(), self.lr, self.betas[0], self.betas[1], self.eps,

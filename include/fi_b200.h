@@ -218,6 +218,13 @@ int fiUpsample2xBackward(const void* d_up, void* d_lo, int N, int h, int w, int 
 int fiWgrad(const void* dz, const void* x0, int c0, const void* x1, int c1, int N, int H, int W, int cout, float* dW,
             void* stream);
 int fiStemWgrad(const void* dz, const float* x, int N, int H, int W, int cin, float* dW, void* stream);
+/* Batch sums -> mean, rstd = 1/sqrt(var + eps), scale = gamma * rstd, shift = beta - mean * scale (C floats each), and
+ * the nn.BatchNorm2d running estimates updated in place (momentum, unbiased variance; either may be NULL). */
+int fiBnFinalize(const float* sum, const float* sumsq, int C, int64_t P, float eps, float momentum, const float* gamma,
+                 const float* beta, float* mean, float* rstd, float* scale, float* shift, float* running_mean,
+                 float* running_var, void* stream);
+/* fiWgrad's dW[tap][cout][cin] added into the parameter-gradient layout grad[cout][cin][3][3]. */
+int fiUnpackConvGrad(const float* dW, int cout, int cin, float* grad, void* stream);
 /* torch.optim.Adam (model/train.py:160) on one flat fp32 parameter vector; step counts from 1. */
 int fiAdamStep(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                int step, void* stream);

@@ -185,3 +185,39 @@ def test_stem_weight_gradient(cuda_device, n, cin, h, w):
     torch.cuda.synchronize()
     assert torch.allclose((dW - prior).cpu(), wt.grad, rtol=1e-4, atol=1e-4)
     assert lib.fiStemWgrad(p(dzd), p(xd), n, h, w, 5, p(dW), st) != 0
+
+
+def test_bn_finalize_and_running_statistics(cuda_device):
+    lib, st = E.lib(), E.current_stream()
+    g = torch.Generator().manual_seed(8)
+    n, c, h, w = 3, 192, 5, 6   # C/8 = 24 does not divide 256: the unpacked reduction walk
+    z = (torch.randn(n, c, h, w, generator=g) * 2 + 0.5).to(torch.bfloat16).float()
+    bn = torch.nn.BatchNorm2d(c)
+    bn.weight.data, bn.bias.data = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    bn.running_mean.data, bn.running_var.data = torch.randn(c, generator=g), torch.rand(c, generator=g) + 0.5
+    rm, rv = bn.running_mean.clone().to(cuda_device), bn.running_var.clone().to(cuda_device)
+    bn.train()
+    ref = bn(z)
+    P = n * h * w
+    zd = nhwc(z, cuda_device)
+    work = torch.zeros(6, c, device=cuda_device)
+    gd, bd = bn.weight.detach().to(cuda_device), bn.bias.detach().to(cuda_device)
+    E.check(lib.fiBnStats(p(zd), P, c, p(work[0]), p(work[1]), st))
+    E.check(lib.fiBnFinalize(p(work[0]), p(work[1]), c, P, bn.eps, 0.1, p(gd), p(bd), p(work[2]), p(work[3]), p(work[4]),
+                             p(work[5]), p(rm), p(rv), st))
+    torch.cuda.synchronize()
+    assert torch.allclose(rm.cpu(), bn.running_mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rv.cpu(), bn.running_var, rtol=1e-3, atol=1e-5)
+    got = nchw(zd.float() * work[4] + work[5])
+    assert torch.allclose(got, ref.detach(), rtol=1e-3, atol=2e-3)
+
+
+def test_unpack_conv_grad(cuda_device):
+    lib, st = E.lib(), E.current_stream()
+    g = torch.Generator().manual_seed(6)
+    dW = torch.randn(9, 128, 64, generator=g).to(cuda_device)
+    grad = torch.randn(128, 64, 3, 3, generator=g).to(cuda_device)
+    want = grad + dW.permute(1, 2, 0).reshape(128, 64, 3, 3)
+    E.check(lib.fiUnpackConvGrad(p(dW), 128, 64, p(grad), st))
+    torch.cuda.synchronize()
+    assert torch.allclose(grad, want, rtol=1e-6, atol=1e-6)
