@@ -5,10 +5,15 @@
 // is a GEMM whose reduction dimension is the pixel index. In NHWC both operands have that dimension as the slow one, i.e.
 // they are "MN-major" tcgen05 operands as they lie in HBM: a TMA box {64 channels, bw, bh, 1 image} with bw*bh = 64 lands
 // in shared memory as 64 pixel rows of 128 swizzled bytes — the canonical MN-major SWIZZLE_128B atom (8 K-rows x 128 B,
-// atoms 1024 B apart along K, 64-channel blocks LBO apart along M/N). The tap is a coordinate shift of the x box and the
-// zero fill of out-of-bounds TMA reads is the convolution's padding, so nothing is transposed, padded or copied. The
-// reduction is split over CTAs; partial tiles are added to dW with fp32 atomics. When the layer has fewer than 128 output
-// channels but at least 128 input channels the operand roles are swapped (M = input channels) to fill the 128 MMA rows.
+// atoms 1024 B apart along K, 64-channel blocks LBO apart along M/N). A tap is a coordinate shift of the box and the zero
+// fill of out-of-bounds TMA reads is the convolution's padding, so nothing is transposed, padded or copied.
+//
+// GEMM shape. The nine taps are stacked along N: a column block is (shift of x, 64 input channels), so one dz slab in
+// shared memory feeds 3-4 column blocks (N = 192 / 256) whatever the layer's channel count. Rows are output channels; a
+// 64-output-channel layer would fill only half of the 128 MMA rows, so there the second row block is dz itself shifted
+// one pixel to the left (dW[a + c] = sum_q dz[q - a] x[q + c]): rows = {a.dx = 0, 1} x 64 co, columns = {c.dy = -1,0,1} x
+// {c.dx = -1, 0} x ci, and the duplicate (a.dx, c.dx) = (1, -1) of tap.dx = 0 is dropped in the epilogue (6 of 8 useful).
+// The reduction is split over CTAs; partial tiles are added to dW with fp32 vector atomics.
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
 #include "train_kernels.cuh"
@@ -20,21 +25,22 @@ namespace fi {
 namespace {
 
 constexpr int WG_THREADS = 192;
-constexpr int WG_BLOCK_BYTES = 64 * 128;      // one 64-channel x 64-pixel block
-constexpr int WG_A_BYTES = 2 * WG_BLOCK_BYTES;  // M = 128 channels
+constexpr int WG_BLOCK_BYTES = 64 * 128;        // one 64-channel x 64-pixel block
+constexpr int WG_A_BYTES = 2 * WG_BLOCK_BYTES;  // M = 128 rows
 
 struct WgradParams {
     int cout, cin, c0;                          // c0 = channels of the first x source (concat layers have two)
-    int m_total, m_tiles, n_tiles;              // GEMM rows / tiles (rows = cout, or cin when swapped)
+    int co_blocks, ci_blocks;                   // 64-channel blocks
+    int stacked;                                // 1: cout == 64, rows = two column shifts of dz
+    int m_tiles, n_tiles;
     int k_chunks, chunk_slabs, total_slabs;     // split of the pixel slabs over work items
     int tiles_w, tiles_h, bw, bh;               // a slab is a bw x bh pixel box of one image
-    int swap;                                   // 1: A = x (M = cin), B = dz (N = cout)
     float* dW;
 };
 
-__host__ __device__ constexpr int wg_stages(int n_tile) { return n_tile == 256 ? 4 : 6; }
-__host__ __device__ constexpr int wg_smem(int n_tile) {
-    return 1024 + wg_stages(n_tile) * (WG_A_BYTES + n_tile * 128) + 256;
+__host__ __device__ constexpr int wg_stages(int n_blocks) { return n_blocks == 4 ? 4 : 5; }
+__host__ __device__ constexpr int wg_smem(int n_blocks) {
+    return 1024 + wg_stages(n_blocks) * (WG_A_BYTES + n_blocks * WG_BLOCK_BYTES) + 256;
 }
 
 // MN-major SWIZZLE_128B operand: 8 K-rows of 128 B per atom, atoms 1024 B apart along K, 64-element blocks `lbo` apart.
@@ -48,15 +54,28 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
     return d;
 }
 
-template <int N_TILE>
+// column block nb -> shift of x and its 64-channel block
+__device__ __forceinline__ void decode_col_block(const WgradParams& p, int nb, int& dy, int& dx, int& cb) {
+    const int sidx = nb / p.ci_blocks;
+    cb = nb - sidx * p.ci_blocks;
+    if (p.stacked) {
+        dy = sidx / 2 - 1;
+        dx = sidx % 2 - 1;   // -1, 0
+    } else {
+        dy = sidx / 3 - 1;
+        dx = sidx % 3 - 1;
+    }
+}
+
+template <int N_BLOCKS>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_x0,
              const __grid_constant__ CUtensorMap map_x1, const WgradParams p) {
-    constexpr int STAGES = wg_stages(N_TILE);
-    constexpr int B_BYTES = N_TILE * 128;
-    constexpr int N_BLOCKS = N_TILE / 64;
+    constexpr int STAGES = wg_stages(N_BLOCKS);
+    constexpr int N_TILE = 64 * N_BLOCKS;
+    constexpr int B_BYTES = N_BLOCKS * WG_BLOCK_BYTES;
     constexpr uint32_t IDESC = umma_idesc_bf16(128, N_TILE) | (1u << 15) | (1u << 16);  // A and B MN-major
-    constexpr int TMEM_COLS = 2 * N_TILE < 32 ? 32 : 2 * N_TILE;
+    constexpr int TMEM_COLS = 512;   // two accumulators of 192 or 256 columns
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -87,15 +106,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    // work item = (tap, m tile, n tile, k chunk); k chunk fastest so that neighbouring CTAs share operand rows in L2
-    const int total = 9 * p.m_tiles * p.n_tiles * p.k_chunks;
-    auto decode = [&](int t, int& tap, int& mt, int& nt, int& s0, int& s1) {
-        const int kc = t % p.k_chunks;
-        int r = t / p.k_chunks;
-        nt = r % p.n_tiles;
-        r /= p.n_tiles;
-        mt = r % p.m_tiles;
-        tap = r / p.m_tiles;
+    // work item = (k chunk, m tile, n tile), tile fastest: CTAs running together share the same pixel slabs in L2
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int total = tiles * p.k_chunks;
+    auto decode = [&](int t, int& mt, int& nt, int& s0, int& s1) {
+        const int kc = t / tiles;
+        const int r = t - kc * tiles;
+        mt = r / p.n_tiles;
+        nt = r - mt * p.n_tiles;
         s0 = kc * p.chunk_slabs;
         s1 = s0 + p.chunk_slabs < p.total_slabs ? s0 + p.chunk_slabs : p.total_slabs;
     };
@@ -103,12 +121,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
     if (warp == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        const int m_blocks = (p.m_total + 63) / 64;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            int tap, mt, nt, s0, s1;
-            decode(t, tap, mt, nt, s0, s1);
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            const int a_blocks = m_blocks - 2 * mt < 2 ? m_blocks - 2 * mt : 2;  // rows past m_total are never stored
+            int mt, nt, s0, s1;
+            decode(t, mt, nt, s0, s1);
+            const int a_blocks = p.stacked ? 2 : (p.co_blocks - 2 * mt < 2 ? p.co_blocks - 2 * mt : 2);
+            int bdy[N_BLOCKS], bdx[N_BLOCKS], bcb[N_BLOCKS];
+#pragma unroll
+            for (int j = 0; j < N_BLOCKS; ++j) decode_col_block(p, nt * N_BLOCKS + j, bdy[j], bdx[j], bcb[j]);
             for (int s = s0; s < s1; ++s) {
                 const int tw = s % p.tiles_w;
                 const int r = s / p.tiles_w;
@@ -118,21 +137,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
                 const uint32_t full = bar_full + 8 * stage;
                 if (elect_one()) {
                     mbar_expect_tx(full, (a_blocks + N_BLOCKS) * WG_BLOCK_BYTES);
-                    auto load_dz = [&](uint32_t dst, int cb) { tma_load_4d(dst, &map_dz, full, cb * 64, w0, h0, img); };
-                    auto load_x = [&](uint32_t dst, int cb) {
-                        const int c = cb * 64;
-                        if (c < p.c0) tma_load_4d(dst, &map_x0, full, c, w0 + dx, h0 + dy, img);
-                        else tma_load_4d(dst, &map_x1, full, c - p.c0, w0 + dx, h0 + dy, img);
-                    };
                     const uint32_t sa = smem_a + stage * WG_A_BYTES, sb = smem_b + stage * B_BYTES;
-                    for (int b = 0; b < a_blocks; ++b) {
-                        if (p.swap) load_x(sa + b * WG_BLOCK_BYTES, 2 * mt + b);
-                        else load_dz(sa + b * WG_BLOCK_BYTES, 2 * mt + b);
+                    for (int b = 0; b < a_blocks; ++b) {   // rows past cout are never stored: their block is not loaded
+                        if (p.stacked) tma_load_4d(sa + b * WG_BLOCK_BYTES, &map_dz, full, 0, w0 - b, h0, img);
+                        else tma_load_4d(sa + b * WG_BLOCK_BYTES, &map_dz, full, (2 * mt + b) * 64, w0, h0, img);
                     }
 #pragma unroll
-                    for (int b = 0; b < N_BLOCKS; ++b) {
-                        if (p.swap) load_dz(sb + b * WG_BLOCK_BYTES, nt * N_BLOCKS + b);
-                        else load_x(sb + b * WG_BLOCK_BYTES, nt * N_BLOCKS + b);
+                    for (int j = 0; j < N_BLOCKS; ++j) {
+                        const int c = bcb[j] * 64;
+                        if (c < p.c0) tma_load_4d(sb + j * WG_BLOCK_BYTES, &map_x0, full, c, w0 + bdx[j], h0 + bdy[j], img);
+                        else tma_load_4d(sb + j * WG_BLOCK_BYTES, &map_x1, full, c - p.c0, w0 + bdx[j], h0 + bdy[j], img);
                     }
                 }
                 __syncwarp();
@@ -147,12 +161,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
         uint32_t phase = 0;
         int it = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-            int tap, mt, nt, s0, s1;
-            decode(t, tap, mt, nt, s0, s1);
+            int mt, nt, s0, s1;
+            decode(t, mt, nt, s0, s1);
             const int acc = it & 1;
             mbar_wait(bar_tempty + 8 * acc, ((it >> 1) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * N_TILE;
+            const uint32_t d_tmem = tmem_base + acc * 256;
             for (int s = s0; s < s1; ++s) {
                 mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
@@ -176,33 +190,31 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
         const int q = warp & 3;
         int it = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-            int tap, mt, nt, s0, s1;
-            decode(t, tap, mt, nt, s0, s1);
+            int mt, nt, s0, s1;
+            decode(t, mt, nt, s0, s1);
             const int acc = it & 1;
             mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * N_TILE;
-            const int m = mt * 128 + q * 32 + lane;
-            float* tap_base = p.dW + static_cast<size_t>(tap) * p.cout * p.cin;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+            const int row = q * 32 + lane;
+            const int adx = p.stacked ? row >> 6 : 0;                      // warp-uniform (q)
+            const int co = p.stacked ? (row & 63) : mt * 128 + row;
 #pragma unroll 1
             for (int c = 0; c < N_TILE / 32; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + c * 32, v);
                 tmem_ld_wait();
-                if (m < p.m_total) {
-                    const int n0 = nt * N_TILE + c * 32;
-                    if (!p.swap) {  // row = co, columns = ci: contiguous in dW
-                        float* row = tap_base + static_cast<size_t>(m) * p.cin + n0;
+                int dy, dx, cb;
+                decode_col_block(p, nt * N_BLOCKS + (c >> 1), dy, dx, cb);
+                const bool duplicate = adx == 1 && dx == -1;               // tap.dx = 0 is produced by (0, 0)
+                if (co < p.cout && !duplicate) {
+                    const int tap = (dy + 1) * 3 + (dx + adx + 1);
+                    float* out = p.dW + (static_cast<size_t>(tap) * p.cout + co) * p.cin + cb * 64 + (c & 1) * 32;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            atomicAdd(reinterpret_cast<float4*>(row + 4 * j),
-                                      make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
-                        }
-                    } else {        // row = ci, columns = co: lanes cover consecutive ci of one co row
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            atomicAdd(tap_base + static_cast<size_t>(n0 + j) * p.cin + m, __uint_as_float(v[j]));
+                    for (int j = 0; j < 8; ++j) {
+                        atomicAdd(reinterpret_cast<float4*>(out + 4 * j),
+                                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
                     }
                 }
             }
@@ -219,16 +231,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
     }
 }
 
-template <int N_TILE>
+template <int N_BLOCKS>
 const char* launch_wgrad(const CUtensorMap* maps, const WgradParams& p, int grid, cudaStream_t st) {
-    auto k = wgrad_kernel<N_TILE>;
+    auto k = wgrad_kernel<N_BLOCKS>;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem(N_TILE)) != cudaSuccess)
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem(N_BLOCKS)) != cudaSuccess)
             return "wgrad: cudaFuncSetAttribute failed";
         configured = true;
     }
-    k<<<grid, WG_THREADS, wg_smem(N_TILE), st>>>(maps[0], maps[1], maps[2], p);
+    k<<<grid, WG_THREADS, wg_smem(N_BLOCKS), st>>>(maps[0], maps[1], maps[2], p);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -257,12 +269,13 @@ const char* wgrad_launch(const void* dz, const void* x0, int c0, const void* x1,
     p.cin = cin;
     p.c0 = c0;
     p.dW = dW;
-    p.swap = (cout % 128 != 0 && cin % 128 == 0) ? 1 : 0;
-    p.m_total = p.swap ? cin : cout;
-    const int n_total = p.swap ? cout : cin;
-    const int n_tile = n_total % 256 == 0 ? 256 : (n_total % 128 == 0 ? 128 : 64);
-    p.m_tiles = (p.m_total + 127) / 128;
-    p.n_tiles = n_total / n_tile;
+    p.co_blocks = cout / 64;
+    p.ci_blocks = cin / 64;
+    p.stacked = cout == 64 ? 1 : 0;
+    p.m_tiles = p.stacked ? 1 : (p.co_blocks + 1) / 2;
+    const int col_blocks = (p.stacked ? 6 : 9) * p.ci_blocks;      // always a multiple of 3
+    const int n_blocks = col_blocks % 4 == 0 ? 4 : 3;
+    p.n_tiles = col_blocks / n_blocks;
     // pixel slab: the 64-pixel box shape that wastes the fewest out-of-bounds pixels
     long long best = -1;
     for (int bw = 16; bw >= 1; bw >>= 1) {
@@ -278,7 +291,7 @@ const char* wgrad_launch(const void* dz, const void* x0, int c0, const void* x1,
     p.tiles_h = (H + p.bh - 1) / p.bh;
     p.total_slabs = N * p.tiles_w * p.tiles_h;
     // split the reduction so that there are a few work items per SM
-    const int base_items = 9 * p.m_tiles * p.n_tiles;
+    const int base_items = p.m_tiles * p.n_tiles;
     int chunks = (4 * num_sms + base_items - 1) / base_items;
     if (chunks > p.total_slabs) chunks = p.total_slabs;
     if (chunks < 1) chunks = 1;
@@ -289,13 +302,9 @@ const char* wgrad_launch(const void* dz, const void* x0, int c0, const void* x1,
     if ((e = encode_pixels(&maps[0], dz, N, H, W, cout, p.bw, p.bh))) return e;
     if ((e = encode_pixels(&maps[1], x0, N, H, W, c0, p.bw, p.bh))) return e;
     if ((e = encode_pixels(&maps[2], c1 > 0 ? x1 : x0, N, H, W, c1 > 0 ? c1 : c0, p.bw, p.bh))) return e;
-    const long long total = 9LL * p.m_tiles * p.n_tiles * p.k_chunks;
+    const long long total = static_cast<long long>(base_items) * p.k_chunks;
     const int grid = static_cast<int>(total < num_sms ? total : num_sms);
-    switch (n_tile) {
-        case 64: return launch_wgrad<64>(maps, p, grid, st);
-        case 128: return launch_wgrad<128>(maps, p, grid, st);
-        default: return launch_wgrad<256>(maps, p, grid, st);
-    }
+    return n_blocks == 4 ? launch_wgrad<4>(maps, p, grid, st) : launch_wgrad<3>(maps, p, grid, st);
 }
 
 }  // namespace fi
