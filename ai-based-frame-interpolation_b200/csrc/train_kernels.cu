@@ -141,28 +141,44 @@ bn_apply_relu_kernel(const uint4* __restrict__ z, long long n8, int c8, const fl
 
 // ------------------------------------------------------------------------------------------------ head + loss
 // y[n][k][pix] = b[k] + sum_c a[n][pix][c] * w[k][c]   (a: bf16 [N*HW][64])
+template <int NCLS>
 __global__ void __launch_bounds__(256)
 head_forward_kernel(const uint4* __restrict__ a, long long P, long long HW, const float* __restrict__ w,
-                    const float* __restrict__ b, int ncls, float* __restrict__ y) {
+                    const float* __restrict__ b, float* __restrict__ y) {
+    constexpr int ncls = NCLS;
     __shared__ float ws[4 * 64];
     for (int i = threadIdx.x; i < ncls * 64; i += blockDim.x) ws[i] = w[i];
     __syncthreads();
-    for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < P;
-         p += static_cast<long long>(gridDim.x) * blockDim.x) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // 8 consecutive lanes share a pixel (one 16-byte load each: a warp reads 512 contiguous bytes), partial dot
+    // products are combined with three xor-shuffles; the trip count is uniform across the warp
+    const int cg = threadIdx.x & 7;
+    float wr[NCLS][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint4 v = __ldg(a + p * 8 + j);
-            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    for (int cls = 0; cls < ncls; ++cls)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 f = unpack2(wv[k]);
-                for (int cls = 0; cls < ncls; ++cls)
-                    acc[cls] = fmaf(f.y, ws[cls * 64 + j * 8 + 2 * k + 1], fmaf(f.x, ws[cls * 64 + j * 8 + 2 * k], acc[cls]));
-            }
+        for (int j = 0; j < 8; ++j) wr[cls][j] = ws[cls * 64 + cg * 8 + j];
+    const long long total = (P * 8 + 31) / 32 * 32;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long p = i >> 3;
+        float f[8];
+        unpack8(p < P ? __ldg(a + i) : make_uint4(0, 0, 0, 0), f);
+        float acc[NCLS];
+#pragma unroll
+        for (int cls = 0; cls < ncls; ++cls) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s = fmaf(f[j], wr[cls][j], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            acc[cls] = s;
         }
-        const long long n = p / HW, pix = p - n * HW;
-        for (int cls = 0; cls < ncls; ++cls) y[(n * ncls + cls) * HW + pix] = acc[cls] + b[cls];
+        if (cg == 0 && p < P) {
+            const long long n = p / HW, pix = p - n * HW;
+#pragma unroll
+            for (int cls = 0; cls < ncls; ++cls) y[(n * ncls + cls) * HW + pix] = acc[cls] + b[cls];
+        }
     }
 }
 
@@ -183,10 +199,12 @@ mse_kernel(const float* __restrict__ y, const float* __restrict__ t, long long n
 }
 
 // da[n][pix][c] = sum_k dy[n][k][pix] w[k][c];  dw[k][c] += sum dy * a;  db[k] += sum dy
+template <int NCLS>
 __global__ void __launch_bounds__(256)
 head_backward_kernel(const uint4* __restrict__ a, const float* __restrict__ dy, long long P, long long HW,
-                     const float* __restrict__ w, int ncls, uint4* __restrict__ da, float* __restrict__ dw,
+                     const float* __restrict__ w, uint4* __restrict__ da, float* __restrict__ dw,
                      float* __restrict__ db) {
+    constexpr int ncls = NCLS;
     __shared__ float ws[4 * 64];
     __shared__ float acc_w[4 * 64];
     __shared__ float acc_b[4];
@@ -206,7 +224,8 @@ head_backward_kernel(const uint4* __restrict__ a, const float* __restrict__ dy, 
         const long long p = i >> 3;
         const long long n = p / HW, pix = p - n * HW;
         float g[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = 0; k < ncls; ++k) g[k] = dy[(n * ncls + k) * HW + pix];
+#pragma unroll
+        for (int k = 0; k < ncls; ++k) g[k] = __ldg(dy + (n * ncls + k) * HW + pix);
         const uint4 v = __ldg(a + i);
         const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
         float av[8];
@@ -216,12 +235,17 @@ head_backward_kernel(const uint4* __restrict__ a, const float* __restrict__ dy, 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float s = 0.f;
+#pragma unroll
             for (int k = 0; k < ncls; ++k) { s = fmaf(g[k], ws[k * 64 + cg * 8 + j], s); lw[k][j] = fmaf(g[k], av[j], lw[k][j]); }
             o[j] = s;
         }
-        if (cg == 0) for (int k = 0; k < ncls; ++k) lb[k] += g[k];
+        if (cg == 0) {
+#pragma unroll
+            for (int k = 0; k < ncls; ++k) lb[k] += g[k];
+        }
         da[i] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
     }
+#pragma unroll
     for (int k = 0; k < ncls; ++k) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) atomicAdd(&acc_w[k * 64 + cg * 8 + j], lw[k][j]);
@@ -383,29 +407,40 @@ upsample2x_bwd_kernel(const uint4* __restrict__ d_up, uint4* __restrict__ d_lo, 
         const int y = static_cast<int>(r % h);
         const int n = static_cast<int>(r / h);
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int oy = max(0, 2 * y - 3); oy <= min(oh - 1, 2 * y + 3); ++oy) {
-            const float fy = rh * oy;
-            const int y0 = static_cast<int>(fy);
-            const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
-            const float ly = fy - y0;
-            const float wy = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
-            if (wy == 0.f) continue;
-            for (int ox = max(0, 2 * x - 3); ox <= min(ow - 1, 2 * x + 3); ++ox) {
+        // weights of the five candidate output rows / columns 2y-2 .. 2y+2 (none further away can reference (y, x):
+        // the source coordinate is o * (h-1)/(2h-1), just under o/2)
+        float wy[5], wx[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+            const int oy = 2 * y - 2 + d, ox = 2 * x - 2 + d;
+            wy[d] = wx[d] = 0.f;
+            if (oy >= 0 && oy < oh) {
+                const float fy = rh * oy;
+                const int y0 = static_cast<int>(fy);
+                const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+                const float ly = fy - y0;
+                wy[d] = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
+            }
+            if (ox >= 0 && ox < ow) {
                 const float fx = rw * ox;
                 const int x0 = static_cast<int>(fx);
                 const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
                 const float lx = fx - x0;
-                const float wx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
-                if (wx == 0.f) continue;
-                const uint4 g = __ldg(d_up + ((static_cast<long long>(n) * oh + oy) * ow + ox) * c8 + cg);
-                const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
-                const float wt = wy * wx;
+                wx[d] = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
+            }
+        }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float2 f = unpack2(gw[k]);
-                    acc[2 * k] = fmaf(wt, f.x, acc[2 * k]);
-                    acc[2 * k + 1] = fmaf(wt, f.y, acc[2 * k + 1]);
-                }
+        for (int dy = 0; dy < 5; ++dy) {
+            if (wy[dy] == 0.f) continue;
+            const uint4* row = d_up + (static_cast<long long>(n) * oh + (2 * y - 2 + dy)) * ow * c8 + cg;
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) {
+                if (wx[dx] == 0.f) continue;
+                float f[8];
+                unpack8(__ldg(row + static_cast<long long>(2 * x - 2 + dx) * c8), f);
+                const float wt = wy[dy] * wx[dx];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(wt, f[k], acc[k]);
             }
         }
         d_lo[i] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
@@ -413,42 +448,79 @@ upsample2x_bwd_kernel(const uint4* __restrict__ d_up, uint4* __restrict__ d_lo, 
     }
 }
 
-// Stem weight gradient (C_in <= 8, K = 9*C_in): dW[co][ci][tap] += sum_px dz[px,co] * x[px+tap, ci]; x in NCHW fp32.
-// thread = one channel pair of dz, 8 pixel lanes per block; the 2 x 9*CIN partial sums live in registers (CIN is a
-// template parameter so that the accumulator array is never indexed dynamically), are reduced over the 8 pixel lanes
-// with shared-memory atomics and leave the block as one global atomic per weight.
+// Stem weight gradient (K = 9*C_in): dW[co][ci][tap] += sum_px dz[px,co] * x[px+tap, ci]; x in NCHW fp32.
+// A block walks 128-pixel row segments: the 3 x 130 input window of a segment is staged in shared memory, each warp
+// takes 16 consecutive pixels and slides a 3x3xCIN register window along them (3*CIN shared loads per pixel); a thread
+// owns one channel pair of dz, so its 2 x 9*CIN partial sums stay in registers (CIN is a template parameter: the
+// accumulator array is never indexed dynamically). Partials are combined per block with shared-memory atomics and leave
+// the block as one global atomic per weight.
+constexpr int STEM_WG_TILE = 128;
+
 template <int CIN>
 __global__ void __launch_bounds__(256)
 stem_wgrad_kernel(const uint32_t* __restrict__ dz, const float* __restrict__ x, int N, int H, int W,
                   float* __restrict__ dW) {
     constexpr int K = 9 * CIN;
+    constexpr int XS = STEM_WG_TILE + 2;
+    __shared__ float xs[CIN][3][XS];
     __shared__ float part[64 * K];
     for (int i = threadIdx.x; i < 64 * K; i += 256) part[i] = 0.f;
-    __syncthreads();
-    const int cp = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    const int cp = threadIdx.x & 31, wp = threadIdx.x >> 5;
     float acc[2][K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[0][k] = acc[1][k] = 0.f;
-    const int P = N * H * W, HW = H * W;   // launcher checks that the pixel count fits 31 bits
-    for (int p = blockIdx.x * 8 + pl; p < P; p += gridDim.x * 8) {
-        const int n = p / HW;
-        const int rem = p - n * HW;
-        const int y = rem / W, xx = rem - y * W;
-        const float2 g = unpack2(__ldg(dz + static_cast<long long>(p) * 32 + cp));
+    const int tiles_per_row = (W + STEM_WG_TILE - 1) / STEM_WG_TILE;
+    const int total = N * H * tiles_per_row;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int tr = tile % tiles_per_row;
+        const int ny = tile / tiles_per_row;
+        const int y = ny % H, n = ny / H;
+        const int x0 = tr * STEM_WG_TILE;
+        __syncthreads();   // the previous segment's readers are done (and `part` is zeroed on the first pass)
+        for (int i = threadIdx.x; i < CIN * 3 * XS; i += 256) {
+            const int c = i % XS;
+            const int r = (i / XS) % 3, ci = i / (3 * XS);
+            const int yy = y + r - 1, xq = x0 + c - 1;
+            (&xs[0][0][0])[i] = (yy >= 0 && yy < H && xq >= 0 && xq < W)
+                                    ? __ldg(x + ((static_cast<long long>(n) * CIN + ci) * H + yy) * W + xq) : 0.f;
+        }
+        __syncthreads();
+        const int px0 = wp * 16;                        // this warp's first pixel inside the segment
+        const uint32_t* dzp = dz + (static_cast<long long>(ny) * W + x0 + px0) * 32 + cp;
+        float win[CIN][3][3];
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {
-            const float* plane = x + (static_cast<long long>(n) * CIN + ci) * H * W;
+        for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int yy = y + t / 3 - 1, xq = xx + t % 3 - 1;
-                const float v = (yy >= 0 && yy < H && xq >= 0 && xq < W) ? __ldg(plane + static_cast<long long>(yy) * W + xq) : 0.f;
-                acc[0][ci * 9 + t] = fmaf(g.x, v, acc[0][ci * 9 + t]);
-                acc[1][ci * 9 + t] = fmaf(g.y, v, acc[1][ci * 9 + t]);
+            for (int r = 0; r < 3; ++r) {
+                win[ci][r][1] = xs[ci][r][px0];
+                win[ci][r][2] = xs[ci][r][px0 + 1];
+            }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    win[ci][r][0] = win[ci][r][1];
+                    win[ci][r][1] = win[ci][r][2];
+                    win[ci][r][2] = xs[ci][r][px0 + j + 2];
+                }
+            if (x0 + px0 + j < W) {                     // warp-uniform
+                const float2 g = unpack2(__ldg(dzp + j * 32));
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const float v = win[ci][t / 3][t % 3];
+                        acc[0][ci * 9 + t] = fmaf(g.x, v, acc[0][ci * 9 + t]);
+                        acc[1][ci * 9 + t] = fmaf(g.y, v, acc[1][ci * 9 + t]);
+                    }
             }
         }
     }
+    __syncthreads();
 #pragma unroll
-    for (int k = 0; k < K; ++k) {   // 8-way contention at most (the 8 pixel lanes)
+    for (int k = 0; k < K; ++k) {   // 8-way contention at most (the 8 warps)
         atomicAdd(&part[(2 * cp) * K + k], acc[0][k]);
         atomicAdd(&part[(2 * cp + 1) * K + k], acc[1][k]);
     }
@@ -485,20 +557,32 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     }
 }
 
-// w fp32 [co][ci][3][3] -> fwd bf16 [co][tap*ci_tot + ci] and bwd bf16 [ci][(8-tap)*co_tot... ] (data-gradient weights:
-// dX = conv3x3(dz, Wb) with Wb[ci][tap'][co] = w[co][ci][8 - tap'])
+// w fp32 [co][ci][3][3] -> fwd bf16 [co][tap*ci_tot + ci] and bwd bf16 [ci][(8-tap)*co_tot + co] (data-gradient weights:
+// dX = conv3x3(dz, Wb) with Wb[ci][tap'][co] = w[co][ci][8 - tap']). A thread owns the nine taps of one (co, ci) pair
+// (36 contiguous bytes); blockIdx.y picks the output: 0 walks pairs with ci fastest (coalesced fwd rows), 1 walks them
+// with co fastest (coalesced bwd rows).
 __global__ void __launch_bounds__(256)
 pack_conv_kernel(const float* __restrict__ w, int co, int ci, __nv_bfloat16* __restrict__ fwd,
                  __nv_bfloat16* __restrict__ bwd) {
-    const long long total = static_cast<long long>(co) * ci * 9;
+    const bool backward = blockIdx.y == 1;
+    __nv_bfloat16* out = backward ? bwd : fwd;
+    if (!out) return;
+    const long long total = static_cast<long long>(co) * ci;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int t = static_cast<int>(i % 9);
-        const int c = static_cast<int>((i / 9) % ci);
-        const int o = static_cast<int>(i / (9LL * ci));
-        const __nv_bfloat16 v = __float2bfloat16(w[i]);
-        if (fwd) fwd[(static_cast<long long>(o) * 9 + t) * ci + c] = v;
-        if (bwd) bwd[(static_cast<long long>(c) * 9 + (8 - t)) * co + o] = v;
+        const int o = static_cast<int>(backward ? i % co : i / ci);
+        const int c = static_cast<int>(backward ? i / co : i % ci);
+        const float* src = w + (static_cast<long long>(o) * ci + c) * 9;
+        float v[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] = __ldg(src + t);
+        if (backward) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) out[(static_cast<long long>(c) * 9 + (8 - t)) * co + o] = __float2bfloat16(v[t]);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) out[(static_cast<long long>(o) * 9 + t) * ci + c] = __float2bfloat16(v[t]);
+        }
     }
 }
 
@@ -548,7 +632,14 @@ const char* bn_apply_relu_launch(const void* z, long long P, int C, const float*
 const char* head_forward_launch(const void* a, int N, long long HW, const float* w, const float* b, int ncls, float* y,
                                 cudaStream_t st) {
     FI_REQUIRE(a && w && b && y && ncls >= 1 && ncls <= 4 && N > 0 && HW > 0, "head_forward: bad arguments");
-    head_forward_kernel<<<blocks_for(N * HW, 256), 256, 0, st>>>(static_cast<const uint4*>(a), N * HW, HW, w, b, ncls, y);
+    const int grid = blocks_for(N * HW * 8, 256 * 2, 148 * 8);
+    const uint4* ap = static_cast<const uint4*>(a);
+    switch (ncls) {
+        case 1: head_forward_kernel<1><<<grid, 256, 0, st>>>(ap, N * HW, HW, w, b, y); break;
+        case 2: head_forward_kernel<2><<<grid, 256, 0, st>>>(ap, N * HW, HW, w, b, y); break;
+        case 3: head_forward_kernel<3><<<grid, 256, 0, st>>>(ap, N * HW, HW, w, b, y); break;
+        default: head_forward_kernel<4><<<grid, 256, 0, st>>>(ap, N * HW, HW, w, b, y); break;
+    }
     return last_error();
 }
 const char* mse_launch(const float* y, const float* t, long long n, float* loss, float* dy, cudaStream_t st) {
@@ -559,8 +650,15 @@ const char* mse_launch(const float* y, const float* t, long long n, float* loss,
 const char* head_backward_launch(const void* a, const float* dy, int N, long long HW, const float* w, int ncls, void* da,
                                  float* dw, float* db, cudaStream_t st) {
     FI_REQUIRE(a && dy && w && da && dw && db && ncls >= 1 && ncls <= 4, "head_backward: bad arguments");
-    head_backward_kernel<<<blocks_for(N * HW * 8, 256, 148 * 4), 256, 0, st>>>(
-        static_cast<const uint4*>(a), dy, N * HW, HW, w, ncls, static_cast<uint4*>(da), dw, db);
+    const int grid = blocks_for(N * HW * 8, 256, 148 * 8);
+    const uint4* ap = static_cast<const uint4*>(a);
+    uint4* dap = static_cast<uint4*>(da);
+    switch (ncls) {
+        case 1: head_backward_kernel<1><<<grid, 256, 0, st>>>(ap, dy, N * HW, HW, w, dap, dw, db); break;
+        case 2: head_backward_kernel<2><<<grid, 256, 0, st>>>(ap, dy, N * HW, HW, w, dap, dw, db); break;
+        case 3: head_backward_kernel<3><<<grid, 256, 0, st>>>(ap, dy, N * HW, HW, w, dap, dw, db); break;
+        default: head_backward_kernel<4><<<grid, 256, 0, st>>>(ap, dy, N * HW, HW, w, dap, dw, db); break;
+    }
     return last_error();
 }
 const char* bn_relu_bwd_reduce_launch(const void* dA, const void* a, const void* z, long long P, int C, const float* mean,
@@ -597,7 +695,7 @@ const char* upsample2x_bwd_launch(const void* d_up, void* d_lo, int N, int h, in
 }
 const char* stem_wgrad_launch(const void* dz, const float* x, int N, int H, int W, int cin, float* dW, cudaStream_t st) {
     FI_REQUIRE(dz && x && dW && cin >= 1 && cin <= 6 && static_cast<long long>(N) * H * W < (1LL << 31), "stem_wgrad: bad arguments");
-    const int grid = blocks_for(static_cast<long long>(N) * H * W, 8 * 16, 148 * 4);
+    const int grid = blocks_for(static_cast<long long>(N) * H * ((W + STEM_WG_TILE - 1) / STEM_WG_TILE), 2, 148 * 4);
     const uint32_t* g = static_cast<const uint32_t*>(dz);
     switch (cin) {
         case 1: stem_wgrad_kernel<1><<<grid, 256, 0, st>>>(g, x, N, H, W, dW); break;
@@ -624,7 +722,7 @@ const char* adam_launch(float* p, const float* g, float* m, float* v, long long 
 }
 const char* pack_conv_launch(const float* w, int co, int ci, void* fwd, void* bwd, cudaStream_t st) {
     FI_REQUIRE(w && (fwd || bwd) && co > 0 && ci > 0, "pack_conv: bad arguments");
-    pack_conv_kernel<<<blocks_for(static_cast<long long>(co) * ci * 9, 256), 256, 0, st>>>(
+    pack_conv_kernel<<<dim3(blocks_for(static_cast<long long>(co) * ci, 256), 2), 256, 0, st>>>(
         w, co, ci, static_cast<__nv_bfloat16*>(fwd), static_cast<__nv_bfloat16*>(bwd));
     return last_error();
 }

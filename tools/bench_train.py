@@ -78,7 +78,14 @@ def main():
     model = FrameInterpolationUNet(bilinear=True).to(dev).train()
     step = TrainStep(model, lr=1e-4, criterion=CombinedLoss() if a.criterion == "combined" else None)
     ms, loss = timed(step, (f0, f1, gt), a.steps, a.warmup)
-    rows.append({"arm": "b200_train_step", "ms_per_step": ms, "samples_per_s": world * a.batch * 1e3 / ms, "loss": loss})
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step(f0, f1, gt)                      # host time to enqueue one step (GPU idle at the start)
+    host_ms = (time.perf_counter() - t0) * 1e3
+    torch.cuda.synchronize()
+    rows.append({"arm": "b200_train_step", "ms_per_step": ms, "samples_per_s": world * a.batch * 1e3 / ms, "loss": loss,
+                 "host_enqueue_ms": host_ms})
     if not a.skip_torch and world == 1:
         for name, amp, tf32 in (("torch_eager_fp32", False, False), ("torch_eager_tf32", False, True),
                                 ("torch_eager_bf16_autocast", True, True)):
