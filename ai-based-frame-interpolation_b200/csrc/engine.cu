@@ -1138,8 +1138,11 @@ int fiUnpackConvGrad(const float* dW, int cout, int cin, float* grad, void* stre
     TRAIN_CALL(fi::unpack_conv_grad_launch(dW, cout, cin, grad, ST));
 }
 int fiAdamStep(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-               int step, void* stream) {
-    TRAIN_CALL(fi::adam_launch(p, g, m, v, n, lr, beta1, beta2, eps, step, ST));
+               int step, const float* hyper_dev, void* stream) {
+    TRAIN_CALL(fi::adam_launch(p, g, m, v, n, lr, beta1, beta2, eps, step, hyper_dev, ST));
+}
+int fiStemPackWeightsDevice(const float* w_dev, int cin, void* packed_dev, void* stream) {
+    TRAIN_CALL(fi::stem_pack_device_launch(w_dev, cin, packed_dev, ST));
 }
 int fiPackConvWeights(const float* w, int cout, int cin, void* fwd, void* bwd, void* stream) {
     TRAIN_CALL(fi::pack_conv_launch(w, cout, cin, fwd, bwd, ST));

@@ -3,6 +3,7 @@
 // statistics / weight gradients / optimizer state are fp32. The conv forward and the data gradient (a conv with the
 // flipped, transposed weights) reuse conv_gemm*.cu / conv_halo*.cu; the weight gradient is wgrad_gemm.cu.
 #include "ptx.cuh"
+#include "aux_kernels.cuh"
 #include "train_kernels.cuh"
 
 namespace fi {
@@ -476,6 +477,12 @@ stem_wgrad_kernel(const uint32_t* __restrict__ dz, const float* __restrict__ x, 
         const int ny = tile / tiles_per_row;
         const int y = ny % H, n = ny / H;
         const int x0 = tr * STEM_WG_TILE;
+        // this warp's 16 dz values first: all loads of the segment are in flight while the window is staged
+        const int px0 = wp * 16;                        // this warp's first pixel inside the segment
+        const uint32_t* dzp = dz + (static_cast<long long>(ny) * W + x0 + px0) * 32 + cp;
+        uint32_t gz[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) gz[j] = x0 + px0 + j < W ? __ldg(dzp + j * 32) : 0u;   // bf16 zeros past the row end
         __syncthreads();   // the previous segment's readers are done (and `part` is zeroed on the first pass)
         for (int i = threadIdx.x; i < CIN * 3 * XS; i += 256) {
             const int c = i % XS;
@@ -485,8 +492,6 @@ stem_wgrad_kernel(const uint32_t* __restrict__ dz, const float* __restrict__ x, 
                                     ? __ldg(x + ((static_cast<long long>(n) * CIN + ci) * H + yy) * W + xq) : 0.f;
         }
         __syncthreads();
-        const int px0 = wp * 16;                        // this warp's first pixel inside the segment
-        const uint32_t* dzp = dz + (static_cast<long long>(ny) * W + x0 + px0) * 32 + cp;
         float win[CIN][3][3];
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci)
@@ -505,17 +510,15 @@ stem_wgrad_kernel(const uint32_t* __restrict__ dz, const float* __restrict__ x, 
                     win[ci][r][1] = win[ci][r][2];
                     win[ci][r][2] = xs[ci][r][px0 + j + 2];
                 }
-            if (x0 + px0 + j < W) {                     // warp-uniform
-                const float2 g = unpack2(__ldg(dzp + j * 32));
+            const float2 g = unpack2(gz[j]);
 #pragma unroll
-                for (int ci = 0; ci < CIN; ++ci)
+            for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        const float v = win[ci][t / 3][t % 3];
-                        acc[0][ci * 9 + t] = fmaf(g.x, v, acc[0][ci * 9 + t]);
-                        acc[1][ci * 9 + t] = fmaf(g.y, v, acc[1][ci * 9 + t]);
-                    }
-            }
+                for (int t = 0; t < 9; ++t) {
+                    const float v = win[ci][t / 3][t % 3];
+                    acc[0][ci * 9 + t] = fmaf(g.x, v, acc[0][ci * 9 + t]);
+                    acc[1][ci * 9 + t] = fmaf(g.y, v, acc[1][ci * 9 + t]);
+                }
         }
     }
     __syncthreads();
@@ -543,9 +546,16 @@ unpack_conv_grad_kernel(const float* __restrict__ dW, long long n, float* __rest
 
 // ------------------------------------------------------------------------------------------------ optimizer / packing
 // torch.optim.Adam defaults (reference model/train.py:160): p -= lr * mhat / (sqrt(vhat) + eps)
+// hyper (optional, device): {lr, step} read at run time, so a captured CUDA graph of the step can be replayed while
+// the learning-rate schedule and the step count advance.
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-            float lr, float b1, float b2, float eps, float bc1, float bc2) {
+            float lr, float b1, float b2, float eps, float bc1, float bc2, const float* __restrict__ hyper) {
+    if (hyper) {
+        lr = hyper[0];
+        bc1 = 1.f - powf(b1, hyper[1]);
+        bc2 = 1.f - powf(b2, hyper[1]);
+    }
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const float gi = g[i];
@@ -555,6 +565,23 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
         v[i] = vi;
         p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
     }
+}
+
+// Device twin of stem_pack_weights (stem_mma.cu): fp32 [64][cin][3][3] -> bf16 [64][kp] = [w_hi | w_lo | w_hi | 0]
+__global__ void __launch_bounds__(256)
+stem_pack_kernel(const float* __restrict__ w, int cin, int kp, __nv_bfloat16* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 64 * kp) return;
+    const int co = i / kp, k = i - co * kp, kt = 9 * cin;
+    const int seg = k / kt, idx = k - seg * kt;
+    __nv_bfloat16 r = __float2bfloat16(0.f);
+    if (seg < 3) {
+        const int tap = idx / cin, c = idx - tap * cin;
+        const float v = w[(co * cin + c) * 9 + tap];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        r = seg == 1 ? __float2bfloat16_rn(v - __bfloat162float(h)) : h;
+    }
+    out[i] = r;
 }
 
 // w fp32 [co][ci][3][3] -> fwd bf16 [co][tap*ci_tot + ci] and bwd bf16 [ci][(8-tap)*co_tot + co] (data-gradient weights:
@@ -714,10 +741,16 @@ const char* unpack_conv_grad_launch(const float* dW, int cout, int cin, float* g
     return last_error();
 }
 const char* adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                        int step, cudaStream_t st) {
-    FI_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adam: bad arguments");
+                        int step, const float* hyper, cudaStream_t st) {
+    FI_REQUIRE(p && g && m && v && n > 0 && (step >= 1 || hyper), "adam: bad arguments");
     adam_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, 1.f - powf(b1, static_cast<float>(step)),
-                                                   1.f - powf(b2, static_cast<float>(step)));
+                                                   1.f - powf(b2, static_cast<float>(step)), hyper);
+    return last_error();
+}
+const char* stem_pack_device_launch(const float* w, int cin, void* out, cudaStream_t st) {
+    FI_REQUIRE(w && out && cin >= 1 && cin <= 8, "stem_pack: bad arguments");
+    const int kp = stem_packed_k(cin);
+    stem_pack_kernel<<<(64 * kp + 255) / 256, 256, 0, st>>>(w, cin, kp, static_cast<__nv_bfloat16*>(out));
     return last_error();
 }
 const char* pack_conv_launch(const float* w, int co, int ci, void* fwd, void* bwd, cudaStream_t st) {

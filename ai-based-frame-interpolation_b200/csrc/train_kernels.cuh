@@ -29,7 +29,8 @@ const char* upsample2x_bwd_launch(const void* d_up, void* d_lo, int N, int h, in
 const char* stem_wgrad_launch(const void* dz, const float* x, int N, int H, int W, int cin, float* dW, cudaStream_t st);
 const char* unpack_conv_grad_launch(const float* dW, int cout, int cin, float* grad, cudaStream_t st);
 const char* adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                        int step, cudaStream_t st);
+                        int step, const float* hyper_dev, cudaStream_t st);
+const char* stem_pack_device_launch(const float* w_dev, int cin, void* out_dev, cudaStream_t st);
 const char* pack_conv_launch(const float* w, int co, int ci, void* fwd, void* bwd, cudaStream_t st);
 
 // wgrad_gemm.cu: dW[tap][co][ci] += sum_q dz[q][co] * x[q + tap][ci], x = channel concat of x0 | x1, all bf16 NHWC

@@ -96,7 +96,8 @@ _SIGNATURES = {
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fiUnpackConvGrad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fiAdamStep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
-                             C.c_float, C.c_int, C.c_void_p]),
+                             C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
+    "fiStemPackWeightsDevice": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "fiPackConvWeights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -57,8 +57,11 @@ class _Layer:
 class TrainStep:
     """loss = TrainStep(model, lr=1e-4)(frame1, frame2, target) — one optimisation step in place on `model`."""
 
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, criterion=None):
-        self.criterion = criterion
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, criterion=None, cuda_graph=False):
+        """cuda_graph=True: after two eager steps the whole step (about 200 launches) is captured once per input shape
+        and replayed; learning rate and step count reach the Adam kernel through a device buffer."""
+        self.criterion, self.cuda_graph = criterion, cuda_graph
+        self._graphs, self._eager_steps = {}, 0
         unet = model.unet if isinstance(model, FrameInterpolationUNet) else model
         if not isinstance(unet, UNet) or not unet.bilinear:
             raise E.FiError("the B200 training step covers the bilinear UNet (what reference train.py builds)")
@@ -97,6 +100,8 @@ class TrainStep:
             L.append(_Layer(f"up{i}.3", blk[3], blk[4], f"up{i}.0"))
         self.layers = L
         self.lib = E.lib()
+        self.hyper = torch.zeros(2, dtype=torch.float32, device=self.device)          # {lr, step} for the Adam kernel
+        self._hyper_host = torch.zeros(2, dtype=torch.float32).pin_memory()
 
     def state_dict(self):
         """torch.optim.Adam-shaped state: per-parameter step / exp_avg / exp_avg_sq plus the param group."""
@@ -162,6 +167,34 @@ class TrainStep:
     # ------------------------------------------------------------------------------------------------ one step
     @torch.no_grad()
     def __call__(self, frame1, frame2, target):
+        self.step_count += 1
+        self._hyper_host[0], self._hyper_host[1] = self.lr, float(self.step_count)
+        with torch.cuda.device(self.device):
+            self.hyper.copy_(self._hyper_host, non_blocking=True)
+            self._invalidate_inference_mirror()
+            if not self.cuda_graph:
+                return self._run(frame1, frame2, target)
+            key = (tuple(frame1.shape), None if frame2 is None else tuple(frame2.shape), tuple(target.shape))
+            entry = self._graphs.get(key)
+            if entry is None:
+                if self._eager_steps < 2:       # warm-up: kernel attributes, allocator pools, autograd of the criterion
+                    self._eager_steps += 1
+                    return self._run(frame1, frame2, target)
+                static = [frame1.clone(), None if frame2 is None else frame2.clone(), target.clone()]
+                graph = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(graph):
+                    loss = self._run(*static)
+                entry = self._graphs[key] = (graph, static, loss)
+            graph, static, loss = entry
+            static[0].copy_(frame1)
+            if frame2 is not None:
+                static[1].copy_(frame2)
+            static[2].copy_(target)
+            graph.replay()
+            return loss
+
+    def _run(self, frame1, frame2, target):
         lib, st = self.lib, E.current_stream
         x = torch.cat([frame1, frame2], 1).contiguous().float() if frame2 is not None else frame1.contiguous().float()
         n, cin0, h, w = x.shape
@@ -185,11 +218,9 @@ class TrainStep:
             for l in self.layers:
                 wt = l.conv.weight.detach()
                 if l.name == "inc.0":
-                    kp = lib.fiStemPackedK(l.cin)
-                    packed = torch.empty((64, kp), dtype=torch.int16)
-                    wc = wt.cpu().contiguous()
-                    E.check(lib.fiStemPackWeights(wc.data_ptr(), l.cin, packed.data_ptr()))
-                    packs[l.name] = (packed.to(self.device), None)
+                    packed = torch.empty((64, lib.fiStemPackedK(l.cin)), dtype=torch.bfloat16, device=self.device)
+                    E.check(lib.fiStemPackWeightsDevice(_ptr(wt), l.cin, _ptr(packed), st()))
+                    packs[l.name] = (packed, None)
                 else:
                     fwd = torch.empty((l.cout, 9 * l.cin), dtype=torch.bfloat16, device=self.device)
                     bwd = torch.empty((l.cin, 9 * l.cout), dtype=torch.bfloat16, device=self.device)
@@ -292,15 +323,16 @@ class TrainStep:
                 dist.all_reduce(self.flat_grad)
                 self.flat_grad.div_(dist.get_world_size())
             torch._foreach_add_([l.bn.num_batches_tracked for l in self.layers], 1)
-            self.step_count += 1
             E.check(lib.fiAdamStep(_ptr(self.flat_param), _ptr(self.flat_grad), _ptr(self.m), _ptr(self.v),
                                    self.flat_param.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
-                                   self.step_count, st()))
-            # the inference engine mirrors the parameters lazily: force a re-upload on the next eval forward
-            for mod in (self.model, self.unet):
-                mod.__dict__["_fi_print"] = None
+                                   self.step_count, _ptr(self.hyper), st()))
         self.last_output, self.last_activations = y, acts
         return loss
+
+    def _invalidate_inference_mirror(self):
+        # the inference engine mirrors the parameters lazily: force a re-upload on the next eval forward
+        for mod in (self.model, self.unet):
+            mod.__dict__["_fi_print"] = None
 
 
 # ---------------------------------------------------------------------------------------------------- reference surface

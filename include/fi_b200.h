@@ -225,9 +225,13 @@ int fiBnFinalize(const float* sum, const float* sumsq, int C, int64_t P, float e
                  float* running_var, void* stream);
 /* fiWgrad's dW[tap][cout][cin] added into the parameter-gradient layout grad[cout][cin][3][3]. */
 int fiUnpackConvGrad(const float* dW, int cout, int cin, float* grad, void* stream);
-/* torch.optim.Adam (model/train.py:160) on one flat fp32 parameter vector; step counts from 1. */
+/* torch.optim.Adam (model/train.py:160) on one flat fp32 parameter vector; step counts from 1. hyper_dev (optional,
+ * device float[2] = {lr, step}) overrides lr / step at run time so that a captured CUDA graph of the step can be
+ * replayed while the schedule advances. */
 int fiAdamStep(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-               int step, void* stream);
+               int step, const float* hyper_dev, void* stream);
+/* fiStemPackWeights on the device: w_dev fp32 [64][cin][3][3] -> packed_dev bf16 [64][fiStemPackedK(cin)]. */
+int fiStemPackWeightsDevice(const float* w_dev, int cin, void* packed_dev, void* stream);
 /* fp32 [cout][cin][3][3] -> bf16 forward rows [cout][tap*cin+ci] and data-gradient rows [cin][(8-tap)*cout+co]
  * (either may be NULL). */
 int fiPackConvWeights(const float* w, int cout, int cin, void* fwd, void* bwd, void* stream);

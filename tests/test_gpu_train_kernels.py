@@ -135,7 +135,7 @@ def test_adam_and_weight_packing(cuda_device):
         ref.grad = grad.clone()
         opt.step()
         gd = grad.to(cuda_device)
-        E.check(lib.fiAdamStep(p(pd), p(gd), p(m), p(v), 1000, 1e-2, 0.9, 0.999, 1e-8, step, st))
+        E.check(lib.fiAdamStep(p(pd), p(gd), p(m), p(v), 1000, 1e-2, 0.9, 0.999, 1e-8, step, None, st))
     assert torch.allclose(pd.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
     w = torch.randn(128, 64, 3, 3, generator=g)
     fwd = torch.empty((128, 9 * 64), dtype=torch.bfloat16, device=cuda_device)

@@ -178,3 +178,32 @@ def test_one_step_against_reference_golden(cuda_device, tag):
     for k in ("running_mean", "running_var"):
         assert np.allclose(sd[f"unet.inc.double_conv.1.{k}"].cpu().numpy(),
                            gold[f"{tag}_after:unet.inc.double_conv.1.{k}"], rtol=2e-2, atol=2e-3)
+
+
+@pytest.mark.parametrize("criterion", ["mse", "combined"])
+def test_cuda_graph_replay_matches_eager(cuda_device, criterion):
+    """cuda_graph=True captures the step after two eager ones; the replayed steps follow the eager trajectory, with the
+    learning rate and the step count (Adam bias correction) reaching the kernel through device memory."""
+    from model.train import CombinedLoss
+    crit = (lambda: CombinedLoss()) if criterion == "combined" else (lambda: None)
+    eager_model = make_model(7).to(cuda_device).train()
+    graph_model = copy.deepcopy(eager_model)
+    eager = TrainStep(eager_model, lr=1e-4, criterion=crit())
+    graphed = TrainStep(graph_model, lr=1e-4, criterion=crit(), cuda_graph=True)
+    g = torch.Generator().manual_seed(2)
+    le, lg = [], []
+    for it in range(6):
+        f1, f2 = torch.rand(2, 1, 32, 32, generator=g).to(cuda_device), torch.rand(2, 1, 32, 32, generator=g).to(cuda_device)
+        tgt = (f1 + f2) / 2
+        if it == 4:
+            eager.lr = graphed.lr = 5e-5     # schedule change after capture
+        le.append(eager(f1, f2, tgt).item())
+        lg.append(graphed(f1, f2, tgt).item())
+    assert len(graphed._graphs) == 1
+    assert np.allclose(le, lg, rtol=2e-2), (le, lg)
+    w_e = eager_model.unet.outc.conv.weight.detach().cpu()
+    w_g = graph_model.unet.outc.conv.weight.detach().cpu()
+    # fp32 atomics reorder sums between runs; where a gradient is ~0 Adam's first steps move by +-lr either way
+    assert torch.allclose(w_e, w_g, atol=6 * 2e-4) and (w_e - w_g).abs().mean() < 5e-5
+    assert eager.step_count == graphed.step_count == 6
+    assert int(graph_model.unet.inc.double_conv[1].num_batches_tracked) == 6

@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--criterion", default="mse")
     ap.add_argument("--skip-torch", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="capture the step in a CUDA graph")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -76,7 +77,7 @@ def main():
     rows = []
     torch.manual_seed(0)
     model = FrameInterpolationUNet(bilinear=True).to(dev).train()
-    step = TrainStep(model, lr=1e-4, criterion=CombinedLoss() if a.criterion == "combined" else None)
+    step = TrainStep(model, lr=1e-4, criterion=CombinedLoss() if a.criterion == "combined" else None, cuda_graph=a.graph)
     ms, loss = timed(step, (f0, f1, gt), a.steps, a.warmup)
     import time
     torch.cuda.synchronize()
@@ -84,7 +85,7 @@ def main():
     step(f0, f1, gt)                      # host time to enqueue one step (GPU idle at the start)
     host_ms = (time.perf_counter() - t0) * 1e3
     torch.cuda.synchronize()
-    rows.append({"arm": "b200_train_step", "ms_per_step": ms, "samples_per_s": world * a.batch * 1e3 / ms, "loss": loss,
+    rows.append({"arm": "b200_train_step" + ("_graph" if a.graph else ""), "ms_per_step": ms, "samples_per_s": world * a.batch * 1e3 / ms, "loss": loss,
                  "host_enqueue_ms": host_ms})
     if not a.skip_torch and world == 1:
         for name, amp, tf32 in (("torch_eager_fp32", False, False), ("torch_eager_tf32", False, True),
