@@ -1098,6 +1098,10 @@ int fiHeadForward(const void* a, int N, int64_t HW, const float* w, const float*
 int fiMseLossGrad(const float* y, const float* target, int64_t n, float* loss, float* dy, void* stream) {
     TRAIN_CALL(fi::mse_launch(y, target, n, loss, dy, ST));
 }
+int fiCombinedLossGrad(const float* y, const float* target, int planes, int H, int W, float mse_weight, float ssim_weight,
+                       float* loss, float* dy, void* stream) {
+    TRAIN_CALL(fi::combined_loss_launch(y, target, planes, H, W, mse_weight, ssim_weight, loss, dy, ST));
+}
 int fiHeadBackward(const void* a, const float* dy, int N, int64_t HW, const float* w, int n_classes, void* da, float* dw,
                    float* db, void* stream) {
     TRAIN_CALL(fi::head_backward_launch(a, dy, N, HW, w, n_classes, da, dw, db, ST));

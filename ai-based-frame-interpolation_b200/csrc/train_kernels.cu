@@ -199,6 +199,123 @@ mse_kernel(const float* __restrict__ y, const float* __restrict__ t, long long n
     if ((threadIdx.x & 31) == 0) atomicAdd(loss, part * inv_n);
 }
 
+__global__ void ssim_offset_kernel(float* loss, float v) { atomicAdd(loss, v); }
+
+// ------------------------------------------------------------------------------------------------ combined loss
+// loss = mse_w * mean((y-t)^2) + ssim_w * (1 - mean(SSIM(y, t)))  and its gradient w.r.t. y  (reference model/train.py:18-87:
+// 11x11 Gaussian window, sigma 1.5, zero-padded 'same' filtering per plane, C1 = 0.01^2, C2 = 0.03^2).
+// With mu1 = G*y, mu2 = G*t, E11 = G*y^2, E22 = G*t^2, E12 = G*(y t):
+//   S = A1 A2 / (B1 B2),  A1 = 2 mu1 mu2 + C1, A2 = 2 (E12 - mu1 mu2) + C2, B1 = mu1^2 + mu2^2 + C1,
+//                          B2 = (E11 - mu1^2) + (E22 - mu2^2) + C2
+//   dSum/dy = G*(dS/dmu1) + 2 y G*(dS/dE11) + t G*(dS/dE12)       (G symmetric, derivative maps zero outside the image)
+// One block owns a 32x32 tile of one plane: inputs with a 10-pixel halo, the five filtered maps and the three derivative
+// maps on the 5-pixel halo, all in shared memory, every filter separable (11 + 11 taps).
+constexpr int SL_TILE = 32, SL_R = 5;
+constexpr int SL_IN = SL_TILE + 4 * SL_R;    // 52: input region
+constexpr int SL_MID = SL_TILE + 2 * SL_R;   // 42: region of the SSIM map / derivative maps
+constexpr int SL_SMEM_FLOATS = 2 * SL_IN * SL_IN + 5 * SL_IN * SL_MID + 3 * SL_MID * SL_MID;
+struct GaussWindow { float g[2 * SL_R + 1]; };
+
+__global__ void __launch_bounds__(256)
+combined_loss_kernel(const float* __restrict__ y, const float* __restrict__ t, int H, int W, const GaussWindow gw,
+                     float mse_scale, float ssim_scale, float* __restrict__ loss, float* __restrict__ dy) {
+    extern __shared__ float sl[];
+    float* sx = sl;                             // [SL_IN][SL_IN]  prediction
+    float* sy = sx + SL_IN * SL_IN;             // [SL_IN][SL_IN]  target
+    float* hb = sy + SL_IN * SL_IN;             // [5][SL_IN][SL_MID] horizontally filtered x, y, xx, yy, xy
+    float* dm = hb + 5 * SL_IN * SL_MID;        // [3][SL_MID][SL_MID] dS/dmu1, dS/dE11, dS/dE12
+    float* hb2 = hb;                            // [3][SL_MID][SL_TILE] (reuses hb)
+    const int tiles_x = (W + SL_TILE - 1) / SL_TILE;
+    const int tx0 = (blockIdx.x % tiles_x) * SL_TILE, ty0 = (blockIdx.x / tiles_x) * SL_TILE;
+    const long long plane = static_cast<long long>(blockIdx.y) * H * W;
+    const float* yp = y + plane;
+    const float* tp = t + plane;
+    for (int i = threadIdx.x; i < SL_IN * SL_IN; i += 256) {
+        const int r = i / SL_IN, c = i - r * SL_IN;
+        const int gy = ty0 - 2 * SL_R + r, gx = tx0 - 2 * SL_R + c;
+        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        sx[i] = in ? __ldg(yp + static_cast<long long>(gy) * W + gx) : 0.f;
+        sy[i] = in ? __ldg(tp + static_cast<long long>(gy) * W + gx) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SL_IN * SL_MID; i += 256) {   // horizontal pass over all 52 rows, 42 columns
+        const int r = i / SL_MID, c = i - r * SL_MID;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+        for (int k = 0; k <= 2 * SL_R; ++k) {
+            const float xv = sx[r * SL_IN + c + k], yv = sy[r * SL_IN + c + k], w = gw.g[k];
+            a0 = fmaf(w, xv, a0); a1 = fmaf(w, yv, a1);
+            a2 = fmaf(w, xv * xv, a2); a3 = fmaf(w, yv * yv, a3); a4 = fmaf(w, xv * yv, a4);
+        }
+        hb[i] = a0; hb[SL_IN * SL_MID + i] = a1; hb[2 * SL_IN * SL_MID + i] = a2;
+        hb[3 * SL_IN * SL_MID + i] = a3; hb[4 * SL_IN * SL_MID + i] = a4;
+    }
+    __syncthreads();
+    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+    float ssim_part = 0.f, mse_part = 0.f;
+    for (int i = threadIdx.x; i < SL_MID * SL_MID; i += 256) {  // vertical pass -> SSIM and its partial derivatives
+        const int r = i / SL_MID, c = i - r * SL_MID;
+        const int gy = ty0 - SL_R + r, gx = tx0 - SL_R + c;
+        float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k <= 2 * SL_R; ++k) {
+            const float w = gw.g[k];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) m[q] = fmaf(w, hb[q * SL_IN * SL_MID + (r + k) * SL_MID + c], m[q]);
+        }
+        float d_mu = 0.f, d_11 = 0.f, d_12 = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            const float mu1 = m[0], mu2 = m[1];
+            const float A1 = 2.f * mu1 * mu2 + C1, A2 = 2.f * (m[4] - mu1 * mu2) + C2;
+            const float B1 = mu1 * mu1 + mu2 * mu2 + C1, B2 = (m[2] - mu1 * mu1) + (m[3] - mu2 * mu2) + C2;
+            const float inv = 1.f / (B1 * B2);
+            const float S = A1 * A2 * inv;
+            d_mu = 2.f * mu2 * (A2 - A1) * inv - 2.f * mu1 * S * (1.f / B1 - 1.f / B2);
+            d_11 = -S / B2;
+            d_12 = 2.f * A1 * inv;
+            if (r >= SL_R && r < SL_R + SL_TILE && c >= SL_R && c < SL_R + SL_TILE) ssim_part += S;   // own tile only
+        }
+        dm[i] = d_mu; dm[SL_MID * SL_MID + i] = d_11; dm[2 * SL_MID * SL_MID + i] = d_12;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SL_MID * SL_TILE; i += 256) {  // horizontal pass of the derivative maps
+        const int r = i / SL_TILE, c = i - r * SL_TILE;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int k = 0; k <= 2 * SL_R; ++k) {
+            const float w = gw.g[k];
+            a0 = fmaf(w, dm[r * SL_MID + c + k], a0);
+            a1 = fmaf(w, dm[SL_MID * SL_MID + r * SL_MID + c + k], a1);
+            a2 = fmaf(w, dm[2 * SL_MID * SL_MID + r * SL_MID + c + k], a2);
+        }
+        hb2[i] = a0; hb2[SL_MID * SL_TILE + i] = a1; hb2[2 * SL_MID * SL_TILE + i] = a2;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SL_TILE * SL_TILE; i += 256) {  // vertical pass -> gradient
+        const int r = i / SL_TILE, c = i - r * SL_TILE;
+        const int gy = ty0 + r, gx = tx0 + c;
+        if (gy >= H || gx >= W) continue;
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll
+        for (int k = 0; k <= 2 * SL_R; ++k) {
+            const float w = gw.g[k];
+            g0 = fmaf(w, hb2[(r + k) * SL_TILE + c], g0);
+            g1 = fmaf(w, hb2[SL_MID * SL_TILE + (r + k) * SL_TILE + c], g1);
+            g2 = fmaf(w, hb2[2 * SL_MID * SL_TILE + (r + k) * SL_TILE + c], g2);
+        }
+        const float xv = sx[(r + 2 * SL_R) * SL_IN + c + 2 * SL_R], yv = sy[(r + 2 * SL_R) * SL_IN + c + 2 * SL_R];
+        const float diff = xv - yv;
+        mse_part = fmaf(diff, diff, mse_part);
+        // d/dy [ mse_scale * sum diff^2 - ssim_scale * sum S ]
+        dy[plane + static_cast<long long>(gy) * W + gx] =
+            2.f * mse_scale * diff - ssim_scale * (g0 + 2.f * xv * g1 + yv * g2);
+    }
+    float part = mse_scale * mse_part - ssim_scale * ssim_part;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss, part);
+}
+
 // da[n][pix][c] = sum_k dy[n][k][pix] w[k][c];  dw[k][c] += sum dy * a;  db[k] += sum dy
 template <int NCLS>
 __global__ void __launch_bounds__(256)
@@ -672,6 +789,30 @@ const char* head_forward_launch(const void* a, int N, long long HW, const float*
 const char* mse_launch(const float* y, const float* t, long long n, float* loss, float* dy, cudaStream_t st) {
     FI_REQUIRE(y && t && loss && dy && n > 0, "mse: bad arguments");
     mse_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, t, n, 1.0f / static_cast<float>(n), loss, dy);
+    return last_error();
+}
+const char* combined_loss_launch(const float* y, const float* t, int planes, int H, int W, float mse_w, float ssim_w,
+                                 float* loss, float* dy, cudaStream_t st) {
+    FI_REQUIRE(y && t && loss && dy && planes > 0 && H > 0 && W > 0 && planes <= 65535, "combined_loss: bad arguments");
+    GaussWindow gw;   // the reference's window: exp(-(i-5)^2 / (2 * 1.5^2)) normalised in fp32
+    float sum = 0.f;
+    for (int i = 0; i <= 2 * SL_R; ++i) {
+        gw.g[i] = static_cast<float>(exp(-static_cast<double>((i - SL_R) * (i - SL_R)) / (2.0 * 1.5 * 1.5)));
+        sum += gw.g[i];
+    }
+    for (int i = 0; i <= 2 * SL_R; ++i) gw.g[i] /= sum;
+    static bool configured = false;
+    const int smem = SL_SMEM_FLOATS * static_cast<int>(sizeof(float));
+    if (!configured) {
+        if (cudaFuncSetAttribute(combined_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return "combined_loss: cudaFuncSetAttribute failed";
+        configured = true;
+    }
+    const float inv_n = 1.0f / (static_cast<float>(planes) * H * W);
+    const int tiles = ((W + SL_TILE - 1) / SL_TILE) * ((H + SL_TILE - 1) / SL_TILE);
+    // loss = mse_w * mean(diff^2) + ssim_w * (1 - mean(S)): the constant ssim_w is added by the first block's caller
+    ssim_offset_kernel<<<1, 1, 0, st>>>(loss, ssim_w);
+    combined_loss_kernel<<<dim3(tiles, planes), 256, smem, st>>>(y, t, H, W, gw, mse_w * inv_n, ssim_w * inv_n, loss, dy);
     return last_error();
 }
 const char* head_backward_launch(const void* a, const float* dy, int N, long long HW, const float* w, int ncls, void* da,

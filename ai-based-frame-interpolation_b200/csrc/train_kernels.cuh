@@ -16,6 +16,8 @@ const char* bn_apply_relu_launch(const void* z, long long P, int C, const float*
 const char* head_forward_launch(const void* a, int N, long long HW, const float* w, const float* b, int ncls, float* y,
                                 cudaStream_t st);
 const char* mse_launch(const float* y, const float* t, long long n, float* loss, float* dy, cudaStream_t st);
+const char* combined_loss_launch(const float* y, const float* t, int planes, int H, int W, float mse_w, float ssim_w,
+                                 float* loss, float* dy, cudaStream_t st);
 const char* head_backward_launch(const void* a, const float* dy, int N, long long HW, const float* w, int ncls, void* da,
                                  float* dw, float* db, cudaStream_t st);
 const char* bn_relu_bwd_reduce_launch(const void* dA, const void* a, const void* z, long long P, int C, const float* mean,

@@ -13,9 +13,9 @@ per-channel vector arithmetic of BatchNorm (C-sized tensors); every per-pixel FL
 Scope: FrameInterpolationUNet / UNet with bilinear=True (what the reference's train.py builds, model/train.py:299),
 H and W multiples of 16 (the reference trains at 256x256, model/train.py:138), bf16 activations and activation
 gradients, fp32 master parameters / gradients / Adam state. Loss: criterion=None is the fused MSE kernel (BASELINE
-config 5); any torch callable on the [N,1,H,W] fp32 network output (e.g. CombinedLoss below, the reference's
-0.5*MSE + 0.5*(1-SSIM), model/train.py:75-87) is differentiated by torch autograd on that one tensor and its
-gradient enters the library backward — the loss touches 1/1000 of the step's bytes.
+config 5); a CombinedLoss instance (the reference's 0.5*MSE + 0.5*(1-SSIM), model/train.py:75-87) is the fused
+fiCombinedLossGrad kernel; any other torch callable on the [N,1,H,W] fp32 network output is differentiated by torch
+autograd on that one tensor and its gradient enters the library backward.
 
 Also here, mirroring the reference file: SSIMLoss / CombinedLoss, FrameTripletDataset, train_model (same checkpoint
 keys, ReduceLROnPlateau(factor 0.5, patience 10) schedule) and main().
@@ -264,7 +264,13 @@ class TrainStep:
                 loss = torch.zeros(1, dtype=torch.float32, device=self.device)
                 dy = torch.empty_like(y)
                 E.check(lib.fiMseLossGrad(_ptr(y), _ptr(tgt), y.numel(), _ptr(loss), _ptr(dy), st()))
-            else:  # a torch loss on the network output: autograd on this one [N,ncls,H,W] tensor only
+            elif (isinstance(self.criterion, CombinedLoss) and self.criterion.ssim_loss.window_size == 11
+                  and self.criterion.ssim_loss.size_average):   # the reference's loss: one fused kernel
+                loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+                dy = torch.empty_like(y)
+                E.check(lib.fiCombinedLossGrad(_ptr(y), _ptr(tgt), n * ncls, h, w, float(self.criterion.mse_weight),
+                                               float(self.criterion.ssim_weight), _ptr(loss), _ptr(dy), st()))
+            else:  # any other torch loss on the network output: autograd on this one [N,ncls,H,W] tensor only
                 with torch.enable_grad():
                     y_req = y.detach().requires_grad_(True)
                     loss_t = self.criterion(y_req, tgt)

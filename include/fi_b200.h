@@ -195,6 +195,11 @@ int fiBnStats(const void* z, int64_t P, int C, float* sum, float* sumsq, void* s
 int fiBnApplyRelu(const void* z, int64_t P, int C, const float* scale, const float* shift, void* a, void* stream);
 /* OutConv (model/unet.py:57-63) on bf16 [N*HW][64] -> fp32 NCHW [N,n_classes,H,W]. */
 int fiHeadForward(const void* a, int N, int64_t HW, const float* w, const float* b, int n_classes, float* y, void* stream);
+/* CombinedLoss (model/train.py:75-87): loss += mse_weight * mean((y-t)^2) + ssim_weight * (1 - mean SSIM(y, t)) with
+ * the 11x11 Gaussian-window SSIM of SSIMLoss (model/train.py:18-73), and dy = d loss / d y. y, target, dy: fp32
+ * [planes][H][W] (planes = N * n_classes; each plane is filtered on its own, like the grouped conv2d). */
+int fiCombinedLossGrad(const float* y, const float* target, int planes, int H, int W, float mse_weight, float ssim_weight,
+                       float* loss, float* dy, void* stream);
 /* nn.MSELoss (model/train.py:81): loss += mean((y-t)^2); dy = 2(y-t)/n. */
 int fiMseLossGrad(const float* y, const float* target, int64_t n, float* loss, float* dy, void* stream);
 int fiHeadBackward(const void* a, const float* dy, int N, int64_t HW, const float* w, int n_classes, void* da, float* dw,

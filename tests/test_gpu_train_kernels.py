@@ -221,3 +221,25 @@ def test_unpack_conv_grad(cuda_device):
     E.check(lib.fiUnpackConvGrad(p(dW), 128, 64, p(grad), st))
     torch.cuda.synchronize()
     assert torch.allclose(grad, want, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("planes,h,w,mw,sw", [(2, 40, 56, 0.5, 0.5), (3, 32, 32, 0.3, 0.7), (1, 7, 9, 1.0, 1.0),
+                                               (4, 70, 33, 0.0, 1.0)])
+def test_combined_loss_kernel_matches_torch(cuda_device, planes, h, w, mw, sw):
+    """fiCombinedLossGrad against autograd of the CombinedLoss mirror (itself pinned to the reference by
+    tests/test_train_loss.py)."""
+    from model.train import CombinedLoss
+    lib, st = E.lib(), E.current_stream()
+    g = torch.Generator().manual_seed(planes * 100 + h)
+    pred = torch.rand(planes, 1, h, w, generator=g).requires_grad_(True)
+    target = (pred.detach() + 0.15 * torch.randn(planes, 1, h, w, generator=g)).clamp(0, 1)
+    loss_ref = CombinedLoss(mw, sw)(pred, target)
+    loss_ref.backward()
+    yd, td = pred.detach().to(cuda_device), target.to(cuda_device)
+    loss = torch.zeros(1, device=cuda_device)
+    dy = torch.full_like(yd, float("nan"))
+    E.check(lib.fiCombinedLossGrad(p(yd), p(td), planes, h, w, mw, sw, p(loss), p(dy), st))
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) < 2e-6 + 1e-5 * abs(loss_ref.item())
+    err = (dy.cpu() - pred.grad).abs().max().item()
+    assert err <= 2e-3 * pred.grad.abs().max().item() + 1e-9, (err, pred.grad.abs().max().item())

@@ -20,7 +20,7 @@ from model.train import CombinedLoss, TrainStep  # noqa: E402
 from model.unet import FrameInterpolationUNet  # noqa: E402
 
 
-def torch_step_factory(model, lr, amp):
+def torch_step_factory(model, lr, amp, criterion):
     from test_gpu_train_step import ref_forward_train
     opt = torch.optim.Adam(model.parameters(), lr=lr)
 
@@ -28,7 +28,7 @@ def torch_step_factory(model, lr, amp):
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
             y = ref_forward_train(model, torch.cat([f0, f1], 1))
-        loss = F.mse_loss(y.float(), gt)
+        loss = criterion(y.float(), gt)
         loss.backward()
         opt.step()
         return loss.detach()
@@ -95,7 +95,8 @@ def main():
             torch.backends.cuda.matmul.allow_tf32 = tf32
             torch.manual_seed(0)
             m = FrameInterpolationUNet(bilinear=True).to(dev).train()
-            ms, loss = timed(torch_step_factory(m, 1e-4, amp), (f0, f1, gt), a.steps, a.warmup)
+            crit = CombinedLoss().to(dev) if a.criterion == "combined" else F.mse_loss
+            ms, loss = timed(torch_step_factory(m, 1e-4, amp, crit), (f0, f1, gt), a.steps, a.warmup)
             rows.append({"arm": name, "ms_per_step": ms, "samples_per_s": a.batch * 1e3 / ms, "loss": loss})
     if local == 0:
         for r in rows:
