@@ -59,8 +59,9 @@ class TrainStep:
 
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, criterion=None, cuda_graph=False,
                  overlap_wgrad=True):
-        """cuda_graph=True: after two eager steps the whole step (about 200 launches) is captured once per input shape
-        and replayed; learning rate and step count reach the Adam kernel through a device buffer.
+        """cuda_graph=True: after two eager steps the step is captured once per input shape
+        (forward + backward, about 200 launches; the all-reduce and the Adam launch stay eager) and replayed; learning
+        rate and step count reach the Adam kernel through a device buffer.
         overlap_wgrad=True: weight gradients run on a second stream, beside the BatchNorm-backward / data-gradient
         chain of the layers below (tensor-core-bound and HBM-bound kernels share the SMs)."""
         self.criterion, self.cuda_graph, self.overlap_wgrad = criterion, cuda_graph, overlap_wgrad
@@ -177,13 +178,17 @@ class TrainStep:
             self.hyper.copy_(self._hyper_host, non_blocking=True)
             self._invalidate_inference_mirror()
             if not self.cuda_graph:
-                return self._run(frame1, frame2, target)
+                loss = self._run(frame1, frame2, target)
+                self._finish()
+                return loss
             key = (tuple(frame1.shape), None if frame2 is None else tuple(frame2.shape), tuple(target.shape))
             entry = self._graphs.get(key)
             if entry is None:
                 if self._eager_steps < 2:       # warm-up: kernel attributes, allocator pools, autograd of the criterion
                     self._eager_steps += 1
-                    return self._run(frame1, frame2, target)
+                    loss = self._run(frame1, frame2, target)
+                    self._finish()
+                    return loss
                 static = [frame1.clone(), None if frame2 is None else frame2.clone(), target.clone()]
                 graph = torch.cuda.CUDAGraph()
                 torch.cuda.synchronize()
@@ -196,6 +201,7 @@ class TrainStep:
                 static[1].copy_(frame2)
             static[2].copy_(target)
             graph.replay()
+            self._finish()
             return loss
 
     def _run(self, frame1, frame2, target):
@@ -338,16 +344,19 @@ class TrainStep:
                     grads[l.src] = d_src
             if self.overlap_wgrad:
                 main_stream.wait_stream(self._side)
-            # ---- gradient all-reduce across data-parallel replicas (NCCL over NVLink), then Adam
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                dist.all_reduce(self.flat_grad)
-                self.flat_grad.div_(dist.get_world_size())
-            torch._foreach_add_([l.bn.num_batches_tracked for l in self.layers], 1)
-            E.check(lib.fiAdamStep(_ptr(self.flat_param), _ptr(self.flat_grad), _ptr(self.m), _ptr(self.v),
-                                   self.flat_param.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
-                                   self.step_count, _ptr(self.hyper), st()))
         self.last_output, self.last_activations = y, acts
         return loss
+
+    def _finish(self):
+        """Gradient all-reduce across data-parallel replicas (NCCL over NVLink), BatchNorm counters, Adam. Kept outside
+        the captured graph: collectives are enqueued eagerly on every rank."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat_grad)
+            self.flat_grad.div_(dist.get_world_size())
+        torch._foreach_add_([l.bn.num_batches_tracked for l in self.layers], 1)
+        E.check(self.lib.fiAdamStep(_ptr(self.flat_param), _ptr(self.flat_grad), _ptr(self.m), _ptr(self.v),
+                                    self.flat_param.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                    self.step_count, _ptr(self.hyper), E.current_stream()))
 
     def _invalidate_inference_mirror(self):
         # the inference engine mirrors the parameters lazily: force a re-upload on the next eval forward
