@@ -1106,14 +1106,14 @@ int fiHeadBackward(const void* a, const float* dy, int N, int64_t HW, const floa
                    float* db, void* stream) {
     TRAIN_CALL(fi::head_backward_launch(a, dy, N, HW, w, n_classes, da, dw, db, ST));
 }
-int fiBnReluBackwardReduce(const void* dA, const void* a, const void* z, int64_t P, int C, const float* mean,
-                           const float* rstd, float* dbeta, float* dgamma, void* stream) {
-    TRAIN_CALL(fi::bn_relu_bwd_reduce_launch(dA, a, z, P, C, mean, rstd, dbeta, dgamma, ST));
+int fiBnReluBackwardReduce(const void* dA, const void* z, int64_t P, int C, const float* mean, const float* rstd,
+                           const float* scale, const float* shift, float* dbeta, float* dgamma, void* stream) {
+    TRAIN_CALL(fi::bn_relu_bwd_reduce_launch(dA, z, P, C, mean, rstd, scale, shift, dbeta, dgamma, ST));
 }
-int fiBnReluBackwardApply(const void* dA, const void* a, const void* z, int64_t P, int C, const float* mean,
-                          const float* rstd, const float* gamma, const float* dbeta, const float* dgamma, void* dz,
+int fiBnReluBackwardApply(const void* dA, const void* z, int64_t P, int C, const float* mean, const float* rstd,
+                          const float* gamma, const float* beta, const float* dbeta, const float* dgamma, void* dz,
                           void* stream) {
-    TRAIN_CALL(fi::bn_relu_bwd_apply_launch(dA, a, z, P, C, mean, rstd, gamma, dbeta, dgamma, dz, ST));
+    TRAIN_CALL(fi::bn_relu_bwd_apply_launch(dA, z, P, C, mean, rstd, gamma, beta, dbeta, dgamma, dz, ST));
 }
 int fiMaxPoolBackwardAdd(const void* a_full, const void* a_pool, const void* d_pool, const void* d_skip, void* d_full,
                          int N, int H, int W, int C, void* stream) {

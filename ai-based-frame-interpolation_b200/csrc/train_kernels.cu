@@ -57,7 +57,7 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bn_stats_kernel(const uint4* __restrict__ z, long long P, int c8, float* __restrict__ sum, float* __restrict__ sumsq) {
     __shared__ float sh[2][RED_MAX_C];
     const int C = 8 * c8;
@@ -376,37 +376,41 @@ head_backward_kernel(const uint4* __restrict__ a, const float* __restrict__ dy, 
 
 // ------------------------------------------------------------------------------------------------ BN + ReLU backward
 // dy = dA * (a > 0); dbeta[c] += sum dy; dgamma[c] += sum dy * zhat, zhat = (z - mean) * rstd.   (same walk as bn_stats)
-__global__ void __launch_bounds__(256)
-bn_relu_bwd_reduce_kernel(const uint4* __restrict__ dA, const uint4* __restrict__ a, const uint4* __restrict__ z,
-                          long long P, int c8, const float* __restrict__ mean, const float* __restrict__ rstd,
-                          float* __restrict__ dbeta, float* __restrict__ dgamma) {
+// The ReLU mask is recomputed from z with the forward's own expression (scale * z + shift > 0) instead of reading the
+// stored activation: one tensor less to stream in both backward kernels.
+__global__ void __launch_bounds__(256, 3)
+bn_relu_bwd_reduce_kernel(const uint4* __restrict__ dA, const uint4* __restrict__ z, long long P, int c8,
+                          const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
+                          const float* __restrict__ shift, float* __restrict__ dbeta, float* __restrict__ dgamma) {
     __shared__ float sh[2][RED_MAX_C];
     const int C = 8 * c8;
     for (int i = threadIdx.x; i < C; i += 256) sh[0][i] = sh[1][i] = 0.f;
     __syncthreads();
     bool any_smem = false;
     channel_reduce_walk(P, c8, [&](int g, long long p, long long step, bool via_smem) {
-        float m[8], b[8], gsum[8];
+        float m[8], sc[8], sf[8], b[8], gsum[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { m[j] = mean[8 * g + j]; b[j] = gsum[j] = 0.f; }
-        auto add = [&](const uint4& dv, const uint4& av, const uint4& zv) {
-            float d[8], af[8], zf[8];
-            unpack8(dv, d); unpack8(av, af); unpack8(zv, zf);
+        for (int j = 0; j < 8; ++j) {
+            m[j] = mean[8 * g + j]; sc[j] = scale[8 * g + j]; sf[j] = shift[8 * g + j];
+            b[j] = gsum[j] = 0.f;
+        }
+        auto add = [&](const uint4& dv, const uint4& zv) {
+            float d[8], zf[8];
+            unpack8(dv, d); unpack8(zv, zf);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float dd = af[j] > 0.f ? d[j] : 0.f;
+                const float dd = fmaf(zf[j], sc[j], sf[j]) > 0.f ? d[j] : 0.f;
                 b[j] += dd;
                 gsum[j] = fmaf(dd, zf[j] - m[j], gsum[j]);
             }
         };
-        for (; p + step < P; p += 2 * step) {
-            const long long i0 = p * c8 + g, i1 = (p + step) * c8 + g;
-            const uint4 d0 = __ldg(dA + i0), a0 = __ldg(a + i0), z0 = __ldg(z + i0);
-            const uint4 d1 = __ldg(dA + i1), a1 = __ldg(a + i1), z1 = __ldg(z + i1);
-            add(d0, a0, z0);
-            add(d1, a1, z1);
+        for (; p + 2 * step < P; p += 3 * step) {
+            const long long i0 = p * c8 + g, i1 = (p + step) * c8 + g, i2 = (p + 2 * step) * c8 + g;
+            const uint4 d0 = __ldg(dA + i0), z0 = __ldg(z + i0), d1 = __ldg(dA + i1), z1 = __ldg(z + i1);
+            const uint4 d2 = __ldg(dA + i2), z2 = __ldg(z + i2);
+            add(d0, z0); add(d1, z1); add(d2, z2);
         }
-        if (p < P) { const long long i0 = p * c8 + g; add(__ldg(dA + i0), __ldg(a + i0), __ldg(z + i0)); }
+        for (; p < P; p += step) { const long long i0 = p * c8 + g; add(__ldg(dA + i0), __ldg(z + i0)); }
 #pragma unroll
         for (int j = 0; j < 8; ++j) gsum[j] *= rstd[8 * g + j];
         flush_group(sh[0], dbeta, g, b, via_smem);
@@ -421,15 +425,15 @@ bn_relu_bwd_reduce_kernel(const uint4* __restrict__ dA, const uint4* __restrict_
 
 // dz = gamma * rstd * (dy - dbeta/P - zhat * dgamma/P)
 __global__ void __launch_bounds__(256)
-bn_relu_bwd_apply_kernel(const uint4* __restrict__ dA, const uint4* __restrict__ a, const uint4* __restrict__ z,
-                         long long n8, int c8, float inv_p, const float* __restrict__ mean, const float* __restrict__ rstd,
-                         const float* __restrict__ gamma, const float* __restrict__ dbeta, const float* __restrict__ dgamma,
+bn_relu_bwd_apply_kernel(const uint4* __restrict__ dA, const uint4* __restrict__ z, long long n8, int c8, float inv_p,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, const float* __restrict__ dbeta, const float* __restrict__ dgamma,
                          uint4* __restrict__ dz) {
     // gridDim.x * 256 is a multiple of c8 (launcher): per-channel constants live in registers
     const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
     const int c = static_cast<int>(i0 % c8) * 8;
-    float k1[8], k2[8], k3[8], m[8];   // dz = k1 * (dy - k2 - (z - m) * k3)
+    float k1[8], k2[8], k3[8], m[8], sf[8];   // dz = k1 * (dy - k2 - (z - m) * k3); mask: k1 * z + sf > 0 (the forward's fma)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float r = rstd[c + j];
@@ -437,22 +441,24 @@ bn_relu_bwd_apply_kernel(const uint4* __restrict__ dA, const uint4* __restrict__
         k2[j] = dbeta[c + j] * inv_p;
         k3[j] = r * dgamma[c + j] * inv_p;
         m[j] = mean[c + j];
+        sf[j] = beta[c + j] - m[j] * k1[j];
     }
-    auto one = [&](long long i, const uint4& dv, const uint4& av, const uint4& zv) {
-        float d[8], af[8], zf[8], r[8];
-        unpack8(dv, d); unpack8(av, af); unpack8(zv, zf);
+    auto one = [&](long long i, const uint4& dv, const uint4& zv) {
+        float d[8], zf[8], r[8];
+        unpack8(dv, d); unpack8(zv, zf);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = k1[j] * ((af[j] > 0.f ? d[j] : 0.f) - k2[j] - (zf[j] - m[j]) * k3[j]);
+        for (int j = 0; j < 8; ++j)
+            r[j] = k1[j] * ((fmaf(zf[j], k1[j], sf[j]) > 0.f ? d[j] : 0.f) - k2[j] - (zf[j] - m[j]) * k3[j]);
         dz[i] = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
     };
     long long i = i0;
     for (; i + step < n8; i += 2 * step) {
-        const uint4 d0 = __ldg(dA + i), a0 = __ldg(a + i), z0 = __ldg(z + i);
-        const uint4 d1 = __ldg(dA + i + step), a1 = __ldg(a + i + step), z1 = __ldg(z + i + step);
-        one(i, d0, a0, z0);
-        one(i + step, d1, a1, z1);
+        const uint4 d0 = __ldg(dA + i), z0 = __ldg(z + i);
+        const uint4 d1 = __ldg(dA + i + step), z1 = __ldg(z + i + step);
+        one(i, d0, z0);
+        one(i + step, d1, z1);
     }
-    if (i < n8) one(i, __ldg(dA + i), __ldg(a + i), __ldg(z + i));
+    if (i < n8) one(i, __ldg(dA + i), __ldg(z + i));
 }
 
 // ------------------------------------------------------------------------------------------------ pool / upsample backward
@@ -736,9 +742,9 @@ pack_conv_kernel(const float* __restrict__ w, int co, int ci, __nv_bfloat16* __r
 
 namespace {
 // grid of a per-channel reduction: every block covers 256/c8 pixel lanes (or one when c8 does not divide 256)
-int reduce_blocks(long long P, int c8) {
+int reduce_blocks(long long P, int c8, int blocks_per_sm = 4) {
     const int rows_par = (c8 <= 256 && 256 % c8 == 0) ? 256 / c8 : 1;
-    return blocks_for(P, rows_par * 4, 148 * 4);
+    return blocks_for(P, rows_par * 4, 148 * blocks_per_sm);   // one resident wave
 }
 // grid of an elementwise per-channel kernel: gridDim * 256 must be a multiple of c8 so threads keep their channel group
 int apply_blocks(long long n8, int c8) {
@@ -829,22 +835,23 @@ const char* head_backward_launch(const void* a, const float* dy, int N, long lon
     }
     return last_error();
 }
-const char* bn_relu_bwd_reduce_launch(const void* dA, const void* a, const void* z, long long P, int C, const float* mean,
-                                      const float* rstd, float* dbeta, float* dgamma, cudaStream_t st) {
-    FI_REQUIRE(dA && a && z && mean && rstd && dbeta && dgamma && C % 8 == 0 && C <= RED_MAX_C, "bn_bwd_reduce: bad arguments");
-    bn_relu_bwd_reduce_kernel<<<reduce_blocks(P, C / 8), 256, 0, st>>>(
-        static_cast<const uint4*>(dA), static_cast<const uint4*>(a), static_cast<const uint4*>(z), P, C / 8, mean, rstd,
-        dbeta, dgamma);
+const char* bn_relu_bwd_reduce_launch(const void* dA, const void* z, long long P, int C, const float* mean,
+                                      const float* rstd, const float* scale, const float* shift, float* dbeta,
+                                      float* dgamma, cudaStream_t st) {
+    FI_REQUIRE(dA && z && mean && rstd && scale && shift && dbeta && dgamma && C % 8 == 0 && C <= RED_MAX_C,
+               "bn_bwd_reduce: bad arguments");
+    bn_relu_bwd_reduce_kernel<<<reduce_blocks(P, C / 8, 3), 256, 0, st>>>(
+        static_cast<const uint4*>(dA), static_cast<const uint4*>(z), P, C / 8, mean, rstd, scale, shift, dbeta, dgamma);
     return last_error();
 }
-const char* bn_relu_bwd_apply_launch(const void* dA, const void* a, const void* z, long long P, int C, const float* mean,
-                                     const float* rstd, const float* gamma, const float* dbeta, const float* dgamma,
-                                     void* dz, cudaStream_t st) {
-    FI_REQUIRE(dA && a && z && dz && C % 8 == 0, "bn_bwd_apply: bad arguments");
+const char* bn_relu_bwd_apply_launch(const void* dA, const void* z, long long P, int C, const float* mean,
+                                     const float* rstd, const float* gamma, const float* beta, const float* dbeta,
+                                     const float* dgamma, void* dz, cudaStream_t st) {
+    FI_REQUIRE(dA && z && dz && mean && rstd && gamma && beta && dbeta && dgamma && C % 8 == 0, "bn_bwd_apply: bad arguments");
     const long long n8 = P * (C / 8);
     bn_relu_bwd_apply_kernel<<<apply_blocks(n8, C / 8), 256, 0, st>>>(
-        static_cast<const uint4*>(dA), static_cast<const uint4*>(a), static_cast<const uint4*>(z), n8, C / 8,
-        1.0f / static_cast<float>(P), mean, rstd, gamma, dbeta, dgamma, static_cast<uint4*>(dz));
+        static_cast<const uint4*>(dA), static_cast<const uint4*>(z), n8, C / 8, 1.0f / static_cast<float>(P), mean, rstd,
+        gamma, beta, dbeta, dgamma, static_cast<uint4*>(dz));
     return last_error();
 }
 const char* maxpool_bwd_add_launch(const void* a_full, const void* a_pool, const void* d_pool, const void* d_skip,

@@ -20,11 +20,12 @@ const char* combined_loss_launch(const float* y, const float* t, int planes, int
                                  float* loss, float* dy, cudaStream_t st);
 const char* head_backward_launch(const void* a, const float* dy, int N, long long HW, const float* w, int ncls, void* da,
                                  float* dw, float* db, cudaStream_t st);
-const char* bn_relu_bwd_reduce_launch(const void* dA, const void* a, const void* z, long long P, int C, const float* mean,
-                                      const float* rstd, float* dbeta, float* dgamma, cudaStream_t st);
-const char* bn_relu_bwd_apply_launch(const void* dA, const void* a, const void* z, long long P, int C, const float* mean,
-                                     const float* rstd, const float* gamma, const float* dbeta, const float* dgamma,
-                                     void* dz, cudaStream_t st);
+const char* bn_relu_bwd_reduce_launch(const void* dA, const void* z, long long P, int C, const float* mean,
+                                      const float* rstd, const float* scale, const float* shift, float* dbeta,
+                                      float* dgamma, cudaStream_t st);
+const char* bn_relu_bwd_apply_launch(const void* dA, const void* z, long long P, int C, const float* mean,
+                                     const float* rstd, const float* gamma, const float* beta, const float* dbeta,
+                                     const float* dgamma, void* dz, cudaStream_t st);
 const char* maxpool_bwd_add_launch(const void* a_full, const void* a_pool, const void* d_pool, const void* d_skip,
                                    void* d_full, int N, int H, int W, int C, cudaStream_t st);
 const char* upsample2x_bwd_launch(const void* d_up, void* d_lo, int N, int h, int w, int C, cudaStream_t st);

@@ -155,7 +155,7 @@ class TrainStep:
         return z
 
     def _bn_forward(self, layer, z, work):
-        """Batch statistics -> a = relu(bn(z)); returns (a, mean, rstd) and updates the running statistics.
+        """Batch statistics -> a = relu(bn(z)); returns (a, work) and updates the running statistics.
         work: zeroed fp32 [6, C] scratch (sum, sumsq, mean, rstd, scale, shift)."""
         n, h, w, c = z.shape
         P = n * h * w
@@ -167,7 +167,7 @@ class TrainStep:
                                       _ptr(bn.running_mean), _ptr(bn.running_var), st))
         a = torch.empty_like(z)
         E.check(self.lib.fiBnApplyRelu(_ptr(z), P, c, _ptr(work[4]), _ptr(work[5]), _ptr(a), st))
-        return a, work[2], work[3]
+        return a, work
 
     # ------------------------------------------------------------------------------------------------ one step
     @torch.no_grad()
@@ -258,8 +258,7 @@ class TrainStep:
                         acts[l.src1] = up
                     z = self._conv(acts[l.src], packs[l.name][0], l.cout, acts.get(l.src1) if l.src1 else None)
                 zs[l.name] = z
-                acts[l.name], mean, rstd = self._bn_forward(l, z, bn_work[l.name])
-                stats[l.name] = (mean, rstd)
+                acts[l.name], stats[l.name] = self._bn_forward(l, z, bn_work[l.name])
             last = acts["up4.3"]
             hw_, hb = self.unet.outc.conv.weight.detach().reshape(-1, 64).contiguous(), self.unet.outc.conv.bias.detach()
             ncls = hw_.shape[0]
@@ -295,14 +294,14 @@ class TrainStep:
                 a, z = acts[l.name], zs[l.name]
                 ln, lh, lw, lc = z.shape
                 P = ln * lh * lw
-                mean, rstd = stats[l.name]
+                wk = stats[l.name]       # rows: sum, sumsq, mean, rstd, scale, shift
                 dA = grads.pop(l.name)
                 dbeta, dgamma = self.grad_view[l.bn.bias], self.grad_view[l.bn.weight]   # zeroed with flat_grad
-                E.check(lib.fiBnReluBackwardReduce(_ptr(dA), _ptr(a), _ptr(z), P, lc, _ptr(mean), _ptr(rstd), _ptr(dbeta),
-                                                   _ptr(dgamma), st()))
+                E.check(lib.fiBnReluBackwardReduce(_ptr(dA), _ptr(z), P, lc, _ptr(wk[2]), _ptr(wk[3]), _ptr(wk[4]),
+                                                   _ptr(wk[5]), _ptr(dbeta), _ptr(dgamma), st()))
                 dz = torch.empty_like(z)
-                E.check(lib.fiBnReluBackwardApply(_ptr(dA), _ptr(a), _ptr(z), P, lc, _ptr(mean), _ptr(rstd),
-                                                  _ptr(l.bn.weight), _ptr(dbeta), _ptr(dgamma), _ptr(dz), st()))
+                E.check(lib.fiBnReluBackwardApply(_ptr(dA), _ptr(z), P, lc, _ptr(wk[2]), _ptr(wk[3]), _ptr(l.bn.weight),
+                                                  _ptr(l.bn.bias), _ptr(dbeta), _ptr(dgamma), _ptr(dz), st()))
                 # weight gradient: on the side stream once dz exists
                 srcs = [] if l.name == "inc.0" else [acts[l.src]] + ([acts[l.src1]] if l.src1 else [])
                 wst = st

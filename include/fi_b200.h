@@ -204,12 +204,14 @@ int fiCombinedLossGrad(const float* y, const float* target, int planes, int H, i
 int fiMseLossGrad(const float* y, const float* target, int64_t n, float* loss, float* dy, void* stream);
 int fiHeadBackward(const void* a, const float* dy, int N, int64_t HW, const float* w, int n_classes, void* da, float* dw,
                    float* db, void* stream);
-/* ReLU + BatchNorm backward: dbeta += sum dy, dgamma += sum dy*zhat (dy = dA masked by a > 0); then
- * dz = gamma*rstd*(dy - dbeta/P - zhat*dgamma/P). */
-int fiBnReluBackwardReduce(const void* dA, const void* a, const void* z, int64_t P, int C, const float* mean,
-                           const float* rstd, float* dbeta, float* dgamma, void* stream);
-int fiBnReluBackwardApply(const void* dA, const void* a, const void* z, int64_t P, int C, const float* mean,
-                          const float* rstd, const float* gamma, const float* dbeta, const float* dgamma, void* dz,
+/* Backward of relu(bn(z)) with batch statistics. The ReLU mask is recomputed from z (scale * z + shift > 0, the
+ * forward's expression; scale = gamma * rstd, shift = beta - mean * scale), so the stored activation is not read.
+ * Reduce: dbeta[c] += sum dy, dgamma[c] += sum dy * zhat (dy = dA * mask, zhat = (z - mean) * rstd).
+ * Apply: dz = gamma * rstd * (dy - dbeta / P - zhat * dgamma / P), bf16. */
+int fiBnReluBackwardReduce(const void* dA, const void* z, int64_t P, int C, const float* mean, const float* rstd,
+                           const float* scale, const float* shift, float* dbeta, float* dgamma, void* stream);
+int fiBnReluBackwardApply(const void* dA, const void* z, int64_t P, int C, const float* mean, const float* rstd,
+                          const float* gamma, const float* beta, const float* dbeta, const float* dgamma, void* dz,
                           void* stream);
 /* MaxPool2d(2) backward (gradient to the first maximum of each window) plus the skip-connection gradient. */
 int fiMaxPoolBackwardAdd(const void* a_full, const void* a_pool, const void* d_pool, const void* d_skip, void* d_full,

@@ -49,11 +49,11 @@ def test_bn_relu_forward_backward(cuda_device, n, c, h, w):
     a = torch.empty_like(zd)
     E.check(lib.fiBnApplyRelu(p(zd), P, c, p(scale), p(shift), p(a), st))
     assert (nchw(a) - a_ref.detach()).abs().max() <= 2.0 ** -7 * a_ref.abs().max() + 1e-3
-    # backward uses the bf16 activation the forward stored (mask a > 0)
+    # backward recomputes the ReLU mask from z with the forward's scale / shift
     red = torch.zeros(2, c, device=cuda_device)
-    E.check(lib.fiBnReluBackwardReduce(p(dAd), p(a), p(zd), P, c, p(mean), p(rstd), p(red[0]), p(red[1]), st))
+    E.check(lib.fiBnReluBackwardReduce(p(dAd), p(zd), P, c, p(mean), p(rstd), p(scale), p(shift), p(red[0]), p(red[1]), st))
     dz = torch.empty_like(zd)
-    E.check(lib.fiBnReluBackwardApply(p(dAd), p(a), p(zd), P, c, p(mean), p(rstd), p(gd), p(red[0]), p(red[1]), p(dz), st))
+    E.check(lib.fiBnReluBackwardApply(p(dAd), p(zd), P, c, p(mean), p(rstd), p(gd), p(bd), p(red[0]), p(red[1]), p(dz), st))
     torch.cuda.synchronize()
     assert torch.allclose(red[0].cpu(), br.grad, rtol=2e-3, atol=2e-3), "dbeta"
     assert torch.allclose(red[1].cpu(), gr.grad, rtol=2e-3, atol=2e-3), "dgamma"
