@@ -95,3 +95,43 @@ def test_metric_functions_exist_with_reference_argument_order():
     for mod in (evaluation, evaluation_simple):
         assert list(inspect.signature(mod.compute_psnr).parameters) == ["pred", "target"]
         assert list(inspect.signature(mod.compute_ssim).parameters) == ["pred", "target"]
+        assert list(inspect.signature(mod.linear_interpolation_baseline).parameters) == ["frame1", "frame2"]
+        assert list(inspect.signature(mod.optical_flow_interpolation_baseline).parameters) == ["frame1_np", "frame2_np"]
+        assert list(inspect.signature(mod.load_test_triplets).parameters) == ["test_dir"]
+    # reference model/evaluation.py:264 / evaluation_simple.py:134
+    lead = ["model", "test_triplets", "device", "save_results", "output_dir"]
+    assert list(inspect.signature(evaluation.evaluate_model).parameters)[:5] == lead
+    assert list(inspect.signature(evaluation_simple.evaluate_model_simple).parameters)[:5] == lead
+
+
+def test_load_test_triplets_and_host_baseline(tmp_path):
+    import cv2
+    import numpy as np
+    from model import evaluation
+    for video, count in (("clip_b", 5), ("clip_a", 3), ("short", 2)):
+        d = tmp_path / video
+        d.mkdir()
+        for i in range(count):
+            img = np.zeros((40, 48), np.uint8)
+            cv2.circle(img, (10 + 4 * i, 20), 6, 255, -1)
+            cv2.imwrite(str(d / f"frame_{i:03d}.png"), img)
+    (tmp_path / "notes.txt").write_text("x")
+    trips = evaluation.load_test_triplets(str(tmp_path))
+    assert len(trips) == 3 + 1 + 0
+    t = next(t for t in trips if t["video_name"] == "clip_b" and t["triplet_id"] == 1)
+    assert (t["frame_t0"], t["ground_truth"], t["frame_t1"]) == ("frame_001.png", "frame_002.png", "frame_003.png")
+    # Farneback baseline: host cv2 code; like the reference it samples frame 1 at x + flow/2 (a half-flow warp)
+    a = cv2.imread(str(tmp_path / "clip_b" / "frame_000.png"), 0)
+    b = cv2.imread(str(tmp_path / "clip_b" / "frame_002.png"), 0)
+    mid = evaluation.optical_flow_interpolation_baseline(a, b)
+    assert mid.shape == a.shape and mid.dtype == np.uint8
+    cx = lambda im: float((im.astype(np.float64) * np.arange(im.shape[1])).sum() / im.sum())  # noqa: E731
+    assert 0.1 < abs(cx(mid) - cx(a)) < abs(cx(b) - cx(a))
+    # summary / JSON writers accept the result schema
+    res = evaluation._summarise(2, {"linear": {"psnr": [30.0, 32.0], "ssim": [0.9, 0.8]}},
+                                {"linear": [{"triplet_id": 0}, {"triplet_id": 1}]}, ["linear"])
+    assert res["metrics_by_method"]["linear"]["average_psnr"] == 31.0 and res["successful_evaluations"] == 2
+    evaluation.print_evaluation_summary(res)
+    evaluation.save_evaluation_results(res, str(tmp_path / "r.json"))
+    import json
+    assert json.load(open(tmp_path / "r.json"))["metrics_by_method"]["linear"]["max_ssim"] == 0.9

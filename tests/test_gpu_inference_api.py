@@ -120,10 +120,55 @@ def test_evaluate_triplets_schema(cuda_device, checkpoints):
     fi = FrameInterpolator(checkpoints[False][0], "cuda")
     trip = [(moving_disc(i), moving_disc(i + 1), moving_disc(i + 2)) for i in range(5)]
     res = evaluate_triplets(fi, trip, batch=2)
-    assert res["num_triplets"] == 5 and set(res["methods"]) == {"unet", "linear"}
-    lin = res["methods"]["linear"]
-    exp = [M.psnr_u8(((t[0].astype(np.float32) + t[2]) / 2).astype(np.uint8), t[1]) for t in trip]
-    assert np.allclose(lin["psnr_values"], exp, atol=1e-4) and len(lin["ssim_values"]) == 5
+    assert res["total_triplets"] == 5 and res["successful_evaluations"] == 5 and res["methods"] == ["unet", "linear"]
+    lin = [r["psnr"] for r in res["results_by_method"]["linear"]]
+    # the reference's linear baseline in its own fp32 arithmetic (preprocess -> average -> postprocess_image)
+    exp = []
+    for t in trip:
+        a, b = (2.0 * (x.astype(np.float32) / 255.0) - 1.0 for x in (t[0], t[2]))
+        img = (np.clip(((a + b) / 2.0 + 1.0) / 2.0, 0.0, 1.0) * 255).astype(np.uint8)
+        exp.append(M.psnr_u8(img, t[1]))
+    assert np.allclose(lin, exp, atol=1e-4)
+    # the U-Net entries are the metrics of the frames the interpolator itself returns
+    pred = fi._forward_pairs([t[0] for t in trip], [t[2] for t in trip])
+    exp_u = [M.ssim_u8(p, t[1]) for p, t in zip(pred, trip)]
+    assert np.allclose([r["ssim"] for r in res["results_by_method"]["unet"]], exp_u, atol=1e-4)
+    s = res["metrics_by_method"]["unet"]
+    assert abs(s["average_ssim"] - np.mean(exp_u)) < 1e-4 and s["min_ssim"] <= s["average_ssim"] <= s["max_ssim"]
+
+
+def test_evaluate_model_on_a_test_directory(cuda_device, checkpoints, tmp_path):
+    """The reference's evaluate_model on <dir>/<video>/<frames>: three methods, its result keys, saved frames."""
+    from model import evaluation
+    from model.inference import load_model
+    for video, n in (("v0", 5), ("v1", 3)):
+        (tmp_path / "test" / video).mkdir(parents=True)
+        for i in range(n):
+            cv2.imwrite(str(tmp_path / "test" / video / f"f{i:02d}.png"), moving_disc(i, 96, 128))
+    (tmp_path / "test" / "v1" / "broken.png").write_bytes(b"not an image")     # sorts first: 2 unreadable triplets
+    trips = evaluation.load_test_triplets(str(tmp_path / "test"))
+    assert len(trips) == 3 + 2
+    model = load_model(checkpoints[True][0], "cuda")
+    out_dir = tmp_path / "results"
+    res = evaluation.evaluate_model(model, trips, "cuda", save_results=True, output_dir=str(out_dir), batch=2)
+    assert res["total_triplets"] == 5 and res["methods"] == ["unet", "linear", "optical_flow"]
+    ok = res["successful_evaluations"]
+    assert ok == 3 + sum(1 for t in trips if t["video_name"] == "v1" and "broken.png" not in t.values())
+    for m in res["methods"]:
+        assert len(res["results_by_method"][m]) == ok
+        assert set(res["metrics_by_method"][m]) == {"average_psnr", "average_ssim", "std_psnr", "std_ssim", "min_psnr",
+                                                    "max_psnr", "min_ssim", "max_ssim"}
+    rec = res["results_by_method"]["optical_flow"][0]
+    assert {"video_name", "triplet_id", "frame_t0", "frame_t1", "ground_truth", "method", "psnr", "ssim"} <= set(rec)
+    # saved frames reproduce the recorded metrics (frames are resized to 256x256 like the reference does)
+    stem = f"{rec['video_name']}_{rec['triplet_id']:03d}"
+    flow, gt = (cv2.imread(str(out_dir / f"{stem}_{k}.png"), 0) for k in ("optical_flow", "ground_truth"))
+    assert flow.shape == (256, 256) and abs(M.psnr_u8(flow, gt) - rec["psnr"]) < 1e-4
+    unet = cv2.imread(str(out_dir / f"{stem}_unet.png"), 0)
+    assert abs(M.ssim_u8(unet, gt) - res["results_by_method"]["unet"][0]["ssim"]) < 1e-4
+    assert evaluation.main(["--test-dir", str(tmp_path / "test"), "--model", checkpoints[True][0], "--json-output",
+                            str(tmp_path / "res.json")]) == 0
+    assert (tmp_path / "res.json").exists()
 
 
 def test_http_interpolate_end_to_end(cuda_device, checkpoints, tmp_path, monkeypatch):
