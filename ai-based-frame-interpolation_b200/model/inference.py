@@ -195,6 +195,27 @@ class FrameInterpolator:
             out += self._forward_pairs(firsts[i:i + self.pairs_per_batch], seconds[i:i + self.pairs_per_batch])
         return out
 
+    def _sequence_midpoints(self, seq):
+        """Midpoint of every consecutive pair of a frame list through the library's pipelined clip call (pinned
+        double-buffered staging, copies overlapped with compute): the video loop's inner step."""
+        arr = np.stack(seq)
+        net = self.model._engine(self.device)
+        ppb = self.pairs_per_batch
+        if arr.ndim == 3:                                   # grey frames
+            if self.n_channels != 2:
+                raise _E.FiError(f"model expects {self.n_channels} input channels, frames are grey")
+            return list(net.interpolate_clip_host_u8(arr[:, None], ppb)[:, 0])
+        c = arr.shape[3]
+        if self.n_channels == 2:                            # grey model: every colour plane is its own clip
+            out = np.empty((arr.shape[0] - 1,) + arr.shape[1:], dtype=np.uint8)
+            for k in range(c):
+                out[..., k] = net.interpolate_clip_host_u8(np.ascontiguousarray(arr[..., k])[:, None], ppb)[:, 0]
+            return list(out)
+        if self.n_channels == 2 * c:                        # colour model: planar frames
+            mids = net.interpolate_clip_host_u8(np.ascontiguousarray(arr.transpose(0, 3, 1, 2)), ppb)
+            return list(np.ascontiguousarray(mids.transpose(0, 2, 3, 1)))
+        raise _E.FiError(f"model expects {self.n_channels} input channels, frames have {c} per frame")
+
     def interpolate_sequence(self, frames, factor=2):
         """factor-1 new frames between every consecutive pair. factor = 2^k: recursive bisection (every new frame is
         a real forward of its two neighbours); any other factor repeats the midpoint, which is what the reference's
@@ -205,53 +226,104 @@ class FrameInterpolator:
         if factor & (factor - 1) == 0:
             seq = frames
             while factor > 1:
-                mids = self._midpoints(seq[:-1], seq[1:])
+                mids = self._sequence_midpoints(seq)
                 merged = []
                 for f, m in zip(seq[:-1], mids):
                     merged += [f, m]
                 seq = merged + [seq[-1]]
                 factor //= 2
             return seq
-        mids = self._midpoints(frames[:-1], frames[1:])
+        mids = self._sequence_midpoints(frames)
         out = []
         for f, m in zip(frames[:-1], mids):
             out += [f] + [m] * (factor - 1)
         return out + [frames[-1]]
 
     def interpolate_video(self, input_path, output_path, factor=2, chunk=64):
-        """Read `input_path` with cv2, write `output_path` (mp4v) at factor x the frame rate."""
+        """Read `input_path` with cv2, write `output_path` (mp4v) at factor x the frame rate. Three stages run
+        concurrently — a decoder thread, the GPU stage (this thread) and an encoder thread — joined by bounded queues,
+        so decode / encode (cv2 releases the GIL) overlap the forwards of the neighbouring chunks."""
+        import queue
+        import threading
         cap = cv2.VideoCapture(input_path)
         if not cap.isOpened():
             raise FileNotFoundError(f"could not open video {input_path}")
         fps = cap.get(cv2.CAP_PROP_FPS) or 30.0
-        writer, prev, total = None, None, 0
+        decoded, encoded = queue.Queue(maxsize=2), queue.Queue(maxsize=2)
+        failure, written = [], [0]
+
+        def decode():
+            try:
+                while not failure:
+                    frames = []
+                    while len(frames) < chunk:
+                        ok, fr = cap.read()
+                        if not ok:
+                            break
+                        frames.append(fr)
+                    decoded.put(frames)
+                    if len(frames) < chunk:
+                        return
+            except Exception as e:  # noqa: BLE001
+                failure.append(e)
+                decoded.put([])
+
+        def encode():
+            writer = None
+            try:
+                while True:
+                    seq = encoded.get()
+                    if seq is None:
+                        return
+                    if failure:
+                        continue        # keep draining so the producer never blocks
+                    if writer is None:
+                        h, w = seq[0].shape[:2]
+                        writer = cv2.VideoWriter(output_path, cv2.VideoWriter_fourcc(*"mp4v"), fps * factor, (w, h), True)
+                        if not writer.isOpened():
+                            raise RuntimeError(f"could not open video writer for {output_path}")
+                    for f in seq:
+                        writer.write(f if f.ndim == 3 else cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+                        written[0] += 1
+            except Exception as e:  # noqa: BLE001
+                failure.append(e)
+                while encoded.get() is not None:
+                    pass
+            finally:
+                if writer is not None:
+                    writer.release()
+
+        threads = [threading.Thread(target=decode, daemon=True), threading.Thread(target=encode, daemon=True)]
+        for t in threads:
+            t.start()
+        prev = None
         try:
-            while True:
-                frames = [] if prev is None else [prev]
-                while len(frames) < chunk:
-                    ok, fr = cap.read()
-                    if not ok:
-                        break
-                    frames.append(fr)
-                if len(frames) < (1 if prev is None else 2):
+            while not failure:
+                new = decoded.get()
+                frames = new if prev is None else [prev] + new
+                if len(frames) >= 2:
+                    seq = self.interpolate_sequence(frames, factor)
+                    encoded.put(seq if prev is None else seq[1:])
+                elif frames and prev is None:
+                    encoded.put(frames)          # a one-frame video is copied through
+                if len(new) < chunk:
                     break
-                seq = self.interpolate_sequence(frames, factor) if len(frames) > 1 else frames
-                if writer is None:
-                    h, w = seq[0].shape[:2]
-                    writer = cv2.VideoWriter(output_path, cv2.VideoWriter_fourcc(*"mp4v"), fps * factor, (w, h), True)
-                    if not writer.isOpened():
-                        raise RuntimeError(f"could not open video writer for {output_path}")
-                for f in (seq if prev is None else seq[1:]):
-                    writer.write(f if f.ndim == 3 else cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
-                    total += 1
                 prev = frames[-1]
-                if len(frames) < chunk:
-                    break
+        except Exception as e:  # noqa: BLE001
+            failure.append(e)
         finally:
+            encoded.put(None)
+            while threads[0].is_alive():         # unblock a decoder waiting on a full queue
+                try:
+                    decoded.get(timeout=0.05)
+                except queue.Empty:
+                    pass
+            for t in threads:
+                t.join()
             cap.release()
-            if writer is not None:
-                writer.release()
-        return total
+        if failure:
+            raise failure[0]
+        return written[0]
 
 
 # ------------------------------------------------------------------------------------------- CLI (reference :204-337)

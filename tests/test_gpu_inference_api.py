@@ -184,3 +184,60 @@ def test_http_interpolate_end_to_end(cuda_device, checkpoints, tmp_path, monkeyp
                                       "frame2": ("b.png", pb.tobytes(), "image/png")},
                data={"num_intermediate": "2", "fps": "12"})
     assert r.status_code == 200 and r.headers["content-type"] == "video/mp4" and len(r.content) > 1000
+
+
+def test_colour_sequences_grey_and_rgb_models(cuda_device, checkpoints, tmp_path):
+    """Video-loop inner step on BGR frames: a grey model runs every colour plane as its own clip, a UNet(6,3) checkpoint
+    takes planar colour pairs; both go through the pipelined clip call and equal the single-pair results."""
+    from model.inference import FrameInterpolator
+    frames = [moving_disc(i, 48, 64, color=True) for i in range(5)]
+    grey = FrameInterpolator(checkpoints[False][0], "cuda", pairs_per_batch=2)
+    seq = grey.interpolate_sequence(frames, 2)
+    assert len(seq) == 9 and seq[3].shape == (48, 64, 3)
+    assert np.array_equal(seq[3], grey.interpolate_frames(frames[1], frames[2]))
+    sd = O.init_state_dict(0, 6, 3, False, prefix="")
+    p = tmp_path / "rgb.pth"
+    torch.save(sd, p)
+    rgb = FrameInterpolator(str(p), "cuda", pairs_per_batch=3)
+    assert (rgb.n_channels, rgb.n_classes) == (6, 3)
+    seq = rgb.interpolate_sequence(frames, 2)
+    assert len(seq) == 9 and np.array_equal(seq[1], rgb.interpolate_frames(frames[0], frames[1]))
+    x0, x1 = (O.preprocess_u8(np.ascontiguousarray(f.transpose(2, 0, 1))[None]) for f in frames[:2])
+    ref = O.postprocess(O.unet_forward(sd, torch.cat([x0, x1], 1)))[0].transpose(1, 2, 0)
+    assert np.abs(seq[1].astype(int) - ref.astype(int)).max() <= 2
+    with pytest.raises(Exception):
+        rgb.interpolate_sequence([f[..., 0] for f in frames], 2)   # grey frames into a colour model
+
+
+def test_video_pipeline_chunk_edges(cuda_device, checkpoints, tmp_path):
+    """The threaded decode -> GPU -> encode loop: frame count a multiple of the chunk, a one-frame video, a missing file,
+    and the same frames whatever the chunk size."""
+    from model.inference import FrameInterpolator
+    fi = FrameInterpolator(checkpoints[False][0], "cuda", pairs_per_batch=2)
+
+    def write(path, n):
+        wr = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"mp4v"), 12.0, (80, 64), True)
+        for i in range(n):
+            wr.write(cv2.cvtColor(moving_disc(i, 64, 80), cv2.COLOR_GRAY2BGR))
+        wr.release()
+
+    def read(path):
+        cap, out = cv2.VideoCapture(str(path)), []
+        while True:
+            ok, fr = cap.read()
+            if not ok:
+                return out
+            out.append(fr)
+
+    write(tmp_path / "eight.mp4", 8)
+    assert fi.interpolate_video(str(tmp_path / "eight.mp4"), str(tmp_path / "a.mp4"), 2, chunk=4) == 15
+    assert fi.interpolate_video(str(tmp_path / "eight.mp4"), str(tmp_path / "b.mp4"), 2, chunk=64) == 15
+    fa, fb = read(tmp_path / "a.mp4"), read(tmp_path / "b.mp4")
+    assert len(fa) == len(fb) == 15 and all(np.array_equal(x, y) for x, y in zip(fa, fb))
+    assert fi.interpolate_video(str(tmp_path / "eight.mp4"), str(tmp_path / "c.mp4"), 4, chunk=3) == 29
+    write(tmp_path / "one.mp4", 1)
+    assert fi.interpolate_video(str(tmp_path / "one.mp4"), str(tmp_path / "d.mp4"), 2) == 1
+    with pytest.raises(FileNotFoundError):
+        fi.interpolate_video(str(tmp_path / "missing.mp4"), str(tmp_path / "e.mp4"), 2)
+    with pytest.raises(RuntimeError):
+        fi.interpolate_video(str(tmp_path / "eight.mp4"), str(tmp_path / "no_such_dir" / "f.mp4"), 2)
