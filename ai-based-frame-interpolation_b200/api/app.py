@@ -1,7 +1,11 @@
 """HTTP surface of the reference's api/app.py (routes, multipart fields, validation ranges, status codes:
 reference api/app.py:121-223), served by a resident FrameInterpolator instead of one subprocess + checkpoint load per
-request (reference api/app.py:82-101)."""
+request (reference api/app.py:82-101). Concurrent uploads are micro-batched: a worker thread gathers the frame pairs
+that arrive within FI_BATCH_WAIT_MS (default 2 ms, at most FI_MAX_BATCH = 16) and runs them as one forward."""
+import asyncio
+import concurrent.futures
 import os
+import queue
 import shutil
 import tempfile
 import threading
@@ -22,6 +26,7 @@ app.add_middleware(CORSMiddleware, allow_origins=["*"], allow_credentials=True, 
                    allow_headers=["*"])
 
 _worker, _worker_lock = None, threading.Lock()
+_batcher = None
 
 
 def get_worker():
@@ -32,6 +37,50 @@ def get_worker():
         from model.inference import FrameInterpolator
         _worker = FrameInterpolator(MODEL_PATH, os.environ.get("FI_DEVICE", "cuda"))
     return _worker
+
+
+class _Batcher:
+    """Single consumer of the GPU handle: drains the pending frame pairs into one batched forward."""
+
+    def __init__(self, max_batch, max_wait_s):
+        self.max_batch, self.max_wait_s = max_batch, max_wait_s
+        self.pending = queue.Queue()
+        self.batch_sizes = []            # sizes of the forwards run so far (observability / tests)
+        threading.Thread(target=self._run, daemon=True).start()
+
+    def submit(self, a, b):
+        fut = concurrent.futures.Future()
+        self.pending.put((a, b, fut))
+        return fut
+
+    def _run(self):
+        import time
+        while True:
+            items = [self.pending.get()]
+            deadline = time.monotonic() + self.max_wait_s
+            while len(items) < self.max_batch:
+                try:
+                    items.append(self.pending.get(timeout=max(deadline - time.monotonic(), 0.0)))
+                except queue.Empty:
+                    break
+            try:
+                with _worker_lock:
+                    mids = get_worker()._forward_pairs([i[0] for i in items], [i[1] for i in items])
+                self.batch_sizes.append(len(items))
+                for (_, _, fut), mid in zip(items, mids):
+                    fut.set_result(mid)
+            except Exception as e:  # noqa: BLE001  (every waiting request gets the error)
+                for _, _, fut in items:
+                    fut.set_exception(e)
+
+
+def get_batcher():
+    global _batcher
+    with _worker_lock:
+        if _batcher is None:
+            _batcher = _Batcher(int(os.environ.get("FI_MAX_BATCH", "16")),
+                                float(os.environ.get("FI_BATCH_WAIT_MS", "2")) / 1e3)
+    return _batcher
 
 
 def _decode(upload: UploadFile, data: bytes):
@@ -54,11 +103,11 @@ async def interpolate(frame1: UploadFile = File(...), frame2: UploadFile = File(
     b = _decode(frame2, await frame2.read())
     try:
         from model.inference import save_frames_as_video
-        with _worker_lock:
-            mid = get_worker().interpolate_frames(a, b)
+        mid = await asyncio.wrap_future(get_batcher().submit(a, b))
         os.makedirs(OUTPUT_DIR, exist_ok=True)
         path = os.path.join(OUTPUT_DIR, f"{uuid.uuid4().hex}.mp4")
-        save_frames_as_video([a] + [mid] * num_intermediate + [b], path, fps)  # same frame list as inference.py:262-283
+        # same frame list as inference.py:262-283; encoding runs off the event loop
+        await asyncio.to_thread(save_frames_as_video, [a] + [mid] * num_intermediate + [b], path, fps)
         return FileResponse(path, media_type="video/mp4", filename="interpolated_video.mp4")
     except HTTPException:
         raise

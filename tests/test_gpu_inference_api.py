@@ -241,3 +241,49 @@ def test_video_pipeline_chunk_edges(cuda_device, checkpoints, tmp_path):
         fi.interpolate_video(str(tmp_path / "missing.mp4"), str(tmp_path / "e.mp4"), 2)
     with pytest.raises(RuntimeError):
         fi.interpolate_video(str(tmp_path / "eight.mp4"), str(tmp_path / "no_such_dir" / "f.mp4"), 2)
+
+
+def test_http_concurrent_requests_are_batched(cuda_device, checkpoints, tmp_path, monkeypatch):
+    """Concurrent uploads share forwards (micro-batching); every client gets the video of its own pair."""
+    import concurrent.futures
+    import api.app as appmod
+    from fastapi.testclient import TestClient
+    from model.inference import FrameInterpolator
+    monkeypatch.setattr(appmod, "MODEL_PATH", checkpoints[True][0])
+    monkeypatch.setattr(appmod, "OUTPUT_DIR", str(tmp_path / "out"))
+    monkeypatch.setattr(appmod, "_worker", None)
+    monkeypatch.setattr(appmod, "_batcher", None)
+    monkeypatch.setenv("FI_BATCH_WAIT_MS", "200")
+    monkeypatch.setenv("FI_MAX_BATCH", "4")
+    c = TestClient(appmod.app)
+
+    def call(i):
+        ok, pa = cv2.imencode(".png", moving_disc(i, 256, 256))
+        ok, pb = cv2.imencode(".png", moving_disc(i + 2, 256, 256))
+        r = c.post("/interpolate", files={"frame1": ("a.png", pa.tobytes(), "image/png"),
+                                          "frame2": ("b.png", pb.tobytes(), "image/png")},
+                   data={"num_intermediate": "1", "fps": "10"})
+        return i, r
+
+    with concurrent.futures.ThreadPoolExecutor(8) as ex:
+        results = list(ex.map(call, range(8)))
+    assert all(r.status_code == 200 and len(r.content) > 1000 for _, r in results)
+    sizes = appmod._batcher.batch_sizes
+    assert sum(sizes) == 8 and max(sizes) <= 4 and len(sizes) < 8, sizes      # fewer forwards than requests
+    # the middle frame of a client's video is the interpolation of ITS pair (mp4v is lossy: compare loosely)
+    ref = FrameInterpolator(checkpoints[True][0], "cuda")
+    for i, r in results[:3]:
+        p = tmp_path / f"r{i}.mp4"
+        p.write_bytes(r.content)
+        cap = cv2.VideoCapture(str(p))
+        frames = []
+        while True:
+            ok, fr = cap.read()
+            if not ok:
+                break
+            frames.append(fr[..., 0])
+        assert len(frames) == 3
+        want = ref.interpolate_frames(moving_disc(i, 256, 256), moving_disc(i + 2, 256, 256))
+        other = ref.interpolate_frames(moving_disc(i + 3, 256, 256), moving_disc(i + 5, 256, 256))
+        err = np.abs(frames[1].astype(int) - want.astype(int)).mean()
+        assert err < 6 and err < np.abs(frames[1].astype(int) - other.astype(int)).mean()
