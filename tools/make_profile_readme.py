@@ -31,6 +31,15 @@ def main():
     w(f"| clocks during the timed region | {ck['sm_mhz']:.0f} MHz median of {ck['sm_max_mhz']:.0f}, reasons {ck['reasons']} |")
     w(f"| CPU baseline (oracle port, {cpu['cores']} host cores) | {cpu['value']:.3f} frames/s |")
     w("")
+    sc = P / f"{R}_scaling.jsonl"
+    if sc.exists():
+        rows = [json.loads(l) for l in sc.read_text().splitlines() if l.strip()]
+        w("## Scaling (`r01_scaling.jsonl`: `torchrun --nproc-per-node N bench.py --gpus N --steps 20 --warmup 3`, "
+          "frame pairs sharded by rank, no collective on the data path)\n")
+        w("| GPUs | frames/s (device-timed, max over ranks) | e2e frames/s (host clip in, host frames out) | x of 1 GPU |\n|---|---|---|---|")
+        for r in rows:
+            w(f"| {r['n_gpus']} | {r['value']:.0f} | {r['e2e']:.0f} | {r['value']/rows[0]['value']:.2f} |")
+        w("")
     w("## Per-launch table (`r01_launch_profile.json`, CUDA events inside the timed region, 4 pairs per launch)\n")
     w("| launch | kernel | ms | TFLOP/s | algorithmic GB/s | share |\n|---|---|---|---|---|---|")
     tot = sum(p["ms_total"] for p in prof)
@@ -88,7 +97,8 @@ def main():
           "on the same GPU.\n")
         w("| arm | workload | ms / step | samples/s |\n|---|---|---|---|")
         for r in rows:
-            w(f"| {r['arm']} | {r['workload'].replace('train step: FrameInterpolationUNet(bilinear) ', '')} | "
+            w(f"| {r['arm']}{' x' + str(r['n_gpus']) + ' GPUs' if r.get('n_gpus', 1) > 1 else ''} | "
+              f"{r['workload'].replace('train step: FrameInterpolationUNet(bilinear) ', '')} | "
               f"{r['ms_per_step']:.2f} | {r['samples_per_s']:.0f} |")
         w("")
         tr = P / f"{R}_train_trace.txt"
