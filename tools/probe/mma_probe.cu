@@ -17,7 +17,13 @@ __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int N, int CG>
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo) {   // MN-major SWIZZLE_128B (wgrad_gemm.cu)
+    return static_cast<uint64_t>((addr >> 4) & 0x3FFF) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16) |
+           (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+}
+
+// MAJOR: 0 = both operands K-major, 1 = both MN-major, 2 = A MN-major / B K-major
+template <int N, int CG, int MAJOR = 0>
 __global__ void __launch_bounds__(128, 1) probe(int iters, int n_acc, unsigned long long* cycles) {
     extern __shared__ uint8_t raw[];
     const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
@@ -38,18 +44,21 @@ __global__ void __launch_bounds__(128, 1) probe(int iters, int n_acc, unsigned l
     if (CG == 2) cluster_sync();
     tc_fence_after();
     const uint32_t tmem = *slot_p;
-    constexpr uint32_t IDESC = umma_idesc_bf16(CG == 2 ? 256 : 128, N);
+    constexpr uint32_t IDESC = umma_idesc_bf16(CG == 2 ? 256 : 128, N) | (MAJOR >= 1 ? (1u << 15) : 0u) |
+                               (MAJOR == 1 ? (1u << 16) : 0u);
     long long t0 = clock64();
     if (warp == 1 && rank == 0) {
         if (elect_one()) {
             for (int i = 0; i < iters; ++i) {
                 const int st = i & 3;
-                const uint64_t da = umma_desc_sw128(sa + st * 16384), db = umma_desc_sw128(sb + st * 32768);
+                const uint64_t da = MAJOR >= 1 ? desc_mn(sa + st * 16384, 8192) : umma_desc_sw128(sa + st * 16384);
+                const uint64_t db = MAJOR == 1 ? desc_mn(sb + st * 32768, 8192) : umma_desc_sw128(sb + st * 32768);
+                const uint32_t ka = MAJOR >= 1 ? 128 : 2, kb = MAJOR == 1 ? 128 : 2;   // descriptor step per K = 16
                 const uint32_t d = tmem + (i % n_acc) * N;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (CG == 1) umma_bf16_ss(d, da + 2 * k, db + 2 * k, IDESC, 1);
-                    else umma2(d, da + 2 * k, db + 2 * k, IDESC, 1);
+                    if (CG == 1) umma_bf16_ss(d, da + ka * k, db + kb * k, IDESC, 1);
+                    else umma2(d, da + ka * k, db + kb * k, IDESC, 1);
                 }
             }
             if (CG == 1) umma_commit(bar);
@@ -69,10 +78,10 @@ __global__ void __launch_bounds__(128, 1) probe(int iters, int n_acc, unsigned l
     }
 }
 
-template <int N, int CG>
+template <int N, int CG, int MAJOR = 0>
 void run(int n_acc) {
     const int iters = 4000, smem = 1024 + 4 * 16384 + 4 * 32768 + 64;
-    auto k = probe<N, CG>;
+    auto k = probe<N, CG, MAJOR>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     unsigned long long* cyc; cudaMalloc(&cyc, 8);
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -90,12 +99,15 @@ void run(int n_acc) {
     unsigned long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
     // per CTA-pair (CG=2) the MMA is 256 x N x 16; CTAs that issue: sms (CG=1) or sms/2 leaders (CG=2)
     const double flops = 2.0 * (CG == 2 ? 256 : 128) * N * 16 * 4.0 * iters * (CG == 2 ? sms / 2 : sms);
-    printf("N=%3d cta_group=%d accs=%d: %.3f ms  %.0f TFLOP/s  %.1f cycles per MMA (clock64)\n", N, CG, n_acc, ms, flops / ms / 1e9,
+    printf("major=%d N=%3d cta_group=%d accs=%d: %.3f ms  %.0f TFLOP/s  %.1f cycles per MMA (clock64)\n", MAJOR, N, CG, n_acc, ms, flops / ms / 1e9,
            double(h) / (4.0 * iters));
 }
 
 int main() {
     run<64, 1>(1); run<64, 1>(2); run<64, 1>(4); run<128, 1>(1); run<128, 1>(2); run<256, 1>(1); run<256, 1>(2);
     run<64, 2>(1); run<64, 2>(2); run<128, 2>(2); run<256, 2>(2);
+    run<64, 1, 1>(2); run<128, 1, 1>(2); run<192, 1, 1>(2); run<256, 1, 1>(2);      // wgrad: both operands MN-major
+    run<64, 1, 2>(2); run<256, 1, 2>(2);                                           // A MN-major only
+    run<256, 2, 1>(2);
     return 0;
 }
