@@ -23,8 +23,31 @@ __device__ __forceinline__ float norm_u8(uint32_t u) {
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// Packed fp32 pairs (FFMA2 on sm_100): one instruction per two lanes of arithmetic, same IEEE results as scalar fma.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    return static_cast<uint64_t>(__float_as_uint(lo)) | (static_cast<uint64_t>(__float_as_uint(hi)) << 32);
+}
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t v) {   // (lo, hi) bf16 -> (lo, hi) fp32, exact
+    return static_cast<uint64_t>(v << 16) | (static_cast<uint64_t>(v & 0xffff0000u) << 32);
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2(uint64_t v) {
+    return pack_bf16x2(__uint_as_float(static_cast<uint32_t>(v)), __uint_as_float(static_cast<uint32_t>(v >> 32)));
+}
+
 // One block row = one output row (blockIdx.y = n*2h + oy): the vertical taps/weights are block-uniform, index math is
-// 32-bit, and consecutive threads walk (ox, channel-group) so both the 16-byte gathers and the store are coalesced.
+// 32-bit (a shift when the channel-group count is a power of two), and consecutive threads walk (ox, channel-group) so
+// both the 16-byte gathers and the store are coalesced. The bf16 path blends with the four tap weights
+// w = (hy|ly) * (hx|lx) on packed fp32 pairs: 4 FFMA2 per 32-bit word of output.
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int h, int w, int c8,
                   const uint4* __restrict__ src_lo, uint4* __restrict__ dst_lo) {
@@ -40,8 +63,9 @@ upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int h,
     const uint4* row1 = src + (static_cast<size_t>(n) * h + y1) * w * c8;
     uint4* out = dst + (static_cast<size_t>(n) * oh + oy) * ow * c8;
     const int items = ow * c8;
+    const int c8_shift = (c8 & (c8 - 1)) == 0 ? __ffs(c8) - 1 : -1;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < items; i += gridDim.x * 256) {
-        const int ox = i / c8, cg = i - ox * c8;
+        const int ox = c8_shift >= 0 ? i >> c8_shift : i / c8, cg = i - ox * c8;
         const float fx = rw * ox;
         const int x0 = static_cast<int>(fx);
         const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
@@ -54,13 +78,16 @@ upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int h,
         const uint32_t c[4] = {p10.x, p10.y, p10.z, p10.w}, e[4] = {p11.x, p11.y, p11.z, p11.w};
         uint32_t o[4];
         if (src_lo == nullptr) {
+            const float w00 = hy * hx, w01 = hy * lx, w10 = ly * hx, w11 = ly * lx;
+            const uint64_t p00w = pack_f32x2(w00, w00), p01w = pack_f32x2(w01, w01);
+            const uint64_t p10w = pack_f32x2(w10, w10), p11w = pack_f32x2(w11, w11);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float lo =
-                    hy * (hx * bf_lo(a[k]) + lx * bf_lo(b[k])) + ly * (hx * bf_lo(c[k]) + lx * bf_lo(e[k]));
-                const float hi =
-                    hy * (hx * bf_hi(a[k]) + lx * bf_hi(b[k])) + ly * (hx * bf_hi(c[k]) + lx * bf_hi(e[k]));
-                o[k] = pack_bf16x2(lo, hi);
+                uint64_t acc = mul_f32x2(bf16x2_to_f32x2(a[k]), p00w);
+                acc = fma_f32x2(bf16x2_to_f32x2(b[k]), p01w, acc);
+                acc = fma_f32x2(bf16x2_to_f32x2(c[k]), p10w, acc);
+                acc = fma_f32x2(bf16x2_to_f32x2(e[k]), p11w, acc);
+                o[k] = f32x2_to_bf16x2(acc);
             }
             out[i] = make_uint4(o[0], o[1], o[2], o[3]);
         } else {
