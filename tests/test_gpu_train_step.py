@@ -219,3 +219,35 @@ def test_cuda_graph_replay_matches_eager(cuda_device, criterion):
     graphed(f1, f2, tgt)
     moved = (graphed.flat_param - before).abs()
     assert moved.max() <= 1e-4 * 4 and moved.mean() > 1e-6, (moved.max().item(), moved.mean().item())   # Adam steps are O(lr)
+
+
+def test_rgb_unet_training_step(cuda_device):
+    """UNet(6, 3, bilinear=True) — colour frame pairs in, colour frame out: the 6-channel stem, the 3-class head and
+    their gradients (frame2=None: the input tensor already holds both frames)."""
+    from model.unet import UNet
+    torch.manual_seed(11)
+    ref = UNet(6, 3, bilinear=True).train()
+    ours = copy.deepcopy(ref).to(cuda_device).train()
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(2, 6, 32, 48, generator=g) * 2 - 1
+    tgt = torch.rand(2, 3, 32, 48, generator=g) * 2 - 1
+
+    class Wrap:          # ref_forward_train expects the FrameInterpolationUNet attribute layout
+        def __init__(self, u):
+            self.unet = u
+    out = ref_forward_train(Wrap(ref), x)
+    loss_ref = F.mse_loss(out, tgt)
+    loss_ref.backward()
+    step = TrainStep(ours, lr=0.0)
+    loss = step(x.to(cuda_device), None, tgt.to(cuda_device))
+    assert abs(loss.item() - loss_ref.item()) <= 5e-3 * loss_ref.item()
+    assert step.last_output.shape == (2, 3, 32, 48)
+    rel = lambda a, b: ((a - b).norm() / (b.norm() + 1e-12)).item()  # noqa: E731
+    assert rel(step.last_output.cpu(), out.detach()) < 0.08
+    # head gradients sit next to the output (noise ~1 %), the stem's at the far end (bf16 noise floor ~50 %)
+    assert rel(step.grad_view[ours.outc.conv.weight].cpu(), ref.outc.conv.weight.grad) < 0.05
+    assert rel(step.grad_view[ours.outc.conv.bias].cpu(), ref.outc.conv.bias.grad) < 0.05
+    g_stem, g_ref = step.grad_view[ours.inc.double_conv[0].weight].cpu(), ref.inc.double_conv[0].weight.grad
+    assert g_stem.shape == (64, 6, 3, 3) and rel(g_stem, g_ref) < 1.0
+    cos = (g_stem * g_ref).sum() / (g_stem.norm() * g_ref.norm())
+    assert cos > 0.5
