@@ -6,6 +6,8 @@
              convs, and bf16 channels_last autocast), i.e. the "library baseline" of SURVEY.md §2.1.
   latency    batch 1 at 256x256 (what one `POST /interpolate` request costs) and at 1080p.
   config[3]  4K (3840x2160), pairs + fused SSIM/PSNR of the result against a synthetic ground truth.
+  colour     the 6-in / 3-out UNet of the README (UNet(6, 3), colour frame pairs) at 1080p, u8 planes in, u8 frames out,
+             and the bilinear (Upsample) decoder variant of the grey network.
 
     python tools/bench_configs.py > profiles/r01_configs.jsonl"""
 import json
@@ -105,6 +107,25 @@ def main():
                       "ms_per_step": round(ms4k, 3), "frames_per_s": round(nn / ms4k * 1e3, 1),
                       "tflops": round(O.flops_per_forward(nn, hh, ww) / ms4k / 1e9, 1),
                       "ssim_psnr_ms_per_4k_pair": round(ms_metric / nn, 4)}))
+
+    # ---- colour UNet(6,3) and the bilinear decoder at 1080p, 4 pairs per forward
+    del net
+    torch.cuda.empty_cache()
+    hh, ww, nn = 1080, 1920, 4
+    for name, (cin, cout, bil) in (("UNet(6,3) colour pairs, ConvT decoder", (6, 3, False)),
+                                   ("UNet(2,1) grey pairs, bilinear decoder", (2, 1, True))):
+        m = E.Net(dev, cin, cout, bil)
+        m.load_state_dict(O.init_state_dict(0, cin, cout, bil))
+        c = cin // 2
+        fa = torch.randint(0, 256, (nn, c, hh, ww), dtype=torch.uint8, device=dev)
+        fb = torch.randint(0, 256, (nn, c, hh, ww), dtype=torch.uint8, device=dev)
+        ms_c = timed(lambda: m.forward(fa, fb, want_f32=False, want_u8=True)[1], 20)
+        fl = O.flops_per_forward(nn, hh, ww, cin, cout, bil)
+        print(json.dumps({"config": f"1080p, {name}, {nn} pairs per forward, u8 in / u8 out",
+                          "ms_per_step": round(ms_c, 3), "frames_per_s": round(nn / ms_c * 1e3, 1),
+                          "tflops": round(fl / ms_c / 1e9, 1)}))
+        del m
+        torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":
