@@ -180,7 +180,7 @@ def main():
     import torch
     import torch.distributed as dist
     from model import _engine as E
-    from oracle import unet_oracle as O  # weights init only (seeded default init == the reference's)
+    from model.unet import UNet
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -204,7 +204,8 @@ def main():
 
     B = args.pairs
     net = E.Net(dev, 2, 1, args.bilinear, args.precision)
-    net.load_state_dict(O.init_state_dict(0, 2, 1, args.bilinear))
+    torch.manual_seed(0)   # random-init weights of the architecture (PyTorch default init, as the reference's modules)
+    net.load_state_dict(UNet(2, 1, args.bilinear).state_dict())
 
     # this rank's contiguous shard of the 599 frame pairs (neighbouring ranks share one boundary frame); the timed
     # steps rotate over a window of the shard (generating all 600 1080p frames on the host would only slow start-up)

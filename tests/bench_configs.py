@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Side measurements for the BASELINE.json configs that are not the headline bench line (on the GPU box):
+"""(Lives under tests/ because it runs the oracle's torch ops as the library baseline.)
+Side measurements for the BASELINE.json configs that are not the headline bench line (on the GPU box):
 
   config[1]  UNet bf16 forward, batch 32 of 256x256 pairs on one B200 — this path vs the same network run by stock
              PyTorch on the same GPU (the oracle's functional ops = the reference module's ops: eager fp32 with TF32
@@ -9,7 +10,7 @@
   colour     the 6-in / 3-out UNet of the README (UNet(6, 3), colour frame pairs) at 1080p, u8 planes in, u8 frames out,
              and the bilinear (Upsample) decoder variant of the grey network.
 
-    python tools/bench_configs.py > profiles/r01_configs.jsonl"""
+    python tests/bench_configs.py > profiles/r01_configs.jsonl"""
 import json
 import sys
 import time

@@ -1,5 +1,5 @@
 """Small end-to-end case for compute-sanitizer (memcheck / racecheck / synccheck), one tool per gpurun call:
-    compute-sanitizer --tool memcheck python tools/sanitizer_case.py
+    compute-sanitizer --tool memcheck python tests/sanitizer_case.py
 Covers both conv kernels (all epilogue modes), the stem, the ConvT scatter store, the bilinear decoder, the fp32x3 path,
 the clip pipeline and the metric kernel on odd sizes (partial tiles + F.pad path)."""
 import sys

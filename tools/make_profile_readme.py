@@ -92,7 +92,7 @@ def main():
     w("")
     cfg = P / f"{R}_configs.jsonl"
     if cfg.exists():
-        w("## Other BASELINE configs (`r01_configs.jsonl` = `python tools/bench_configs.py`)\n")
+        w("## Other BASELINE configs (`r01_configs.jsonl` = `python tests/bench_configs.py`)\n")
         for l in cfg.read_text().splitlines():
             if l.strip():
                 w("```json\n" + l + "\n```")
