@@ -63,3 +63,35 @@ def test_argument_validation_without_gpu():
     assert E.lib().fiNetCreate(C.byref(h), 0, 99, 1, 0) == -1
     assert E.lib().fiSsimPsnrWorkspaceBytes(0, 10, 10) == 0
     assert E.lib().fiSsimPsnrWorkspaceBytes(2, 2160, 3840) == 2 * 8 * 60 * 16
+
+
+def test_product_code_never_touches_the_oracle_or_the_reference():
+    """oracle/ is test infrastructure: the package, the tools and the measured arm of bench.py must not import it, and
+    nothing that runs on the GPU box may read /root/reference."""
+    import ast
+    import pathlib
+    root = pathlib.Path(__file__).resolve().parent.parent
+
+    def oracle_imports(path, skip_functions=()):
+        tree = ast.parse(path.read_text())
+        hits = []
+        for node in ast.walk(tree):
+            if isinstance(node, (ast.FunctionDef, ast.AsyncFunctionDef)) and node.name in skip_functions:
+                for sub in ast.walk(node):
+                    sub._skipped = True
+            mod = None
+            if isinstance(node, ast.ImportFrom):
+                mod = node.module or ""
+            elif isinstance(node, ast.Import):
+                mod = ",".join(a.name for a in node.names)
+            if mod is not None and "oracle" in mod and not getattr(node, "_skipped", False):
+                hits.append((path.name, node.lineno))
+        return hits
+
+    files = list((root / "ai-based-frame-interpolation_b200").rglob("*.py")) + list((root / "tools").rglob("*.py"))
+    bad = [h for f in files for h in oracle_imports(f)]
+    # bench.py: only the CPU-baseline / reference arm may run the oracle
+    bad += oracle_imports(root / "bench.py", skip_functions=("cpu_forward_seconds", "run_reference"))
+    assert not bad, bad
+    for f in files + [root / "bench.py", root / "__graft_entry__.py"]:
+        assert "/root/reference" not in f.read_text(), f
