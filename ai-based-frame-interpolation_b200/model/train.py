@@ -66,6 +66,7 @@ class TrainStep:
         chain of the layers below (tensor-core-bound and HBM-bound kernels share the SMs)."""
         self.criterion, self.cuda_graph, self.overlap_wgrad = criterion, cuda_graph, overlap_wgrad
         self._graphs, self._eager_steps = {}, 0
+        self.keep_activations = False
         unet = model.unet if isinstance(model, FrameInterpolationUNet) else model
         if not isinstance(unet, UNet) or not unet.bilinear:
             raise E.FiError("the B200 training step covers the bilinear UNet (what reference train.py builds)")
@@ -343,7 +344,8 @@ class TrainStep:
                     grads[l.src] = d_src
             if self.overlap_wgrad:
                 main_stream.wait_stream(self._side)
-        self.last_output, self.last_activations = y, acts
+        self.last_output = y
+        self.last_activations = acts if self.keep_activations else None   # diagnostics only: pins GBs of HBM
         return loss
 
     def _finish(self):

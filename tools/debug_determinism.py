@@ -16,6 +16,7 @@ for overlap in (False, True):
     for run in range(3):
         m = copy.deepcopy(base)
         s = TrainStep(m, lr=0.0, overlap_wgrad=overlap)
+        s.keep_activations = True
         s(f1, f2, tgt)
         torch.cuda.synchronize()
         grads.append({n: s.grad_view[p].clone() for n, p in m.named_parameters()})

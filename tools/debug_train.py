@@ -42,6 +42,7 @@ def run(n, h, w, emulate):
     out = u.outc.conv(y)
     loss_ref = F.mse_loss(out, tgt); loss_ref.backward()
     step = TrainStep(ours, lr=0.0)
+    step.keep_activations = True
     loss = step(f1.to(dev), f2.to(dev), tgt.to(dev))
     print(f"--- n={n} {h}x{w} emulate_bf16={emulate}: loss {loss.item():.6f} ref {loss_ref.item():.6f}")
     for k, v in acts.items():
