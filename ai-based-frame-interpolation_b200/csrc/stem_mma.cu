@@ -9,6 +9,12 @@
 //     B row  = [ w_hi (KT) | w_lo (KT) | w_hi (KT) | 0 ... ]        -> sum = x_hi*w_hi + x_hi*w_lo + x_lo*w_hi
 // (the dropped x_lo*w_lo term is O(2^-18) relative). Input normalisation u8/255*2-1 (reference inference.py:32-35),
 // the frame-pair torch.cat (unet.py:109) and the conv zero padding are all done by the gather.
+// C_in > 4 (the colour pair, C_in = 6): the row is laid out tap-major with the channels padded to 8, so that one tap of
+// one pixel is exactly one 16-byte chunk: K = 3 segments x 9 taps x 8 = 216 (4 slabs). The input tile is parked in
+// shared memory as one hi chunk and one lo chunk per pixel, and a pixel's row is 27 chunk copies (LDS.128 -> STS.128)
+// instead of ~2 000 instructions of 16-bit element shuffling; two A stages so that two CTAs fit per SM (measured by
+// knocking phases out: gather, row build and the MMA/epilogue skeleton were strictly serial in a lone CTA, 1.45 ms for
+// four 1080p colour pairs; two co-resident CTAs overlap them: 0.90 ms).
 // Warp roles (288 threads): 0..3 = im2col producers (thread = pixel of the 8x16 tile), 4 = MMA issuer + TMEM owner,
 // 5..8 = epilogue (bias + ReLU -> bf16 -> swizzled staging -> TMA store). Two CTAs fit per SM.
 #include "aux_kernels.cuh"
@@ -22,7 +28,7 @@ namespace fi {
 namespace {
 
 constexpr int SM_THREADS = 288;
-constexpr int SM_A_STAGES = 3;
+__host__ __device__ constexpr int stem_a_stages(int cin) { return cin > 4 ? 2 : 3; }   // chunked rows: 2 CTAs per SM
 constexpr int SM_A_BYTES = 128 * 128;  // 128 pixels x 64 bf16
 
 struct StemParams {
@@ -33,11 +39,15 @@ struct StemParams {
     const float* bias;
 };
 
-__host__ __device__ constexpr int stem_slabs(int cin) { return (27 * cin + 63) / 64; }
+__host__ __device__ constexpr bool stem_chunked(int cin) { return cin > 4; }   // tap-major rows, channels padded to 8
+__host__ __device__ constexpr int stem_slabs(int cin) { return stem_chunked(cin) ? 4 : (27 * cin + 63) / 64; }
 constexpr int SM_IN_ROWS = TILE_H + 2, SM_IN_COLS = TILE_W + 2, SM_IN_PITCH = 20;  // input tile + halo, padded pitch
-__host__ __device__ constexpr int stem_in_bytes(int cin) { return 2 * cin * SM_IN_ROWS * SM_IN_PITCH * 4; }
+__host__ __device__ constexpr int stem_in_bytes(int cin) {
+    return stem_chunked(cin) ? 2 * 2 * SM_IN_ROWS * SM_IN_COLS * 16   // two buffers x (hi, lo) x 180 pixels x 16 B
+                             : 2 * cin * SM_IN_ROWS * SM_IN_PITCH * 4;
+}
 __host__ __device__ constexpr int stem_smem_bytes(int cin) {
-    return 1024 + SM_A_STAGES * SM_A_BYTES + stem_slabs(cin) * 8192 + 4 * 2 * 4096 + 256 + 1040 + stem_in_bytes(cin);
+    return 1024 + stem_a_stages(cin) * SM_A_BYTES + stem_slabs(cin) * 8192 + 4 * 2 * 4096 + 256 + 1040 + stem_in_bytes(cin);
 }
 
 __device__ __forceinline__ float norm_u8_stem(uint8_t u) {
@@ -50,11 +60,12 @@ __device__ __forceinline__ uint32_t bf16_bits(float v) {  // round-to-nearest-ev
 }
 
 template <int CIN, bool U8>
-__global__ void __launch_bounds__(SM_THREADS, CIN <= 3 ? 2 : 1)
+__global__ void __launch_bounds__(SM_THREADS, (CIN <= 3 || CIN > 4) ? 2 : 1)
 stem_mma_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
                 const __grid_constant__ CUtensorMap map_out_lo, const StemParams p) {
     constexpr int KT = 9 * CIN;
     constexpr int SLABS = stem_slabs(CIN);
+    constexpr int SM_A_STAGES = stem_a_stages(CIN);
     constexpr uint32_t IDESC = umma_idesc_bf16(128, 64);
     constexpr int TMEM_COLS = 128;  // 2 accumulators x 64 columns
 
@@ -107,7 +118,98 @@ stem_mma_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     const int per_img = p.tiles_y * p.tiles_x;
     const int total_tiles = p.N * per_img;
 
-    if (warp < 4) {
+    if (warp < 4 && stem_chunked(CIN)) {
+        // ------------------------------------------------------------ chunked producers (C_in > 4): thread = pixel
+        if constexpr (stem_chunked(CIN)) {
+            const int m = threadIdx.x;  // 0..127, tile row = m / 16, tile column = m % 16
+            constexpr int NPX = SM_IN_ROWS * SM_IN_COLS;   // 180 tile pixels incl. halo
+            constexpr int PER = (NPX + 127) / 128;         // tile pixels converted by one thread
+            uint4* chunk_tile = reinterpret_cast<uint4*>(in_tile);   // [buffer][hi | lo][NPX] 16-byte chunks
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            uint32_t raw[PER][CIN];
+            auto fetch = [&](int tile_idx) {
+                const int img = tile_idx / per_img;
+                const int r = tile_idx - img * per_img;
+                const int y0 = (r / p.tiles_x) * TILE_H, x0 = (r % p.tiles_x) * TILE_W;
+#pragma unroll
+                for (int k = 0; k < PER; ++k) {
+                    const int i = m + 128 * k;
+                    const int rr = i / SM_IN_COLS, col = i - rr * SM_IN_COLS;
+                    const int yy = y0 + rr - 1, xx = x0 + col - 1;
+                    const bool in = i < NPX && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+#pragma unroll
+                    for (int c = 0; c < CIN; ++c) {
+                        uint32_t v = U8 ? 256u : 0u;  // out of bounds -> zero padding (LUT slot 256 / +0.0f)
+                        if (in) {
+                            const bool first = c < p.src[0].channels;
+                            const PlaneSrc& sp = first ? p.src[0] : p.src[1];
+                            const int cc = first ? c : c - p.src[0].channels;
+                            const long long off = img * sp.batch_stride + cc * sp.chan_stride + yy * sp.row_stride +
+                                                  xx * sp.px_stride;
+                            if (U8) v = __ldg(static_cast<const uint8_t*>(sp.ptr) + off);
+                            else v = __float_as_uint(__ldg(static_cast<const float*>(sp.ptr) + off));
+                        }
+                        raw[k][c] = v;
+                    }
+                }
+            };
+            if (static_cast<int>(blockIdx.x) < total_tiles) fetch(blockIdx.x);
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                uint4* hi_tile = chunk_tile + (it & 1) * 2 * NPX;
+                uint4* lo_tile = hi_tile + NPX;
+#pragma unroll
+                for (int k = 0; k < PER; ++k) {
+                    const int i = m + 128 * k;
+                    if (i < NPX) {
+                        uint32_t pk[8];   // per channel: bf16 hi in the low half, bf16 lo in the high half
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            if (c >= CIN) pk[c] = 0u;
+                            else if (U8) pk[c] = lut[raw[k][c]];
+                            else {
+                                const float v = __uint_as_float(raw[k][c]);
+                                const uint32_t h = bf16_bits(v);
+                                pk[c] = (h >> 16) | bf16_bits(v - __uint_as_float(h));
+                            }
+                        }
+                        hi_tile[i] = make_uint4(__byte_perm(pk[0], pk[1], 0x5410), __byte_perm(pk[2], pk[3], 0x5410),
+                                                __byte_perm(pk[4], pk[5], 0x5410), __byte_perm(pk[6], pk[7], 0x5410));
+                        lo_tile[i] = make_uint4(__byte_perm(pk[0], pk[1], 0x7632), __byte_perm(pk[2], pk[3], 0x7632),
+                                                __byte_perm(pk[4], pk[5], 0x7632), __byte_perm(pk[6], pk[7], 0x7632));
+                    }
+                }
+                if (t + static_cast<int>(gridDim.x) < total_tiles) fetch(t + gridDim.x);
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // two buffers: one barrier per tile (see below)
+                const int base_px = (m >> 4) * SM_IN_COLS + (m & 15);
+#pragma unroll
+                for (int s = 0; s < SLABS; ++s) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t row = smem_a + stage * SM_A_BYTES + m * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int q = s * 8 + j;          // chunk index in the row: [hi x 9 | hi x 9 | lo x 9 | 0 x 5]
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                        if (q < 27) {
+                            const int tap = q % 9;
+                            const int n = base_px + (tap / 3) * SM_IN_COLS + (tap % 3);
+                            v = q < 18 ? hi_tile[n] : lo_tile[n];
+                        }
+                        st_shared_v4(row + ((j ^ (m & 7)) << 4), v.x, v.y, v.z, v.w);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+                    if (++stage == SM_A_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp < 4) {
+        if constexpr (!stem_chunked(CIN)) {
         // ------------------------------------------------------------ im2col producers: thread = pixel
         // Phase A (cooperative): the (8+2)x(16+2) input tile of every channel is loaded once, normalised and split into
         // bf16 hi/lo, and parked in smem. Phase B: each thread assembles the im2col row of its pixel from 9*CIN LDS.
@@ -205,6 +307,7 @@ stem_mma_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
                     phase ^= 1;
                 }
             }
+        }
         }
     } else if (warp == 4) {
         // ------------------------------------------------------------ weights (once) + MMA issue
@@ -364,7 +467,9 @@ int stem_packed_k(int cin) { return stem_slabs(cin) * 64; }
 
 void stem_pack_weights(const float* w, int cin, uint16_t* out) {
     // w: fp32 [64][cin][3][3] (BN already folded); out: bf16 [64][stem_packed_k(cin)] = [w_hi | w_lo | w_hi | 0]
-    const int kt = 9 * cin, kp = stem_packed_k(cin);
+    // cin > 4: tap-major with the channels padded to 8 (segment length 72), matching the chunked producer
+    const bool chunked = stem_chunked(cin);
+    const int kt = chunked ? 72 : 9 * cin, kp = stem_packed_k(cin);
     for (int co = 0; co < 64; ++co) {
         uint16_t* row = out + static_cast<size_t>(co) * kp;
         for (int k = 0; k < kp; ++k) row[k] = 0;
@@ -373,7 +478,7 @@ void stem_pack_weights(const float* w, int cin, uint16_t* out) {
                 const float v = w[(static_cast<size_t>(co) * cin + c) * 9 + tap];
                 const uint16_t h = host_bf16(v);
                 const uint16_t l = host_bf16(v - host_bf16_to_f32(h));
-                const int k = tap * cin + c;
+                const int k = chunked ? tap * 8 + c : tap * cin + c;
                 row[k] = h;
                 row[kt + k] = l;
                 row[2 * kt + k] = h;

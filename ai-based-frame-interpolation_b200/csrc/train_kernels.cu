@@ -695,11 +695,13 @@ __global__ void __launch_bounds__(256)
 stem_pack_kernel(const float* __restrict__ w, int cin, int kp, __nv_bfloat16* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 64 * kp) return;
-    const int co = i / kp, k = i - co * kp, kt = 9 * cin;
+    const bool chunked = cin > 4;            // tap-major rows with the channels padded to 8 (stem_mma.cu)
+    const int group = chunked ? 8 : cin;
+    const int co = i / kp, k = i - co * kp, kt = 9 * group;
     const int seg = k / kt, idx = k - seg * kt;
+    const int tap = idx / group, c = idx - tap * group;
     __nv_bfloat16 r = __float2bfloat16(0.f);
-    if (seg < 3) {
-        const int tap = idx / cin, c = idx - tap * cin;
+    if (seg < 3 && c < cin) {
         const float v = w[(co * cin + c) * 9 + tap];
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         r = seg == 1 ? __float2bfloat16_rn(v - __bfloat162float(h)) : h;
