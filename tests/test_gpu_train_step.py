@@ -251,3 +251,44 @@ def test_rgb_unet_training_step(cuda_device):
     assert g_stem.shape == (64, 6, 3, 3) and rel(g_stem, g_ref) < 1.0
     cos = (g_stem * g_ref).sum() / (g_stem.norm() * g_ref.norm())
     assert cos > 0.5
+
+
+def test_train_model_end_to_end_on_a_frame_directory(cuda_device, tmp_path, monkeypatch):
+    """The reference's training entry point on a tiny synthetic data set: FrameTripletDataset -> DataLoader ->
+    train_model (CombinedLoss, Adam, plateau schedule) -> best_model.pth with the reference's checkpoint keys, which
+    model.inference.load_model reads back for inference."""
+    import cv2
+    from model import train as T
+    from model.inference import load_model
+    rs = np.random.RandomState(0)
+    for video in ("a", "b", "c"):
+        d = tmp_path / "data" / video
+        d.mkdir(parents=True)
+        for i in range(6):
+            img = np.zeros((64, 80), np.uint8)
+            cv2.circle(img, (12 + 9 * i, 30 + 2 * i), 9, 255, -1)
+            img = cv2.GaussianBlur(img, (5, 5), 0) + rs.randint(0, 8, img.shape).astype(np.uint8)
+            cv2.imwrite(str(d / f"frame_{i:03d}.png"), img)
+    ds = T.FrameTripletDataset(str(tmp_path / "data"))
+    assert len(ds) == 12 and ds[0][0].shape == (1, 256, 256)
+    monkeypatch.chdir(tmp_path)   # train_model writes best_model.pth into the cwd, like the reference
+    train_set, val_set = torch.utils.data.random_split(ds, [9, 3], generator=torch.Generator().manual_seed(0))
+    mk = lambda d, sh: torch.utils.data.DataLoader(d, batch_size=3, shuffle=sh, num_workers=0)  # noqa: E731
+    torch.manual_seed(0)
+    model = FrameInterpolationUNet(bilinear=True).to(cuda_device)
+    train_losses, val_losses = T.train_model(model, mk(train_set, True), mk(val_set, False), num_epochs=3,
+                                             device=cuda_device, lr=1e-3)
+    assert len(train_losses) == len(val_losses) == 3 and all(np.isfinite(train_losses + val_losses))
+    assert train_losses[-1] < train_losses[0]
+    ck = torch.load(tmp_path / "best_model.pth", map_location="cpu")
+    assert {"epoch", "model_state_dict", "optimizer_state_dict", "train_loss", "val_loss", "train_losses",
+            "val_losses"} <= set(ck)
+    assert set(ck["model_state_dict"]) == set(model.state_dict())
+    st = ck["optimizer_state_dict"]
+    assert st["param_groups"][0]["lr"] == 1e-3 and len(st["state"]) == len(list(model.parameters()))
+    loaded = load_model(str(tmp_path / "best_model.pth"), cuda_device)
+    f0, f1, gt = (t[None].to(cuda_device) for t in ds[0])
+    out = loaded(f0, f1)
+    assert out.shape == (1, 1, 256, 256) and torch.isfinite(out).all()
+    # the CLI wrapper (main.py train -> model.train.main) runs the same path
+    assert T.main(["--data-dir", str(tmp_path / "data"), "--epochs", "1", "--batch-size", "4", "--device", "cuda"]) is None
