@@ -292,3 +292,27 @@ def test_train_model_end_to_end_on_a_frame_directory(cuda_device, tmp_path, monk
     assert out.shape == (1, 1, 256, 256) and torch.isfinite(out).all()
     # the CLI wrapper (main.py train -> model.train.main) runs the same path
     assert T.main(["--data-dir", str(tmp_path / "data"), "--epochs", "1", "--batch-size", "4", "--device", "cuda"]) is None
+
+
+def test_optimizer_state_round_trip(cuda_device):
+    """TrainStep.state_dict() has torch.optim.Adam's layout (what train_model saves as optimizer_state_dict) and
+    load_state_dict() resumes from it: step count, learning rate and both moment vectors."""
+    model = make_model(5).to(cuda_device).train()
+    step = TrainStep(model, lr=3e-4)
+    g = torch.Generator().manual_seed(1)
+    f1, f2 = torch.rand(2, 1, 32, 32, generator=g).to(cuda_device), torch.rand(2, 1, 32, 32, generator=g).to(cuda_device)
+    for _ in range(2):
+        step(f1, f2, (f1 + f2) / 2)
+    sd = step.state_dict()
+    names = [n for n, _ in model.named_parameters()]
+    assert len(sd["state"]) == len(names) and sd["param_groups"][0]["params"] == list(range(len(names)))
+    ref_opt = torch.optim.Adam(model.parameters(), lr=1.0)
+    ref_opt.load_state_dict(sd)                       # torch accepts the layout as is
+    assert ref_opt.param_groups[0]["lr"] == 3e-4
+    resumed = TrainStep(copy.deepcopy(model), lr=1.0)
+    resumed.load_state_dict(sd)
+    assert resumed.step_count == 2 and resumed.lr == 3e-4 and resumed.betas == (0.9, 0.999)
+    assert torch.equal(resumed.m, step.m) and torch.equal(resumed.v, step.v)
+    before = resumed.flat_param.clone()
+    resumed(f1, f2, (f1 + f2) / 2)
+    assert resumed.step_count == 3 and (resumed.flat_param - before).abs().max() <= 3e-4 * 1.5
