@@ -61,7 +61,9 @@ class TrainStep:
                  overlap_wgrad=True):
         """cuda_graph=True: after two eager steps the step is captured once per input shape
         (forward + backward, about 200 launches; the all-reduce and the Adam launch stay eager) and replayed; learning
-        rate and step count reach the Adam kernel through a device buffer.
+        rate and step count reach the Adam kernel through a device buffer. With several data-parallel replicas the
+        capture is two graphs and the decoder's gradients are all-reduced while the second one (the encoder half of
+        the backward pass) runs.
         overlap_wgrad=True: weight gradients run on a second stream, beside the BatchNorm-backward / data-gradient
         chain of the layers below (tensor-core-bound and HBM-bound kernels share the SMs)."""
         self.criterion, self.cuda_graph, self.overlap_wgrad = criterion, cuda_graph, overlap_wgrad
@@ -82,8 +84,14 @@ class TrainStep:
         self.v = torch.zeros_like(self.flat_grad)
         off = 0
         self.grad_view = {}
+        # parameters() order is inc, down1-4, up1-4, outc: the decoder's gradients (finished first by the backward pass)
+        # are the tail of the flat buffer starting at the first parameter of up1
+        names = {id(p): nm for nm, p in model.named_parameters()}
+        self._decoder_offset = None
         with torch.no_grad():  # parameters become views of one flat buffer: Adam and the all-reduce see one vector
             for p in self.params:
+                if self._decoder_offset is None and ".up1." in "." + names[id(p)]:
+                    self._decoder_offset = off
                 k = p.numel()
                 self.flat_param[off:off + k] = p.detach().reshape(-1)
                 p.data = self.flat_param[off:off + k].view_as(p)
@@ -179,33 +187,61 @@ class TrainStep:
             self.hyper.copy_(self._hyper_host, non_blocking=True)
             self._invalidate_inference_mirror()
             if not self.cuda_graph:
-                loss = self._run(frame1, frame2, target)
-                self._finish()
-                return loss
+                return self._eager_step(frame1, frame2, target)
             key = (tuple(frame1.shape), None if frame2 is None else tuple(frame2.shape), tuple(target.shape))
             entry = self._graphs.get(key)
             if entry is None:
                 if self._eager_steps < 2:       # warm-up: kernel attributes, allocator pools, autograd of the criterion
                     self._eager_steps += 1
-                    loss = self._run(frame1, frame2, target)
-                    self._finish()
-                    return loss
+                    return self._eager_step(frame1, frame2, target)
                 static = [frame1.clone(), None if frame2 is None else frame2.clone(), target.clone()]
-                graph = torch.cuda.CUDAGraph()
                 torch.cuda.synchronize()
-                with torch.cuda.graph(graph):
-                    loss = self._run(*static)
-                entry = self._graphs[key] = (graph, static, loss)
-            graph, static, loss = entry
+                phases = self._phases(*static)
+                graphs = [torch.cuda.CUDAGraph()]
+                with torch.cuda.graph(graphs[0]):
+                    loss = next(phases)
+                    if not self._distributed():
+                        next(phases)            # one replica: the whole backward pass is one graph
+                if self._distributed():         # second graph = the encoder half of the backward pass (same pool)
+                    graphs.append(torch.cuda.CUDAGraph())
+                    with torch.cuda.graph(graphs[1], pool=graphs[0].pool()):
+                        next(phases)
+                entry = self._graphs[key] = (graphs, static, loss, phases)   # `phases` keeps the tensors alive
+            graphs, static, loss = entry[:3]
             static[0].copy_(frame1)
             if frame2 is not None:
                 static[1].copy_(frame2)
             static[2].copy_(target)
-            graph.replay()
-            self._finish()
+            graphs[0].replay()
+            if len(graphs) == 2:
+                early = self._reduce_decoder_async()
+                graphs[1].replay()
+                self._finish(early)
+            else:
+                self._finish(None)
             return loss
 
-    def _run(self, frame1, frame2, target):
+    @staticmethod
+    def _distributed():
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _eager_step(self, frame1, frame2, target):
+        phases = self._phases(frame1, frame2, target)
+        loss = next(phases)
+        early = self._reduce_decoder_async() if self._distributed() else None
+        next(phases)
+        self._finish(early)
+        return loss
+
+    def _reduce_decoder_async(self):
+        """All-reduce (mean) of the decoder + head gradients, enqueued while the encoder half of the backward pass is
+        still to run: NCCL works on its own stream behind the kernels enqueued so far."""
+        return dist.all_reduce(self.flat_grad[self._decoder_offset:], op=dist.ReduceOp.AVG, async_op=True)
+
+    def _phases(self, frame1, frame2, target):
+        """The step as a two-phase generator: forward + loss + backward through the decoder, then the encoder half of
+        the backward pass. Both phases yield the loss tensor; data-parallel runs reduce the decoder's gradients between
+        the two."""
         lib, st = self.lib, E.current_stream
         x = torch.cat([frame1, frame2], 1).contiguous().float() if frame2 is not None else frame1.contiguous().float()
         n, cin0, h, w = x.shape
@@ -292,6 +328,11 @@ class TrainStep:
             E.check(lib.fiHeadBackward(_ptr(last), _ptr(dy), n, h * w, _ptr(hw_), ncls, _ptr(dA), _ptr(gw), _ptr(gb), st()))
             grads["up4.3"] = dA
             for l in reversed(self.layers):
+                if l.name == "down4.3":        # every decoder layer is done: its gradients may be reduced now
+                    if self.overlap_wgrad:
+                        main_stream.wait_stream(self._side)
+                    self.last_output = y
+                    yield loss
                 a, z = acts[l.name], zs[l.name]
                 ln, lh, lw, lc = z.shape
                 P = ln * lh * lw
@@ -346,14 +387,16 @@ class TrainStep:
                 main_stream.wait_stream(self._side)
         self.last_output = y
         self.last_activations = acts if self.keep_activations else None   # diagnostics only: pins GBs of HBM
-        return loss
+        yield loss
 
-    def _finish(self):
-        """Gradient all-reduce across data-parallel replicas (NCCL over NVLink), BatchNorm counters, Adam. Kept outside
-        the captured graph: collectives are enqueued eagerly on every rank."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat_grad)
-            self.flat_grad.div_(dist.get_world_size())
+    def _finish(self, early):
+        """Rest of the gradient all-reduce across data-parallel replicas (NCCL over NVLink; `early` is the handle of
+        the decoder bucket already in flight), BatchNorm counters, Adam. Kept outside the captured graphs: collectives
+        are enqueued eagerly on every rank."""
+        if self._distributed():
+            rest = dist.all_reduce(self.flat_grad[:self._decoder_offset], op=dist.ReduceOp.AVG, async_op=True)
+            early.wait()
+            rest.wait()
         torch._foreach_add_([l.bn.num_batches_tracked for l in self.layers], 1)
         E.check(self.lib.fiAdamStep(_ptr(self.flat_param), _ptr(self.flat_grad), _ptr(self.m), _ptr(self.v),
                                     self.flat_param.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
