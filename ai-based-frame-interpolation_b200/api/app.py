@@ -6,8 +6,6 @@ import asyncio
 import concurrent.futures
 import os
 import queue
-import shutil
-import tempfile
 import threading
 import uuid
 
@@ -16,6 +14,7 @@ import numpy as np
 from fastapi import FastAPI, File, Form, HTTPException, UploadFile
 from fastapi.middleware.cors import CORSMiddleware
 from fastapi.responses import FileResponse
+from starlette.background import BackgroundTask
 
 MODEL_PATH = os.environ.get("FI_MODEL_PATH", "best_model.pth")
 OUTPUT_DIR = os.environ.get("FI_OUTPUT_DIR", "temp_outputs")
@@ -25,8 +24,9 @@ app = FastAPI(title="Frame Interpolation API", description="B200-native UNet fra
 app.add_middleware(CORSMiddleware, allow_origins=["*"], allow_credentials=True, allow_methods=["*"],
                    allow_headers=["*"])
 
-_worker, _worker_lock = None, threading.Lock()
-_batcher = None
+_worker, _worker_lock = None, threading.Lock()    # _worker_lock: held by the batcher thread around GPU work
+_batcher, _batcher_lock = None, threading.Lock()  # _batcher_lock: creation only, never held during a forward
+_written = set()                                   # result files this process created and has not deleted yet
 
 
 def get_worker():
@@ -76,7 +76,9 @@ class _Batcher:
 
 def get_batcher():
     global _batcher
-    with _worker_lock:
+    if _batcher is not None:     # fast path: the event loop never waits behind a running forward
+        return _batcher
+    with _batcher_lock:
         if _batcher is None:
             _batcher = _Batcher(int(os.environ.get("FI_MAX_BATCH", "16")),
                                 float(os.environ.get("FI_BATCH_WAIT_MS", "2")) / 1e3)
@@ -106,9 +108,12 @@ async def interpolate(frame1: UploadFile = File(...), frame2: UploadFile = File(
         mid = await asyncio.wrap_future(get_batcher().submit(a, b))
         os.makedirs(OUTPUT_DIR, exist_ok=True)
         path = os.path.join(OUTPUT_DIR, f"{uuid.uuid4().hex}.mp4")
+        _written.add(path)
         # same frame list as inference.py:262-283; encoding runs off the event loop
         await asyncio.to_thread(save_frames_as_video, [a] + [mid] * num_intermediate + [b], path, fps)
-        return FileResponse(path, media_type="video/mp4", filename="interpolated_video.mp4")
+        # the file is deleted as soon as the response has been sent (the reference reuses one video.mp4 per request)
+        return FileResponse(path, media_type="video/mp4", filename="interpolated_video.mp4",
+                            background=BackgroundTask(_discard, path))
     except HTTPException:
         raise
     except Exception as e:
@@ -127,6 +132,19 @@ async def health():
     return {"status": "healthy", "model_exists": os.path.exists(MODEL_PATH), "model_path": MODEL_PATH}
 
 
+def _discard(path):
+    _written.discard(path)
+    try:
+        os.remove(path)
+    except OSError:
+        pass
+
+
 @app.on_event("shutdown")
 async def _cleanup():
-    shutil.rmtree(OUTPUT_DIR, ignore_errors=True)
+    for path in list(_written):      # only what this process wrote: FI_OUTPUT_DIR may be a shared directory
+        _discard(path)
+    try:
+        os.rmdir(OUTPUT_DIR)         # succeeds only when nothing else lives there
+    except OSError:
+        pass

@@ -289,13 +289,9 @@ const char* launch_inst(const ConvLaunch& l, cudaStream_t stream) {
         if (l.split) return launch_inst<BLOCK_N, MODE, true>(l, stream);
     }
     auto kfn = conv_gemm_kernel<BLOCK_N, MODE, SPLIT>;
-    static bool configured = false;  // per instantiation; attribute is per-device-context but idempotent to set
+    static std::atomic<uint64_t> configured{0};  // per instantiation: devices with the shared-memory opt-in
     constexpr int smem = smem_bytes(BLOCK_N);
-    if (!configured) {
-        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
-        configured = true;
-    }
+    if (!smem_opt_in(kfn, smem, configured)) return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
     kfn<<<l.grid, eight_epilogue_warps(BLOCK_N, MODE, SPLIT) ? NUM_THREADS_8 : NUM_THREADS, smem, stream>>>(l.maps, l.p);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

@@ -217,12 +217,8 @@ const char* launch_pair_inst(const ConvLaunch& l, cudaStream_t stream) {
         if (l.split) return launch_pair_inst<MODE, true>(l, stream);
     }
     auto kfn = conv_gemm2_kernel<MODE, SPLIT>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM) != cudaSuccess)
-            return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};
+    if (!smem_opt_in(kfn, C2_SMEM, configured)) return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
     kfn<<<l.grid, C2_THREADS, C2_SMEM, stream>>>(l.maps, l.p);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

@@ -305,14 +305,10 @@ const char* launch_halo_inst(const ConvLaunch& l, cudaStream_t stream) {
         if (l.split) return launch_halo_inst<COUT, MODE, false, true>(l, stream);
     }
     auto kfn = conv_halo_kernel<COUT, MODE, RESIDENT, SPLIT>;
-    static bool configured = false;
+    static std::atomic<uint64_t> configured{0};  // per instantiation: devices with the shared-memory opt-in
     constexpr int smem = halo_smem_bytes(COUT, RESIDENT);
     static_assert(smem <= 232448, "halo kernel exceeds the 227 KB shared memory limit");
-    if (!configured) {
-        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
-        configured = true;
-    }
+    if (!smem_opt_in(kfn, smem, configured)) return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
     kfn<<<l.grid, SPLIT ? HALO_THREADS : HALO_THREADS_8, smem, stream>>>(l.maps, l.p);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

@@ -300,12 +300,8 @@ const char* launch_halo2_inst(const ConvLaunch& l, cudaStream_t stream) {
         if (9 * l.p.slabs * (COUT / 2) * 128 <= H2_B_BYTES) return launch_halo2_inst<COUT, MODE, true, SPLIT>(l, stream);
     }
     auto kfn = conv_halo2_kernel<COUT, MODE, RESIDENT, SPLIT>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, H2_SMEM) != cudaSuccess)
-            return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};
+    if (!smem_opt_in(kfn, H2_SMEM, configured)) return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
     kfn<<<l.grid, SPLIT ? H2_THREADS : H2_THREADS_8, H2_SMEM, stream>>>(l.maps, l.p);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

@@ -929,8 +929,8 @@ int fiNetReadActivation(fiNet* net, const char* name, float* out_host, int64_t c
     }
     for (int nn = 0; nn < pl.last_n; ++nn)
         for (int y = 0; y < a.H; ++y)
-            for (int x = 0; x < a.W; ++x)
-                for (int c = 0; c < a.C; ++c) {
+            for (int c = 0; c < a.C; ++c)       // row-blocked transpose: one NHWC row stays in cache, NCHW writes are contiguous
+                for (int x = 0; x < a.W; ++x) {
                     const size_t src_i = ((static_cast<size_t>(nn) * a.H + y) * a.W + x) * a.C + c;
                     const uint32_t bits = static_cast<uint32_t>(raw[src_i]) << 16;
                     float f;

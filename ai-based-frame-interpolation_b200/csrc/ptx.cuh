@@ -2,12 +2,27 @@
 // mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (MMA / TMEM alloc / TMEM load / commit).
 // Everything here is device-only and header-only.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace fi {
+
+// Host helper: cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel, and one process may
+// drive several GPUs (one fiNet + one worker thread per device). `done` is the per-instantiation bit mask of devices
+// that already have the opt-in; safe to call from several threads.
+template <class Kernel>
+inline bool smem_opt_in(Kernel kfn, int bytes, std::atomic<uint64_t>& done) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return true;
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+    done.fetch_or(bit, std::memory_order_release);
+    return true;
+}
 
 #ifndef FI_WAIT_WATCHDOG
 #define FI_WAIT_WATCHDOG (1u << 26)   // bounded spins before a role gives up and traps (no silent hangs)

@@ -426,22 +426,14 @@ template <int CIN>
 const char* launch_stem(const StemDesc& d, const CUtensorMap& map_b, const CUtensorMap& map_out,
                         const CUtensorMap& map_out_lo, const StemParams& p, int grid, cudaStream_t stream) {
     constexpr int smem = stem_smem_bytes(CIN);
-    static bool configured[2] = {false, false};
+    static std::atomic<uint64_t> configured[2];
     if (d.is_u8) {
         auto k = stem_mma_kernel<CIN, true>;
-        if (!configured[1]) {
-            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-                return "stem: cudaFuncSetAttribute failed";
-            configured[1] = true;
-        }
+        if (!smem_opt_in(k, smem, configured[1])) return "stem: cudaFuncSetAttribute failed";
         k<<<grid, SM_THREADS, smem, stream>>>(map_b, map_out, map_out_lo, p);
     } else {
         auto k = stem_mma_kernel<CIN, false>;
-        if (!configured[0]) {
-            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-                return "stem: cudaFuncSetAttribute failed";
-            configured[0] = true;
-        }
+        if (!smem_opt_in(k, smem, configured[0])) return "stem: cudaFuncSetAttribute failed";
         k<<<grid, SM_THREADS, smem, stream>>>(map_b, map_out, map_out_lo, p);
     }
     const cudaError_t e = cudaGetLastError();

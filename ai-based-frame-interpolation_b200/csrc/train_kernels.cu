@@ -809,13 +809,9 @@ const char* combined_loss_launch(const float* y, const float* t, int planes, int
         sum += gw.g[i];
     }
     for (int i = 0; i <= 2 * SL_R; ++i) gw.g[i] /= sum;
-    static bool configured = false;
+    static std::atomic<uint64_t> configured{0};
     const int smem = SL_SMEM_FLOATS * static_cast<int>(sizeof(float));
-    if (!configured) {
-        if (cudaFuncSetAttribute(combined_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return "combined_loss: cudaFuncSetAttribute failed";
-        configured = true;
-    }
+    if (!smem_opt_in(combined_loss_kernel, smem, configured)) return "combined_loss: cudaFuncSetAttribute failed";
     const float inv_n = 1.0f / (static_cast<float>(planes) * H * W);
     const int tiles = ((W + SL_TILE - 1) / SL_TILE) * ((H + SL_TILE - 1) / SL_TILE);
     // loss = mse_w * mean(diff^2) + ssim_w * (1 - mean(S)): the constant ssim_w is added by the first block's caller

@@ -234,12 +234,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
 template <int N_BLOCKS>
 const char* launch_wgrad(const CUtensorMap* maps, const WgradParams& p, int grid, cudaStream_t st) {
     auto k = wgrad_kernel<N_BLOCKS>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem(N_BLOCKS)) != cudaSuccess)
-            return "wgrad: cudaFuncSetAttribute failed";
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};
+    if (!smem_opt_in(k, wg_smem(N_BLOCKS), configured)) return "wgrad: cudaFuncSetAttribute failed";
     k<<<grid, WG_THREADS, wg_smem(N_BLOCKS), st>>>(maps[0], maps[1], maps[2], p);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

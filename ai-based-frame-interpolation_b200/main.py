@@ -12,29 +12,33 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 def build_parser():
     p = argparse.ArgumentParser(description="AI-Based Frame Interpolation (B200-native path)")
     sub = p.add_subparsers(dest="command", help="Available commands")
-    t = sub.add_parser("train", help="Train the model")
-    t.add_argument("--data-dir", required=True)
-    t.add_argument("--epochs", type=int, default=100)
-    t.add_argument("--batch-size", type=int, default=8)
-    t.add_argument("--lr", type=float, default=1e-4)
-    t.add_argument("--device", default="auto")
-    i = sub.add_parser("infer", help="Interpolate one frame pair")
-    i.add_argument("--model", required=True)
-    i.add_argument("--frame1", required=True)
-    i.add_argument("--frame2", required=True)
-    i.add_argument("--output", default="interpolated.png")
-    i.add_argument("--device", default="auto")
-    v = sub.add_parser("video", help="Interpolate a video")
-    v.add_argument("--model", required=True)
-    v.add_argument("--input", required=True)
-    v.add_argument("--output", required=True)
-    v.add_argument("--factor", type=int, default=2)
-    v.add_argument("--device", default="auto")
-    s = sub.add_parser("serve", help="Start the HTTP API")
-    s.add_argument("--host", default="0.0.0.0")
-    s.add_argument("--port", type=int, default=8000)
-    s.add_argument("--reload", action="store_true")
-    sub.add_parser("info", help="Show model information")
+    # flags, defaults and required-ness as reference main.py:40-72; --gpus is the only addition
+    t = sub.add_parser("train", help="Train the frame interpolation model")
+    t.add_argument("--data-dir", required=True, help="Directory containing training data")
+    t.add_argument("--epochs", type=int, default=100, help="Number of training epochs")
+    t.add_argument("--batch-size", type=int, default=8, help="Training batch size")
+    t.add_argument("--lr", type=float, default=0.001, help="Learning rate")
+    t.add_argument("--device", default="auto", help="Device to use (cuda/auto)")
+    i = sub.add_parser("infer", help="Run inference on two frames")
+    i.add_argument("--frame1", required=True, help="Path to first frame")
+    i.add_argument("--frame2", required=True, help="Path to second frame")
+    i.add_argument("--output", required=True, help="Output path for interpolated frame")
+    i.add_argument("--model", default="best_model.pth", help="Path to trained model")
+    i.add_argument("--device", default="auto", help="Device to use (cuda/auto)")
+    v = sub.add_parser("video", help="Interpolate frames in a video")
+    v.add_argument("--input", required=True, help="Input video path")
+    v.add_argument("--output", required=True, help="Output video path")
+    v.add_argument("--factor", type=int, default=2, help="Interpolation factor")
+    v.add_argument("--model", default="best_model.pth", help="Path to trained model")
+    v.add_argument("--device", default="auto", help="Device to use (cuda/auto)")
+    v.add_argument("--gpus", type=int, default=None,
+                   help="Shard the frame pairs over this many GPUs of the box (default: $FI_GPUS, else 1)")
+    s = sub.add_parser("serve", help="Start the web API server")
+    s.add_argument("--host", default="0.0.0.0", help="Host to bind to")
+    s.add_argument("--port", type=int, default=8000, help="Port to bind to")
+    s.add_argument("--reload", action="store_true", help="Enable auto-reload for development")
+    info = sub.add_parser("info", help="Show model information")
+    info.add_argument("--model", default="best_model.pth", help="Path to model file")
     return p
 
 
@@ -48,8 +52,16 @@ def main(argv=None):
     try:
         if args.command == "train":
             from model.train import main as train_main
-            train_main(["--data-dir", args.data_dir, "--epochs", str(args.epochs), "--batch-size", str(args.batch_size),
-                        "--lr", str(args.lr), "--device", args.device])
+            # reference main.py:92 forwards only --data-dir / --epochs, so its training always runs train.py's own
+            # defaults (Adam lr 1e-4, batch 8) whatever --lr / --batch-size say; here flags the user typed ARE forwarded
+            # and untouched ones keep train.py's defaults
+            fwd = ["--data-dir", args.data_dir, "--epochs", str(args.epochs), "--device", args.device]
+            typed = {a.split("=")[0] for a in (sys.argv[1:] if argv is None else argv)}
+            if "--lr" in typed:
+                fwd += ["--lr", str(args.lr)]
+            if "--batch-size" in typed:
+                fwd += ["--batch-size", str(args.batch_size)]
+            train_main(fwd)
             return 0
         if args.command == "infer":
             import cv2
@@ -64,7 +76,7 @@ def main(argv=None):
             print(f"Interpolated frame saved to: {args.output}")
         elif args.command == "video":
             from model.inference import FrameInterpolator
-            interpolator = FrameInterpolator(args.model, device)
+            interpolator = FrameInterpolator(args.model, device, gpus=args.gpus)
             print(f"Interpolating video: {args.input}\nOutput: {args.output}\nFactor: {args.factor}x")
             n = interpolator.interpolate_video(args.input, args.output, args.factor)
             print(f"Video interpolation completed! ({n} frames written)")
@@ -73,11 +85,30 @@ def main(argv=None):
             print(f"Starting API server on {args.host}:{args.port}")
             uvicorn.run("api.app:app", host=args.host, port=args.port, reload=args.reload)
         elif args.command == "info":
-            from model.unet import FrameInterpolationUNet, count_parameters
-            for bilinear in (False, True):
-                m = FrameInterpolationUNet(bilinear=bilinear)
-                print(f"FrameInterpolationUNet(bilinear={bilinear}): {count_parameters(m):,} parameters")
-            print("Input: two grayscale frames [B,1,H,W]; output: one intermediate frame [B,1,H,W]")
+            # reference main.py:139-158: checkpoint summary, then the architecture's parameter counts
+            if not os.path.exists(args.model):
+                print(f"Model file not found: {args.model}")
+                return 0
+            import torch
+            checkpoint = torch.load(args.model, map_location="cpu")
+            meta = checkpoint if isinstance(checkpoint, dict) and "model_state_dict" in checkpoint else {}
+
+            def fmt(v):  # the reference crashes formatting 'Unknown' with :.6f; print it as is
+                return f"{v:.6f}" if isinstance(v, (int, float)) else str(v)
+
+            print(f"Model: {args.model}")
+            print(f"Epoch: {meta.get('epoch', 'Unknown')}")
+            print(f"Training Loss: {fmt(meta.get('train_loss', 'Unknown'))}")
+            print(f"Validation Loss: {fmt(meta.get('val_loss', 'Unknown'))}")
+            from model.unet import FrameInterpolationUNet
+            state = meta.get("model_state_dict", checkpoint)
+            bilinear = not any(k.endswith("up1.up.weight") for k in state)
+            model = FrameInterpolationUNet(bilinear=bilinear)
+            total = sum(p.numel() for p in model.parameters())
+            trainable = sum(p.numel() for p in model.parameters() if p.requires_grad)
+            print(f"Architecture: FrameInterpolationUNet(bilinear={bilinear})")
+            print(f"Total Parameters: {total:,}")
+            print(f"Trainable Parameters: {trainable:,}")
     except ImportError as e:
         print(f"Import error: {e}")
         return 1

@@ -19,7 +19,11 @@ EPI_STORE, EPI_STORE_POOL, EPI_CONVT, EPI_HEAD = 0, 1, 2, 3
 
 
 class FiError(RuntimeError):
-    pass
+    """code: the negative fiStatus of the failed C-ABI call (None for errors raised on the Python side)."""
+
+    def __init__(self, msg, code=None):
+        super().__init__(msg)
+        self.code = code
 
 
 class Planes(C.Structure):
@@ -125,7 +129,7 @@ def lib():
 
 def check(rc):
     if rc != 0:
-        raise FiError(f"libfi_b200 error {rc}: {lib().fiLastError().decode(errors='replace')}")
+        raise FiError(f"libfi_b200 error {rc}: {lib().fiLastError().decode(errors='replace')}", rc)
 
 
 def current_stream():
@@ -224,13 +228,18 @@ class Net:
                                                current_stream()))
         return out
 
-    def interpolate_clip_host_u8(self, frames, pairs_per_batch=4):
+    def interpolate_clip_host_u8(self, frames, pairs_per_batch=4, out=None):
         """numpy uint8 [F,C,H,W] host clip in, numpy uint8 [F-1,n_classes,H,W] midpoints out; copies and compute are
-        pipelined inside the library."""
+        pipelined inside the library. `out`: optional preallocated C-contiguous result array (e.g. this GPU's slice of a
+        clip-wide buffer when the pairs are sharded across GPUs)."""
         import numpy as np
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         f, c, h, w = frames.shape
-        out = np.empty((f - 1, self.n_classes, h, w), dtype=np.uint8)
+        if out is None:
+            out = np.empty((f - 1, self.n_classes, h, w), dtype=np.uint8)
+        elif (out.dtype != np.uint8 or out.shape != (f - 1, self.n_classes, h, w) or not out.flags.c_contiguous
+              or not out.flags.writeable):
+            raise FiError(f"out must be a writable C-contiguous uint8 array of shape {(f - 1, self.n_classes, h, w)}")
         with torch.cuda.device(self.device):
             check(lib().fiNetInterpolateClipHostU8(self._h, frames.ctypes.data, f, c, out.ctypes.data, h, w,
                                                    pairs_per_batch, current_stream()))

@@ -16,9 +16,11 @@ import torch
 
 try:
     from . import _engine as _E
+    from .multigpu import GpuPool
     from .unet import FrameInterpolationUNet, UNet
 except ImportError:  # `python model/inference.py` / model/ on sys.path, like the reference's scripts
     import _engine as _E
+    from multigpu import GpuPool
     from unet import FrameInterpolationUNet, UNet
 
 
@@ -145,7 +147,9 @@ class FrameInterpolator:
     and postprocess_image are fused into the first and last kernels.
     """
 
-    def __init__(self, model_path, device="cuda", pairs_per_batch=4):
+    def __init__(self, model_path, device="cuda", pairs_per_batch=4, gpus=None):
+        """gpus: number of GPUs (device indices device.index .. +gpus-1) or an explicit list of device indices that
+        `interpolate_sequence` / `interpolate_video` shard the frame pairs over (default: $FI_GPUS, else 1)."""
         self.device = _resolve_device(device)
         state, _ = _read_checkpoint(model_path, self.device)
         keys = list(state.keys())
@@ -160,8 +164,36 @@ class FrameInterpolator:
             state = {k[len(prefix):]: v for k, v in state.items()} if prefix else state
         self.model.load_state_dict(state)
         self.model = self.model.to(self.device).eval()
-        self.n_channels, self.n_classes = n_channels, n_classes
+        self.n_channels, self.n_classes, self.bilinear = n_channels, n_classes, bilinear
         self.pairs_per_batch = max(1, int(pairs_per_batch))
+        if gpus is None:
+            gpus = int(os.environ.get("FI_GPUS", "1"))
+        first = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.devices = [int(d) for d in gpus] if isinstance(gpus, (list, tuple)) else [first + i for i in range(int(gpus))]
+        if not self.devices:
+            raise ValueError("gpus must name at least one device")
+        n_dev = torch.cuda.device_count()
+        if any(d < 0 or d >= n_dev for d in self.devices):
+            raise _E.FiError(f"gpus={gpus!r} asks for devices {self.devices} but only {n_dev} CUDA device(s) are visible")
+        self._single_device = self.devices == [first]       # then the module's own engine handle does the work
+        self.device = torch.device("cuda", first)
+        self._pool = None
+
+    @property
+    def gpus(self):
+        return len(self.devices)
+
+    def _gpu_pool(self):
+        """One fiNet per device of `self.devices`, each driven by its own host thread (model/multigpu.py)."""
+        if self._pool is None:
+            self._pool = GpuPool.for_devices(self.devices, self.n_channels, self.n_classes, self.bilinear,
+                                             self.model.precision, self.model.state_dict())
+        return self._pool
+
+    def close(self):
+        if self._pool is not None:
+            self._pool.close()
+            self._pool = None
 
     # frames: list/array of HxW (grey) or HxWx3 (BGR) uint8 images, all the same shape
     def _forward_pairs(self, firsts, seconds):
@@ -195,36 +227,56 @@ class FrameInterpolator:
             out += self._forward_pairs(firsts[i:i + self.pairs_per_batch], seconds[i:i + self.pairs_per_batch])
         return out
 
-    def _sequence_midpoints(self, seq):
-        """Midpoint of every consecutive pair of a frame list through the library's pipelined clip call (pinned
-        double-buffered staging, copies overlapped with compute): the video loop's inner step."""
-        arr = np.stack(seq)
-        net = self.model._engine(self.device)
-        ppb = self.pairs_per_batch
+    def _clip_call(self, frames, out):
+        """[F,C,H,W] u8 host clip -> out [F-1,n_classes,H,W]: one GPU = the library's pipelined clip call (pinned
+        double-buffered staging, copies overlapped with compute); several GPUs = contiguous pair ranges, one per GPU."""
+        if self._single_device:
+            return self.model._engine(self.device).interpolate_clip_host_u8(frames, self.pairs_per_batch, out=out)
+        return self._gpu_pool().clip_midpoints(frames, self.pairs_per_batch, out)
+
+    def interpolate_clip(self, frames, out=None):
+        """Midpoint of every consecutive pair of a clip held in ONE uint8 array: [F,H,W] grey or [F,H,W,3] BGR ->
+        [F-1,H,W] / [F-1,H,W,3]. `out` may be a preallocated result array (re-used across calls by the video loop and by
+        bench.py; a fresh 1 GB result array costs page faults comparable to the GPU time of a short clip)."""
+        arr = np.asarray(frames)
+        if arr.dtype != np.uint8 or arr.ndim not in (3, 4) or arr.shape[0] < 2:
+            raise ValueError("expected a uint8 clip [F,H,W] or [F,H,W,C] with at least two frames")
+        if out is None:
+            out = np.empty((arr.shape[0] - 1,) + arr.shape[1:], dtype=np.uint8)
+        elif out.shape != (arr.shape[0] - 1,) + arr.shape[1:] or out.dtype != np.uint8 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous uint8 array with one frame less than the clip")
         if arr.ndim == 3:                                   # grey frames
             if self.n_channels != 2:
                 raise _E.FiError(f"model expects {self.n_channels} input channels, frames are grey")
-            return list(net.interpolate_clip_host_u8(arr[:, None], ppb)[:, 0])
+            self._clip_call(np.ascontiguousarray(arr)[:, None], out[:, None])
+            return out
         c = arr.shape[3]
         if self.n_channels == 2:                            # grey model: every colour plane is its own clip
-            out = np.empty((arr.shape[0] - 1,) + arr.shape[1:], dtype=np.uint8)
+            plane = np.empty(out.shape[:3], dtype=np.uint8)
             for k in range(c):
-                out[..., k] = net.interpolate_clip_host_u8(np.ascontiguousarray(arr[..., k])[:, None], ppb)[:, 0]
-            return list(out)
+                self._clip_call(np.ascontiguousarray(arr[..., k])[:, None], plane[:, None])
+                out[..., k] = plane
+            return out
         if self.n_channels == 2 * c:                        # colour model: planar frames
-            mids = net.interpolate_clip_host_u8(np.ascontiguousarray(arr.transpose(0, 3, 1, 2)), ppb)
-            return list(np.ascontiguousarray(mids.transpose(0, 2, 3, 1)))
+            mids = np.empty((out.shape[0], c) + out.shape[1:3], dtype=np.uint8)
+            self._clip_call(np.ascontiguousarray(arr.transpose(0, 3, 1, 2)), mids)
+            out[...] = mids.transpose(0, 2, 3, 1)
+            return out
         raise _E.FiError(f"model expects {self.n_channels} input channels, frames have {c} per frame")
+
+    def _sequence_midpoints(self, seq):
+        """Midpoint of every consecutive pair of a frame list / array: the video loop's inner step."""
+        arr = seq if isinstance(seq, np.ndarray) else np.stack(seq)
+        return list(self.interpolate_clip(arr))
 
     def interpolate_sequence(self, frames, factor=2):
         """factor-1 new frames between every consecutive pair. factor = 2^k: recursive bisection (every new frame is
         a real forward of its two neighbours); any other factor repeats the midpoint, which is what the reference's
         only precedent does (model/inference.py:141-145)."""
-        frames = list(frames)
         if factor < 2 or len(frames) < 2:
-            return frames
+            return list(frames)
         if factor & (factor - 1) == 0:
-            seq = frames
+            seq = frames                                    # an ndarray clip is used as it lies (no stacking copy)
             while factor > 1:
                 mids = self._sequence_midpoints(seq)
                 merged = []
@@ -234,6 +286,7 @@ class FrameInterpolator:
                 factor //= 2
             return seq
         mids = self._sequence_midpoints(frames)
+        frames = list(frames)
         out = []
         for f, m in zip(frames[:-1], mids):
             out += [f] + [m] * (factor - 1)
@@ -248,6 +301,7 @@ class FrameInterpolator:
         cap = cv2.VideoCapture(input_path)
         if not cap.isOpened():
             raise FileNotFoundError(f"could not open video {input_path}")
+        chunk = chunk * len(self.devices)                   # every GPU gets `chunk` pairs of each decoded chunk
         fps = cap.get(cv2.CAP_PROP_FPS) or 30.0
         decoded, encoded = queue.Queue(maxsize=2), queue.Queue(maxsize=2)
         failure, written = [], [0]

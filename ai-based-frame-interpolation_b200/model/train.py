@@ -60,8 +60,8 @@ class TrainStep:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, criterion=None, cuda_graph=False,
                  overlap_wgrad=True):
         """cuda_graph=True: after two eager steps the step is captured once per input shape
-        (forward + backward, about 200 launches; the all-reduce and the Adam launch stay eager) and replayed; learning
-        rate and step count reach the Adam kernel through a device buffer. With several data-parallel replicas the
+        (forward + backward, about 200 launches; the all-reduce and the Adam launch stay eager) and replayed; the Adam
+        launch stays outside the graphs and takes learning rate and step count by value. With several data-parallel replicas the
         capture is two graphs and the decoder's gradients are all-reduced while the second one (the encoder half of
         the backward pass) runs.
         overlap_wgrad=True: weight gradients run on a second stream, beside the BatchNorm-backward / data-gradient
@@ -114,8 +114,34 @@ class TrainStep:
         self.layers = L
         self.lib = E.lib()
         self._side = torch.cuda.Stream(device=self.device)
-        self.hyper = torch.zeros(2, dtype=torch.float32, device=self.device)          # {lr, step} for the Adam kernel
-        self._hyper_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._sync_replicas()
+
+    def _sync_replicas(self):
+        """Data-parallel replicas must start from the same point: parameters, Adam moments and the BatchNorm running
+        estimates of rank 0 are broadcast once (torch DDP does the same for parameters and buffers at construction).
+        Afterwards only gradients are exchanged; the running estimates stay per replica (DDP default) and are averaged
+        by `average_bn_buffers()` before validation / checkpointing."""
+        if not self._distributed():
+            return
+        for t in (self.flat_param, self.m, self.v):
+            dist.broadcast(t, 0)
+        for l in self.layers:
+            dist.broadcast(l.bn.running_mean, 0)
+            dist.broadcast(l.bn.running_var, 0)
+        self._invalidate_inference_mirror()
+
+    def average_bn_buffers(self):
+        """Mean over the replicas of every BatchNorm running_mean / running_var (no-op on one replica)."""
+        if not self._distributed():
+            return
+        bufs = [b for l in self.layers for b in (l.bn.running_mean, l.bn.running_var)]
+        flat = torch.cat([b.reshape(-1) for b in bufs])
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        off = 0
+        for b in bufs:
+            b.copy_(flat[off:off + b.numel()].view_as(b))
+            off += b.numel()
+        self._invalidate_inference_mirror()
 
     def state_dict(self):
         """torch.optim.Adam-shaped state: per-parameter step / exp_avg / exp_avg_sq plus the param group."""
@@ -182,9 +208,7 @@ class TrainStep:
     @torch.no_grad()
     def __call__(self, frame1, frame2, target):
         self.step_count += 1
-        self._hyper_host[0], self._hyper_host[1] = self.lr, float(self.step_count)
         with torch.cuda.device(self.device):
-            self.hyper.copy_(self._hyper_host, non_blocking=True)
             self._invalidate_inference_mirror()
             if not self.cuda_graph:
                 return self._eager_step(frame1, frame2, target)
@@ -400,7 +424,7 @@ class TrainStep:
         torch._foreach_add_([l.bn.num_batches_tracked for l in self.layers], 1)
         E.check(self.lib.fiAdamStep(_ptr(self.flat_param), _ptr(self.flat_grad), _ptr(self.m), _ptr(self.v),
                                     self.flat_param.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
-                                    self.step_count, _ptr(self.hyper), E.current_stream()))
+                                    self.step_count, None, E.current_stream()))  # eager launch: lr / step by value
 
     def _invalidate_inference_mirror(self):
         # the inference engine mirrors the parameters lazily: force a re-upload on the next eval forward
@@ -505,47 +529,73 @@ class _PlateauSchedule:
 
 
 def train_model(model, train_loader, val_loader, num_epochs=100, device="cuda", criterion="combined", lr=1e-4,
-                checkpoint_path="best_model.pth"):
+                checkpoint_path="best_model.pth", cuda_graph=True):
     """The reference's train_model (model/train.py:153-249): Adam(lr=1e-4), CombinedLoss, plateau schedule, best
-    checkpoint by validation loss with the same dictionary keys. The optimisation step is TrainStep (B200 kernels);
-    validation runs the eval-mode inference path. criterion: "combined" | "mse" | a torch callable."""
+    checkpoint by validation loss with the same dictionary keys. The optimisation step is TrainStep (B200 kernels,
+    captured in CUDA graphs per batch shape); validation runs the eval-mode inference path. criterion: "combined" |
+    "mse" | a torch callable.
+
+    Under an initialised process group (torchrun: see main) every rank calls this with its own shard of the training
+    data; gradients are averaged by TrainStep, the validation loss is averaged over ranks, and rank 0 alone prints and
+    writes the checkpoint."""
     crit = CombinedLoss() if criterion == "combined" else (None if criterion == "mse" else criterion)
     val_crit = crit if crit is not None else nn.MSELoss()
-    step = TrainStep(model, lr=lr, criterion=crit)
+    step = TrainStep(model, lr=lr, criterion=crit, cuda_graph=cuda_graph)
     sched = _PlateauSchedule(step)
+    distributed = TrainStep._distributed()
+    rank0 = not distributed or dist.get_rank() == 0
+    say = print if rank0 else (lambda *a, **k: None)
     train_losses, val_losses, best = [], [], math.inf
-    print(f"Starting training for {num_epochs} epochs...")
-    print(f"Using device: {device}")
+
+    def mean_over_ranks(total, count):
+        if distributed:
+            t = torch.tensor([total, float(count)], dtype=torch.float64, device=device)
+            dist.all_reduce(t)
+            total, count = t[0].item(), t[1].item()
+        return total / max(count, 1)
+
+    say(f"Starting training for {num_epochs} epochs...")
+    say(f"Using device: {device}")
     for epoch in range(num_epochs):
+        sampler = getattr(train_loader, "sampler", None)
+        if hasattr(sampler, "set_epoch"):
+            sampler.set_epoch(epoch)
         model.train()
-        total = 0.0
+        total = torch.zeros((), dtype=torch.float32, device=device)   # summed on the device: no sync per step
         for f0, f1, gt in train_loader:
-            total += step(f0.to(device), f1.to(device), gt.to(device)).item()
-        train_losses.append(total / max(len(train_loader), 1))
+            total += step(f0.to(device, non_blocking=True), f1.to(device, non_blocking=True),
+                          gt.to(device, non_blocking=True)).detach().reshape(())
+        train_losses.append(mean_over_ranks(total.item(), len(train_loader)))
+        step.average_bn_buffers()
         model.eval()
         total = 0.0
         with torch.no_grad():
             for f0, f1, gt in val_loader:
                 total += val_crit(model(f0.to(device), f1.to(device)), gt.to(device)).item()
-        val_losses.append(total / max(len(val_loader), 1))
+        val_losses.append(mean_over_ranks(total, len(val_loader)))
         sched.step(val_losses[-1])
-        print(f"Epoch {epoch + 1}/{num_epochs}:\n  Train Loss: {train_losses[-1]:.6f}\n  Val Loss: {val_losses[-1]:.6f}\n"
-              f"  Learning Rate: {step.lr:.2e}")
+        say(f"Epoch {epoch + 1}/{num_epochs}:\n  Train Loss: {train_losses[-1]:.6f}\n  Val Loss: {val_losses[-1]:.6f}\n"
+            f"  Learning Rate: {step.lr:.2e}")
         if val_losses[-1] < best:
             best = val_losses[-1]
-            torch.save({"epoch": epoch, "model_state_dict": model.state_dict(),
-                        "optimizer_state_dict": step.state_dict(), "train_loss": train_losses[-1],
-                        "val_loss": val_losses[-1], "train_losses": train_losses, "val_losses": val_losses},
-                       checkpoint_path)
-            print(f"  New best model saved! (Val Loss: {best:.6f})")
-        print("-" * 50)
-    print(f"Training completed! Best validation loss: {best:.6f}")
+            if rank0:
+                torch.save({"epoch": epoch, "model_state_dict": model.state_dict(),
+                            "optimizer_state_dict": step.state_dict(), "train_loss": train_losses[-1],
+                            "val_loss": val_losses[-1], "train_losses": train_losses, "val_losses": val_losses},
+                           checkpoint_path)
+            say(f"  New best model saved! (Val Loss: {best:.6f})")
+        say("-" * 50)
+    say(f"Training completed! Best validation loss: {best:.6f}")
     return train_losses, val_losses
 
 
 def main(argv=None):
     """python model/train.py --data-dir D [--epochs 100 --batch-size 8 --device auto --val-split 0.2]
-    (reference model/train.py:251-313)."""
+    (reference model/train.py:251-313). Data parallel over the GPUs of a box:
+
+        torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 model/train.py --data-dir D ...
+
+    one process per GPU, NCCL all-reduce of the gradients (the only collective), --batch-size is per GPU."""
     ap = argparse.ArgumentParser(description="Train Frame Interpolation UNet (B200 training step)")
     ap.add_argument("--data-dir", required=True)
     ap.add_argument("--epochs", type=int, default=100)
@@ -553,19 +603,43 @@ def main(argv=None):
     ap.add_argument("--device", default="auto")
     ap.add_argument("--val-split", type=float, default=0.2)
     ap.add_argument("--lr", type=float, default=1e-4)
+    ap.add_argument("--no-cuda-graph", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
     args = ap.parse_args(argv)
-    device = torch.device("cuda" if args.device == "auto" else args.device)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        device = torch.device("cuda", local)
+        torch.cuda.set_device(device)
+        dist.init_process_group("nccl", device_id=device)
+    else:
+        device = torch.device("cuda" if args.device == "auto" else args.device)
     E.require_cuda(device)
+    rank0 = world == 1 or dist.get_rank() == 0
     data = FrameTripletDataset(args.data_dir)
     n_val = int(len(data) * args.val_split)
-    train_set, val_set = torch.utils.data.random_split(data, [len(data) - n_val, n_val])
-    print(f"Dataset split: {len(train_set)} train, {len(val_set)} validation")
-    mk = lambda d, sh: torch.utils.data.DataLoader(d, batch_size=args.batch_size, shuffle=sh, num_workers=4,  # noqa: E731
-                                                   pin_memory=True)
+    split_gen = torch.Generator().manual_seed(0) if world > 1 else None     # every rank must draw the same split
+    train_set, val_set = torch.utils.data.random_split(data, [len(data) - n_val, n_val], generator=split_gen)
+    if rank0:
+        print(f"Dataset split: {len(train_set)} train, {len(val_set)} validation")
+
+    def mk(d, shuffle):
+        sampler = None
+        if world > 1:
+            sampler = torch.utils.data.distributed.DistributedSampler(d, shuffle=shuffle, drop_last=shuffle)
+        return torch.utils.data.DataLoader(d, batch_size=args.batch_size, shuffle=shuffle and sampler is None,
+                                           sampler=sampler, num_workers=4, pin_memory=True)
+
     model = FrameInterpolationUNet(bilinear=True).to(device)
-    print(f"Model parameters: {sum(p.numel() for p in model.parameters()):,} total")
-    train_model(model, mk(train_set, True), mk(val_set, False), num_epochs=args.epochs, device=device, lr=args.lr)
-    print("Training completed successfully!")
+    if rank0:
+        print(f"Model parameters: {sum(p.numel() for p in model.parameters()):,} total")
+    try:
+        train_model(model, mk(train_set, True), mk(val_set, False), num_epochs=args.epochs, device=device, lr=args.lr,
+                    cuda_graph=not args.no_cuda_graph)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+    if rank0:
+        print("Training completed successfully!")
 
 
 if __name__ == "__main__":

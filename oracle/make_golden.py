@@ -59,6 +59,13 @@ def main():
         with torch.no_grad():
             y = m(x[:, :1], x[:, 1:]) if wrapper else m(x)
         out[name + "/frames"] = frames
+        if stressed:
+            # the non-default tensors of the stressed fixture (BatchNorm vectors + calibrated head), so that a test can
+            # rebuild the exact weights from a seeded module without calling the oracle
+            base = O.init_state_dict(seed, n_ch, n_cls, bil, prefix="unet." if wrapper else "")
+            for k, v in sd.items():
+                if v.dtype.is_floating_point and not torch.equal(v, base[k]):
+                    out[name + "/sd/" + k] = v.numpy()
         out[name + "/logits"] = y.numpy()
         out[name + "/sd_sha256"] = np.frombuffer(bytes.fromhex(sd_digest(sd)), dtype=np.uint8)
         out[name + "/cfg"] = np.array([n_ch, n_cls, int(bil), int(wrapper), int(stressed)], dtype=np.int32)

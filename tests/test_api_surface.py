@@ -63,15 +63,44 @@ def test_linear_baseline_matches_reference_formula():
     assert [float(f.mean()) for f in fr] == [0.25, 0.5, 0.75]
 
 
-def test_main_cli_surface(capsys):
+def test_main_cli_surface(capsys, tmp_path):
+    import shlex
+    import torch
     import main as cli
     p = cli.build_parser()
-    a = p.parse_args(["video", "--model", "m.pth", "--input", "i.mp4", "--output", "o.mp4", "--factor", "4"])
-    assert (a.command, a.factor, a.device) == ("video", 4, "auto")
-    a = p.parse_args(["infer", "--model", "m.pth", "--frame1", "a", "--frame2", "b"])
-    assert a.output == "interpolated.png"
-    assert p.parse_args(["serve"]).port == 8000
-    assert cli.main(["info"]) == 0  # the reference raises AttributeError here (no --device on `info`)
+    # the command lines the reference documents (README.md:75-111), verbatim after `python main.py`
+    readme = {
+        "train --data-dir data/train --epochs 100 --batch-size 16": dict(command="train", batch_size=16, lr=0.001),
+        "train --data-dir data/train --epochs 200 --lr 0.0001": dict(command="train", epochs=200, lr=0.0001, batch_size=8),
+        "infer --frame1 frame1.jpg --frame2 frame2.jpg --output result.jpg": dict(model="best_model.pth", device="auto"),
+        "infer --frame1 frame1.jpg --frame2 frame2.jpg --output result.jpg --model my_model.pth": dict(model="my_model.pth"),
+        "video --input video.mp4 --output interpolated.mp4 --factor 2": dict(model="best_model.pth", factor=2, gpus=None),
+        "video --input video.mp4 --output interpolated.mp4 --factor 4": dict(factor=4, device="auto"),
+        "serve --host 0.0.0.0 --port 8000": dict(port=8000, reload=False),
+        "serve --host 0.0.0.0 --port 8000 --reload": dict(reload=True),
+        "info --model best_model.pth": dict(model="best_model.pth"),
+        "serve": dict(host="0.0.0.0", port=8000),
+    }
+    for line, expect in readme.items():
+        a = p.parse_args(shlex.split(line))
+        for k, v in expect.items():
+            assert getattr(a, k) == v, (line, k)
+    with pytest.raises(SystemExit):  # reference main.py:52: --output is required on `infer`
+        p.parse_args(["infer", "--frame1", "a", "--frame2", "b"])
+    assert p.parse_args(["video", "--input", "i", "--output", "o", "--gpus", "8"]).gpus == 8
+    # `info`: reference main.py:139-158 (it raises AttributeError before getting there: no --device on `info`)
+    assert cli.main(["info", "--model", str(tmp_path / "missing.pth")]) == 0
+    assert "Model file not found" in capsys.readouterr().out
+    from model.unet import FrameInterpolationUNet
+    ck = tmp_path / "best_model.pth"
+    torch.save({"epoch": 7, "model_state_dict": FrameInterpolationUNet(bilinear=True).state_dict(), "train_loss": 0.125,
+                "val_loss": 0.25}, ck)
+    assert cli.main(["info", "--model", str(ck)]) == 0
+    out = capsys.readouterr().out
+    assert "Epoch: 7" in out and "Training Loss: 0.125000" in out and "Validation Loss: 0.250000" in out
+    assert "17,262,401" in out
+    torch.save(FrameInterpolationUNet(bilinear=False).state_dict(), ck)     # bare state dict, ConvT decoder
+    assert cli.main(["info", "--model", str(ck)]) == 0
     assert "31,037,057" in capsys.readouterr().out
 
 

@@ -184,6 +184,7 @@ def test_http_interpolate_end_to_end(cuda_device, checkpoints, tmp_path, monkeyp
                                       "frame2": ("b.png", pb.tobytes(), "image/png")},
                data={"num_intermediate": "2", "fps": "12"})
     assert r.status_code == 200 and r.headers["content-type"] == "video/mp4" and len(r.content) > 1000
+    assert not list((tmp_path / "out").glob("*.mp4")), "the per-request result file must be deleted after the response"
 
 
 def test_colour_sequences_grey_and_rgb_models(cuda_device, checkpoints, tmp_path):
