@@ -1,12 +1,20 @@
 """CPU oracle for compute_psnr / compute_ssim — TEST INFRASTRUCTURE ONLY (see oracle/unet_oracle.py for the rules).
 
-PARITY UNPINNED: the reference (model/evaluation.py:194-218, model/evaluation_simple.py:103-109) delegates to
-scikit-image (`skimage.metrics.peak_signal_noise_ratio` / `structural_similarity`, unpinned in requirements.txt:8).
-scikit-image is neither vendored in /root/reference nor installed in this image, and the reference holds no golden
-SSIM/PSNR value. This file restates the published scikit-image algorithm (metrics/_structural_similarity.py and
-metrics/simple_metrics.py, defaults: win_size=7, uniform window via scipy.ndimage.uniform_filter, sample covariance,
-K1=0.01, K2=0.03, crop (win_size-1)//2) for uint8 2-D inputs with data_range=255, and cross-checks it against an
-independent exact-integer window implementation (ssim_u8_integer) in tests/test_oracle.py.
+PARITY: pinned by closed-form vectors, NOT by a run of the real dependency. The reference
+(model/evaluation.py:194-218, model/evaluation_simple.py:103-109) delegates to scikit-image
+(`skimage.metrics.peak_signal_noise_ratio` / `structural_similarity`, unpinned in requirements.txt:8). scikit-image is
+neither vendored in /root/reference nor installed in this image, and the reference holds no golden SSIM/PSNR value, so
+"parity unpinned" still holds in the strict sense (no output of skimage itself was ever compared). This file restates the
+published scikit-image algorithm (metrics/_structural_similarity.py and metrics/simple_metrics.py, defaults: win_size=7,
+uniform window via scipy.ndimage.uniform_filter, sample covariance, K1=0.01, K2=0.03, crop (win_size-1)//2) for uint8
+2-D inputs with data_range=255. What pins it (tests/test_oracle.py):
+  * tests/golden/metrics_golden.json — eight images whose SSIM is an exact rational number derived by hand from that
+    definition (oracle/make_metrics_golden.py: 7-periodic impulse lattice, a single centred impulse, correlated and
+    anti-correlated two-level stripes with S < 0, a pure brightness shift, a 0/255 checkerboard with two window classes,
+    constants, identical images -> 1.0 / +inf; non-square sizes, widths that are not multiples of 4, a single-window
+    7x7 image, and the H < 7 / W < 7 error). The oracle agrees with every one to 1e-12;
+  * an independent exact-integer window implementation (ssim_u8_integer below) on random images to 1e-12.
+The worked SSIM values quoted in scikit-image's own documentation/tests could not be reproduced from memory and are not used.
 """
 from __future__ import annotations
 

@@ -143,3 +143,39 @@ def test_clip_pipeline_matches_pairwise_calls(cuda_device):
     for b in (1, 3, 4, 16):
         out = net.interpolate_clip_host_u8(clip, pairs_per_batch=b)
         assert out.shape == (11, 1, 40, 56) and np.array_equal(out, ref), b
+
+
+def _metrics_golden():
+    import json
+    from pathlib import Path
+    return json.loads((Path(__file__).parent / "golden" / "metrics_golden.json").read_text())
+
+
+@pytest.mark.parametrize("row", _metrics_golden()["cases"], ids=lambda r: r["name"])
+def test_ssim_psnr_kernel_against_closed_forms(cuda_device, row):
+    """fiSsimPsnrU8 and the compute_psnr / compute_ssim drop-ins against the hand-derived exact values of
+    tests/golden/metrics_golden.json (north-star bar: within 1e-4 of model/evaluation.py:194-218)."""
+    from model import evaluation
+    pred, target = np.array(row["pred"], np.uint8), np.array(row["target"], np.uint8)
+    out = E.ssim_psnr_u8(torch.from_numpy(pred).to(cuda_device), torch.from_numpy(target).to(cuda_device)).cpu().numpy()[0]
+    want_psnr = float("inf") if row["psnr"] == "inf" else row["psnr"]
+    if want_psnr == float("inf"):
+        assert out[0] == float("inf") and evaluation.compute_psnr(pred, target) == float("inf")
+        assert out[1] == 1.0
+    else:
+        assert abs(out[0] - want_psnr) <= 1e-4
+        assert abs(evaluation.compute_psnr(pred, target) - want_psnr) <= 1e-4
+    assert abs(out[1] - row["ssim"]) <= 1e-4
+    assert abs(evaluation.compute_ssim(pred, target) - row["ssim"]) <= 1e-4
+    # batched with a second, different pair: results do not leak between images
+    both = E.ssim_psnr_u8(torch.from_numpy(np.stack([pred, target])).to(cuda_device),
+                          torch.from_numpy(np.stack([target, target])).to(cuda_device)).cpu().numpy()
+    assert abs(both[0, 1] - row["ssim"]) <= 1e-4 and both[1, 1] == 1.0 and both[1, 0] == float("inf")
+
+
+def test_ssim_error_rows(cuda_device):
+    from model import evaluation
+    for row in _metrics_golden()["errors"]:
+        z = np.zeros(row["shape"], np.uint8)
+        with pytest.raises((E.FiError, ValueError)):
+            evaluation.compute_ssim(z, z)

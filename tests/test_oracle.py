@@ -74,3 +74,33 @@ def test_ssim_known_values():
     assert M.ssim_u8(a, b) == pytest.approx((2 * 100 * 110 + c1) / (100 ** 2 + 110 ** 2 + c1), rel=1e-12)
     with pytest.raises(ValueError):
         M.ssim_u8(np.zeros((6, 20), np.uint8), np.zeros((6, 20), np.uint8))
+
+
+# ---------------------------------------------------------------------- closed-form metric vectors (hand-derived)
+import json  # noqa: E402
+
+METRICS_GOLD = json.loads((Path(__file__).parent / "golden" / "metrics_golden.json").read_text())
+
+
+@pytest.mark.parametrize("row", METRICS_GOLD["cases"], ids=lambda r: r["name"])
+def test_metrics_oracle_against_closed_forms(row):
+    """The restated scikit-image metrics against exact rational SSIM / closed-form PSNR values derived by hand in
+    oracle/make_metrics_golden.py (reference call sites model/evaluation.py:194-218)."""
+    from fractions import Fraction
+    pred, target = np.array(row["pred"], np.uint8), np.array(row["target"], np.uint8)
+    assert list(pred.shape) == row["shape"]
+    num, den = row["ssim_fraction"].split("/")
+    exact = float(Fraction(int(num), int(den)))
+    assert exact == row["ssim"]
+    assert abs(M.ssim_u8(pred, target) - exact) <= 1e-12
+    assert abs(M.ssim_u8_integer(pred, target) - exact) <= 1e-12
+    want = float("inf") if row["psnr"] == "inf" else row["psnr"]
+    got = M.psnr_u8(pred, target)
+    assert got == want if want == float("inf") else abs(got - want) <= 1e-10
+
+
+def test_metrics_oracle_error_rows():
+    for row in METRICS_GOLD["errors"]:
+        z = np.zeros(row["shape"], np.uint8)
+        with pytest.raises(ValueError):
+            M.ssim_u8(z, z)
