@@ -8,7 +8,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <list>
 #include <map>
 #include <string>
 #include <vector>
@@ -124,7 +126,16 @@ struct fiNet {
     ConvW convs[17];        // inc.3, down{1-4}.{0,3}, up{1-4}.{0,3}
     ConvW upT[4];           // ConvTranspose2d of up1..up4 (bilinear=False)
     DevBuf head_w, head_b;  // fp32 [n_classes][64], [n_classes]
-    Plan plan;
+    // Prepared plans (arena + tensor maps + launch list), one per frame size, most recently used first. A server that
+    // alternates between shapes (256x256 API requests, 1080p video, the levels of a mixed clip) re-uses them instead of
+    // re-allocating a multi-GB arena and re-encoding ~60 tensor maps on every switch. FI_PLAN_CACHE (default 4) bounds
+    // the list; the least recently used plan is dropped first, and all idle plans are dropped when an arena does not fit.
+    std::list<Plan> plans;
+    int max_plans = 4;
+    long long plan_builds = 0;  // how many plans were built so far (observability: fiNetPlanStats)
+    Plan& plan() { return plans.front(); }
+    bool has_plan() const { return !plans.empty(); }
+    void drop_plans() { plans.clear(); }
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;  // [call][step][2], resolved by fiNetGetProfile
     int prof_calls = 0;
@@ -302,11 +313,39 @@ int load_convT(const StateDict& sd, const std::string& key, int cin, int cout, C
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+int fill_plan(fiNet* net, Plan& pl, int N, int H, int W);
+
+// Makes the plan for (N, H, W) the current one (net->plan()): an existing plan of that frame size with enough batch
+// capacity is moved to the front of the LRU list, otherwise a new one is built (replacing a smaller one of the same size).
 int build_plan(fiNet* net, int N, int H, int W) {
-    Plan& pl = net->plan;
-    if (pl.N >= N && pl.H == H && pl.W == W && pl.arena.p) return FI_OK;
-    pl.reset();
     if ((H >> 4) < 1 || (W >> 4) < 1) return fail(FI_ERR_INVALID, "input %dx%d is smaller than 16x16 (4 poolings)", H, W);
+    for (auto it = net->plans.begin(); it != net->plans.end(); ++it) {
+        if (it->H != H || it->W != W || !it->arena.p) continue;
+        if (it->N >= N) {
+            if (it != net->plans.begin()) net->plans.splice(net->plans.begin(), net->plans, it);
+            return FI_OK;
+        }
+        net->plans.erase(it);  // same frame size, smaller batch capacity: superseded
+        break;
+    }
+    while (static_cast<int>(net->plans.size()) >= net->max_plans && !net->plans.empty()) net->plans.pop_back();
+    net->plans.emplace_front();
+    int rc = fill_plan(net, net->plans.front(), N, H, W);
+    if (rc == FI_ERR_NOMEM && net->plans.size() > 1) {  // make room: drop every idle plan and try once more
+        net->plans.resize(1);
+        net->plans.front().reset();
+        rc = fill_plan(net, net->plans.front(), N, H, W);
+    }
+    if (rc != FI_OK) {
+        net->plans.pop_front();
+        return rc;
+    }
+    ++net->plan_builds;
+    return FI_OK;
+}
+
+int fill_plan(fiNet* net, Plan& pl, int N, int H, int W) {
+    pl.reset();
 
     ConvShape cs[17], stem;
     int upc[4][2];
@@ -571,6 +610,7 @@ int fiNetCreate(fiNet** out, int device, int n_channels, int n_classes, int bili
     net->n_classes = n_classes;
     net->bilinear = bilinear ? 1 : 0;
     net->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("FI_PLAN_CACHE")) net->max_plans = atoi(e) > 0 ? atoi(e) : 1;
     *out = net;
     return FI_OK;
 }
@@ -582,7 +622,7 @@ int fiNetSetPrecision(fiNet* net, int precision) {
     if (net->precise != precision) {  // packed weights and the arena layout depend on it
         net->precise = precision;
         net->loaded = false;
-        net->plan.reset();
+        net->drop_plans();
     }
     return FI_OK;
 }
@@ -616,7 +656,7 @@ int fiNetLoadWeights(fiNet* net, const char* const* names, const float* const* d
     StateDict sd;
     for (int i = 0; i < count; ++i) sd.m[names[i]] = {data_host[i], numel[i]};
     net->loaded = false;
-    net->plan.reset();  // launches hold weight pointers
+    net->drop_plans();  // launches hold weight pointers
 
     ConvShape cs[17], stem;
     int upc[4][2];
@@ -674,7 +714,7 @@ int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dt
     if ((rc = set_device(net->device))) return rc;
     if ((rc = build_plan(net, N, H, W))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    Plan& pl = net->plan;
+    Plan& pl = net->plan();
     pl.last_n = N;
     cudaEvent_t* evs = nullptr;
     if (net->profiling) {
@@ -737,7 +777,8 @@ int fiNetSetProfiling(fiNet* net, int enable) {
 
 int fiNetGetProfile(fiNet* net, fiLaunchProfile* out, int capacity, int* count) {
     if (!net || !count) return fail(FI_ERR_INVALID, "null argument");
-    const Plan& pl = net->plan;
+    if (!net->has_plan()) return fail(FI_ERR_STATE, "no forward has run yet");
+    const Plan& pl = net->plan();
     const int n = static_cast<int>(pl.steps.size());
     *count = n;
     if (!out) return FI_OK;
@@ -904,14 +945,27 @@ int fiNetForwardCost(fiNet* net, int N, int H, int W, double* flops, int* launch
     int rc = set_device(net->device);
     if (rc) return rc;
     if ((rc = build_plan(net, N, H, W))) return rc;
-    if (flops) *flops = net->plan.flops * N;
-    if (launches) *launches = static_cast<int>(net->plan.steps.size());
+    if (flops) *flops = net->plan().flops * N;
+    if (launches) *launches = static_cast<int>(net->plan().steps.size());
+    return FI_OK;
+}
+
+int fiNetPlanStats(fiNet* net, int* cached, long long* builds, size_t* arena_bytes) {
+    if (!net) return fail(FI_ERR_INVALID, "net is null");
+    if (cached) *cached = static_cast<int>(net->plans.size());
+    if (builds) *builds = net->plan_builds;
+    if (arena_bytes) {
+        size_t total = 0;
+        for (const Plan& p : net->plans) total += p.arena.bytes;
+        *arena_bytes = total;
+    }
     return FI_OK;
 }
 
 int fiNetReadActivation(fiNet* net, const char* name, float* out_host, int64_t capacity, int* C, int* H, int* W) {
     if (!net || !name || !out_host) return fail(FI_ERR_INVALID, "null argument");
-    Plan& pl = net->plan;
+    if (!net->has_plan()) return fail(FI_ERR_INVALID, "no activation named '%s': no forward has run yet", name);
+    Plan& pl = net->plan();
     auto it = pl.acts.find(name);
     if (!pl.arena.p || it == pl.acts.end()) return fail(FI_ERR_INVALID, "no activation named '%s' in the current plan", name);
     const Act& a = it->second;

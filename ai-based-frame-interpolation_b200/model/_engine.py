@@ -63,6 +63,7 @@ _SIGNATURES = {
     "fiNetInterpolateClipHostU8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                              C.c_int, C.c_void_p]),
     "fiNetForwardCost": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "fiNetPlanStats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_size_t)]),
     "fiNetReadActivation": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int),
                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fiConvGemm": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
@@ -263,6 +264,12 @@ class Net:
         with torch.cuda.device(self.device):
             check(lib().fiNetForwardCost(self._h, n, h, w, C.byref(fl), C.byref(ln)))
         return fl.value, ln.value
+
+    def plan_stats(self):
+        """(plans cached, plans built so far, bytes held by their arenas) — see fiNetPlanStats."""
+        cached, builds, nbytes = C.c_int(), C.c_longlong(), C.c_size_t()
+        check(lib().fiNetPlanStats(self._h, C.byref(cached), C.byref(builds), C.byref(nbytes)))
+        return cached.value, builds.value, nbytes.value
 
     def read_activation(self, name, n, max_elems=1 << 24):
         buf = torch.empty(max_elems, dtype=torch.float32)

@@ -109,6 +109,11 @@ typedef struct fiLaunchProfile {
 } fiLaunchProfile;
 int fiNetSetProfiling(fiNet* net, int enable);
 int fiNetGetProfile(fiNet* net, fiLaunchProfile* out, int capacity, int* count);
+/* Plan cache: a plan (activation arena + tensor maps + prepared launches) is kept per frame size, most recently used
+ * first, at most $FI_PLAN_CACHE (default 4) of them, so alternating shapes — one 256x256 pair per POST /interpolate
+ * (reference api/app.py:121-205) between 1080p video batches — neither re-allocate nor re-encode. Outputs (any may be
+ * NULL): plans currently cached, plans built since fiNetCreate, bytes of device memory held by their arenas. */
+int fiNetPlanStats(fiNet* net, int* cached, long long* builds, size_t* arena_bytes);
 /* Debug tap: copy an intermediate activation (bf16 NHWC) of the last forward to the host as fp32 NCHW.
  * name in {inc, down1..down4, up1..up4 (block outputs), up1.up..up4.up (upsampled tensors)}. */
 int fiNetReadActivation(fiNet* net, const char* name, float* out_host, int64_t capacity, int* C, int* H, int* W);

@@ -332,3 +332,41 @@ def test_c_abi_error_paths(cuda_device):
         E.Net(cuda_device, 2, 1, False, "fp64")
     out = net.forward(x, x)[0]  # the handle is still usable after the failed calls
     assert torch.isfinite(out).all()
+
+
+def test_plan_cache_keeps_alternating_shapes(cuda_device, monkeypatch):
+    """A server alternates between frame sizes (256x256 API requests between video batches): each size gets its plan once
+    and switching back neither rebuilds nor changes results; the cache is LRU-bounded ($FI_PLAN_CACHE)."""
+    from model import _engine as E
+    sd = O.init_state_dict(0, 2, 1, False)
+    net = E.Net(cuda_device, 2, 1, False)
+    net.load_state_dict(sd)
+    shapes = [(1, 64, 64), (2, 48, 80), (1, 96, 128)]
+    inputs = {s: (frames(40 + i, s[0], 1, s[1], s[2]).to(cuda_device), frames(50 + i, s[0], 1, s[1], s[2]).to(cuda_device))
+              for i, s in enumerate(shapes)}
+    first = {s: net.forward(*inputs[s], want_f32=True)[0].clone() for s in shapes}
+    cached, builds, nbytes = net.plan_stats()
+    assert (cached, builds) == (3, 3) and nbytes > 0
+    for _ in range(3):
+        for s in shapes:
+            assert torch.equal(net.forward(*inputs[s], want_f32=True)[0], first[s])
+    assert net.plan_stats()[:2] == (3, 3), "alternating shapes must not rebuild plans"
+    # a smaller batch of a cached size reuses its plan; a larger one supersedes it (one plan per frame size)
+    net.forward(inputs[(2, 48, 80)][0][:1], inputs[(2, 48, 80)][1][:1])
+    assert net.plan_stats()[:2] == (3, 3)
+    big = frames(60, 3, 1, 48, 80).to(cuda_device)
+    net.forward(big, big)
+    assert net.plan_stats()[:2] == (3, 4)
+    # the read-back tap follows the most recent forward's plan
+    net.forward(*inputs[(1, 64, 64)])
+    assert net.read_activation("inc", 1).shape == (1, 64, 64, 64)
+    # LRU bound
+    monkeypatch.setenv("FI_PLAN_CACHE", "2")
+    small = E.Net(cuda_device, 2, 1, False)
+    small.load_state_dict(sd)
+    for s in shapes:
+        small.forward(*inputs[s])
+    assert small.plan_stats()[:2] == (2, 3)
+    small.forward(*inputs[shapes[0]])          # evicted earlier: rebuilt, same result
+    assert small.plan_stats()[:2] == (2, 4)
+    assert torch.equal(small.forward(*inputs[shapes[0]], want_f32=True)[0], first[shapes[0]])
