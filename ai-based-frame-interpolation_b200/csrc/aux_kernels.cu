@@ -51,6 +51,8 @@ __device__ __forceinline__ uint32_t f32x2_to_bf16x2(uint64_t v) {
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int h, int w, int c8,
                   const uint4* __restrict__ src_lo, uint4* __restrict__ dst_lo) {
+    pdl_launch_dependents();
+    pdl_wait();  // launched with programmatic stream serialization: the layer below is complete from here on
     const int oh = 2 * h, ow = 2 * w;
     const int n = blockIdx.y / oh, oy = blockIdx.y - n * oh;
     const float rh = oh > 1 ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.f;
@@ -404,10 +406,8 @@ const char* upsample2x_launch(const void* src, void* dst, int N, int h, int w, i
     if (static_cast<long long>(N) * 2 * h > 65535) return "upsample: N*2h must be <= 65535 (grid.y)";
     const int items = 2 * w * (C / 8);
     const int gx = (items + 1023) / 1024;  // 4 items per thread
-    upsample2x_kernel<<<dim3(gx, N * 2 * h), 256, 0, stream>>>(static_cast<const uint4*>(src),
-                                                                static_cast<uint4*>(dst), h, w, C / 8,
-                                                                static_cast<const uint4*>(src_lo),
-                                                                static_cast<uint4*>(dst_lo));
+    launch_kernel(upsample2x_kernel, dim3(gx, N * 2 * h), dim3(256), 0, stream, static_cast<const uint4*>(src),
+                  static_cast<uint4*>(dst), h, w, C / 8, static_cast<const uint4*>(src_lo), static_cast<uint4*>(dst_lo));
     return last_launch_error();
 }
 

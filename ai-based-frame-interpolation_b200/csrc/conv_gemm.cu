@@ -117,6 +117,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_launch_dependents();  // the next layer may run its prologue on SMs this grid vacates
+    pdl_wait();               // the previous layer's output is complete and visible from here on
 
     const int total_tiles = p.n_blocks * p.n_img * p.tiles_y * p.tiles_x;
     const int slabs = p.slabs;
@@ -292,8 +294,8 @@ const char* launch_inst(const ConvLaunch& l, cudaStream_t stream) {
     static std::atomic<uint64_t> configured{0};  // per instantiation: devices with the shared-memory opt-in
     constexpr int smem = smem_bytes(BLOCK_N);
     if (!smem_opt_in(kfn, smem, configured)) return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
-    kfn<<<l.grid, eight_epilogue_warps(BLOCK_N, MODE, SPLIT) ? NUM_THREADS_8 : NUM_THREADS, smem, stream>>>(l.maps, l.p);
-    const cudaError_t e = cudaGetLastError();
+    const cudaError_t e = launch_kernel(kfn, dim3(l.grid), dim3(eight_epilogue_warps(BLOCK_N, MODE, SPLIT) ? NUM_THREADS_8 : NUM_THREADS),
+                                        smem, stream, l.maps, l.p);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -346,6 +348,31 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
         conv_halo_geometry(&t, &box_w, &box_h, &out_w, &out_h, &pool_w, &pool_h);
         tile_w = tile_h = t;
         block_n = d.n_total;
+    }
+    if (!l.halo && (d.mode == EPI_STORE || d.mode == EPI_STORE_POOL)) {
+        // Column-block width of the per-tap kernel. N = 256 is the efficient shape (an M128 x N256 MMA is tensor-bound,
+        // N = 128 / 64 are increasingly bound by the A-operand reads: ~128 / ~70 / ~51 cycles per K16 step, measured
+        // with tools/probe/mma_probe.cu), but a small frame gives a wide layer very few tiles: down4.conv.3 of ONE
+        // 256x256 pair is 2 pixel tiles x 4 column blocks = 8 CTAs on 148 SMs. Narrower blocks multiply the CTA count;
+        // pick the width with the smallest (waves x cycles per K step). Large frames keep 256. FI_BLOCK_N forces one.
+        const long long m_tiles = static_cast<long long>(d.N) * ((d.H + TILE_H - 1) / TILE_H) * ((d.W + TILE_W - 1) / TILE_W);
+        const int widths[3] = {256, 128, 64};
+        const double cycles[3] = {128.0, 70.0, 51.0};
+        const char* force = getenv("FI_BLOCK_N");
+        double best = 0;
+        for (int i = 0; i < 3; ++i) {
+            if (d.n_total % widths[i]) continue;
+            if (force && atoi(force) == widths[i]) {
+                block_n = widths[i];
+                break;
+            }
+            const long long tiles = m_tiles * (d.n_total / widths[i]);
+            const double est = static_cast<double>((tiles + num_sms - 1) / num_sms) * cycles[i];
+            if (best == 0 || est < best * 0.999) {
+                best = est;
+                block_n = widths[i];
+            }
+        }
     }
     ConvMaps& m = l.maps;
     if ((e = encode_nhwc(&m.a[0], d.src0, d.N, d.H, d.W, d.c0, box_w, box_h))) return e;

@@ -102,6 +102,8 @@ conv_gemm2_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams 
     cluster_sync_all();  // both CTAs' barriers exist before any remote signal can arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int per_img = p.tiles_y * p.tiles_x;
     const int pairs_per_nb = (p.n_img * per_img + 1) >> 1;
@@ -219,8 +221,7 @@ const char* launch_pair_inst(const ConvLaunch& l, cudaStream_t stream) {
     auto kfn = conv_gemm2_kernel<MODE, SPLIT>;
     static std::atomic<uint64_t> configured{0};
     if (!smem_opt_in(kfn, C2_SMEM, configured)) return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
-    kfn<<<l.grid, C2_THREADS, C2_SMEM, stream>>>(l.maps, l.p);
-    const cudaError_t e = cudaGetLastError();
+    const cudaError_t e = launch_kernel(kfn, dim3(l.grid), dim3(C2_THREADS), C2_SMEM, stream, l.maps, l.p);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

@@ -128,6 +128,8 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int total_tiles = p.n_img * p.tiles_y * p.tiles_x;
     const int slabs = p.slabs;
@@ -309,8 +311,8 @@ const char* launch_halo_inst(const ConvLaunch& l, cudaStream_t stream) {
     constexpr int smem = halo_smem_bytes(COUT, RESIDENT);
     static_assert(smem <= 232448, "halo kernel exceeds the 227 KB shared memory limit");
     if (!smem_opt_in(kfn, smem, configured)) return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
-    kfn<<<l.grid, SPLIT ? HALO_THREADS : HALO_THREADS_8, smem, stream>>>(l.maps, l.p);
-    const cudaError_t e = cudaGetLastError();
+    const cudaError_t e = launch_kernel(kfn, dim3(l.grid), dim3(SPLIT ? HALO_THREADS : HALO_THREADS_8), smem, stream,
+                                        l.maps, l.p);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

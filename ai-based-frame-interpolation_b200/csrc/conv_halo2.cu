@@ -125,6 +125,8 @@ conv_halo2_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams 
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int tiles = p.n_img * p.tiles_y * p.tiles_x;
     const int total = (tiles + 1) >> 1;
@@ -302,8 +304,8 @@ const char* launch_halo2_inst(const ConvLaunch& l, cudaStream_t stream) {
     auto kfn = conv_halo2_kernel<COUT, MODE, RESIDENT, SPLIT>;
     static std::atomic<uint64_t> configured{0};
     if (!smem_opt_in(kfn, H2_SMEM, configured)) return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
-    kfn<<<l.grid, SPLIT ? H2_THREADS : H2_THREADS_8, H2_SMEM, stream>>>(l.maps, l.p);
-    const cudaError_t e = cudaGetLastError();
+    const cudaError_t e = launch_kernel(kfn, dim3(l.grid), dim3(SPLIT ? H2_THREADS : H2_THREADS_8), H2_SMEM, stream,
+                                        l.maps, l.p);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

@@ -5,6 +5,8 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -13,6 +15,29 @@ namespace fi {
 // Host helper: cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel, and one process may
 // drive several GPUs (one fiNet + one worker thread per device). `done` is the per-instantiation bit mask of devices
 // that already have the opt-in; safe to call from several threads.
+// FI_PDL=0 turns programmatic dependent launch off (plain stream order), e.g. to A/B its effect.
+inline bool pdl_enabled() {
+    const char* e = getenv("FI_PDL");  // read per launch (tens of ns) so that tests can flip it
+    return e ? e[0] != '0' : true;
+}
+
+// Launch of a kernel that calls pdl_wait() before its first dependent memory access.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <class Kernel>
 inline bool smem_opt_in(Kernel kfn, int bytes, std::atomic<uint64_t>& done) {
     int dev = 0;
@@ -43,6 +68,16 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Kernels of the forward schedule are launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch_kernel
+// below): the next layer's CTAs may be scheduled onto SMs that the current layer has already vacated and run their
+// prologue (barrier init, TMEM allocation, descriptor prefetch) there. pdl_wait() blocks until the preceding grid has
+// COMPLETED and its memory is visible, so everything after it is ordered exactly as without PDL; nothing before it may
+// touch memory another kernel produces or consumes. pdl_launch_dependents() lets the grid after this one start its
+// own prologue early. Both are no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

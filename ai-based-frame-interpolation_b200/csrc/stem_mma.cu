@@ -114,6 +114,8 @@ stem_mma_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int per_img = p.tiles_y * p.tiles_x;
     const int total_tiles = p.N * per_img;
@@ -430,11 +432,11 @@ const char* launch_stem(const StemDesc& d, const CUtensorMap& map_b, const CUten
     if (d.is_u8) {
         auto k = stem_mma_kernel<CIN, true>;
         if (!smem_opt_in(k, smem, configured[1])) return "stem: cudaFuncSetAttribute failed";
-        k<<<grid, SM_THREADS, smem, stream>>>(map_b, map_out, map_out_lo, p);
+        launch_kernel(k, dim3(grid), dim3(SM_THREADS), smem, stream, map_b, map_out, map_out_lo, p);
     } else {
         auto k = stem_mma_kernel<CIN, false>;
         if (!smem_opt_in(k, smem, configured[0])) return "stem: cudaFuncSetAttribute failed";
-        k<<<grid, SM_THREADS, smem, stream>>>(map_b, map_out, map_out_lo, p);
+        launch_kernel(k, dim3(grid), dim3(SM_THREADS), smem, stream, map_b, map_out, map_out_lo, p);
     }
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
