@@ -5,6 +5,8 @@
 #include "conv_gemm.cuh"
 #include "train_kernels.cuh"
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges are no-ops unless a profiler is attached
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -136,6 +138,7 @@ struct fiNet {
     Plan& plan() { return plans.front(); }
     bool has_plan() const { return !plans.empty(); }
     void drop_plans() { plans.clear(); }
+    bool nvtx = false;  // FI_NVTX=1: one NVTX range per forward and per layer launch (named like the state-dict layer)
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;  // [call][step][2], resolved by fiNetGetProfile
     int prof_calls = 0;
@@ -574,10 +577,30 @@ fi::PlaneSrc to_src(const fiPlanes* p) {
     return s;
 }
 
-int set_device(int device) {
-    CUDA_TRY(cudaSetDevice(device));
-    return FI_OK;
-}
+// Every entry point that works on a handle switches to the handle's device for the duration of the call and puts the
+// caller's current device back on every exit path: a library must not leave cudaSetDevice side effects behind (torch's
+// "current device" IS the runtime's, so a leaked switch silently re-targets the caller's next "cuda" tensor).
+struct DeviceGuard {
+    int prev = -1;
+    int rc = FI_OK;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) {
+            const cudaError_t e = cudaSetDevice(device);
+            if (e != cudaSuccess) rc = fail(FI_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+        } else {
+            prev = -1;  // nothing to restore
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ON_DEVICE(device)              \
+    DeviceGuard _device_guard(device); \
+    if (_device_guard.rc) return _device_guard.rc
 
 }  // namespace
 
@@ -597,8 +620,7 @@ int fiNetCreate(fiNet** out, int device, int n_channels, int n_classes, int bili
         return fail(FI_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail(FI_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
-    int rc = set_device(device);
-    if (rc) return rc;
+    ON_DEVICE(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
@@ -611,6 +633,7 @@ int fiNetCreate(fiNet** out, int device, int n_channels, int n_classes, int bili
     net->bilinear = bilinear ? 1 : 0;
     net->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("FI_PLAN_CACHE")) net->max_plans = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char* e = getenv("FI_NVTX")) net->nvtx = e[0] == '1';
     *out = net;
     return FI_OK;
 }
@@ -629,7 +652,7 @@ int fiNetSetPrecision(fiNet* net, int precision) {
 
 int fiNetDestroy(fiNet* net) {
     if (!net) return FI_OK;
-    cudaSetDevice(net->device);
+    DeviceGuard guard(net->device);
     if (net->pin_in) cudaFreeHost(net->pin_in);
     if (net->pin_out) cudaFreeHost(net->pin_out);
     for (cudaEvent_t e : net->prof_events) cudaEventDestroy(e);
@@ -651,8 +674,8 @@ int fiNetDestroy(fiNet* net) {
 int fiNetLoadWeights(fiNet* net, const char* const* names, const float* const* data_host, const int64_t* numel,
                      int count) {
     if (!net || !names || !data_host || !numel) return fail(FI_ERR_INVALID, "null argument");
-    int rc = set_device(net->device);
-    if (rc) return rc;
+    ON_DEVICE(net->device);
+    int rc = FI_OK;
     StateDict sd;
     for (int i = 0; i < count; ++i) sd.m[names[i]] = {data_host[i], numel[i]};
     net->loaded = false;
@@ -711,7 +734,7 @@ int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dt
     if (in_dtype != FI_IN_F32 && in_dtype != FI_IN_U8) return fail(FI_ERR_INVALID, "unknown input dtype");
     int rc = check_planes(net, in0, in1);
     if (rc) return rc;
-    if ((rc = set_device(net->device))) return rc;
+    ON_DEVICE(net->device);
     if ((rc = build_plan(net, N, H, W))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Plan& pl = net->plan();
@@ -724,8 +747,21 @@ int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dt
         evs = net->prof_events.data() + base;
         ++net->prof_calls;
     }
+    struct NvtxScope {  // pops on every exit path (the launch macros return early on errors)
+        bool on;
+        NvtxScope(bool enable, const char* name) : on(enable) {
+            if (on) nvtxRangePushA(name);
+        }
+        ~NvtxScope() {
+            if (on) nvtxRangePop();
+        }
+    };
+    char fwd_name[64];
+    if (net->nvtx) snprintf(fwd_name, sizeof fwd_name, "fiNetForward %dx%dx%d", N, H, W);
+    NvtxScope fwd_range(net->nvtx, fwd_name);
     for (size_t i = 0; i < pl.steps.size(); ++i) {
         Step& s = pl.steps[i];
+        NvtxScope layer_range(net->nvtx, s.name);
         if (evs) CUDA_TRY(cudaEventRecord(evs[2 * i], st));
         if (s.kind == STEP_STEM) {
             fi::StemDesc d;
@@ -785,8 +821,8 @@ int fiNetGetProfile(fiNet* net, fiLaunchProfile* out, int capacity, int* count) 
     if (capacity < n) return fail(FI_ERR_INVALID, "profile buffer too small: need %d entries", n);
     if (net->prof_calls == 0 || net->prof_events.size() != static_cast<size_t>(2) * n * net->prof_calls)
         return fail(FI_ERR_STATE, "no profiled forward of the current shape has run");
-    int rc = set_device(net->device);
-    if (rc) return rc;
+    ON_DEVICE(net->device);
+    int rc = FI_OK;
     CUDA_TRY(cudaDeviceSynchronize());
     for (int i = 0; i < n; ++i) {
         const Step& s = pl.steps[i];
@@ -814,8 +850,8 @@ int fiNetInterpolateHostU8(fiNet* net, const uint8_t* frame1_host, const uint8_t
     if (2 * channels_per_frame != net->n_channels)
         return fail(FI_ERR_INVALID, "2 x %d channels per frame != n_channels %d", channels_per_frame, net->n_channels);
     if (N <= 0 || H <= 0 || W <= 0) return fail(FI_ERR_INVALID, "empty batch or image");
-    int rc = set_device(net->device);
-    if (rc) return rc;
+    ON_DEVICE(net->device);
+    int rc = FI_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t frame_bytes = static_cast<size_t>(N) * channels_per_frame * H * W;
     const size_t out_bytes = static_cast<size_t>(N) * net->n_classes * H * W;
@@ -865,8 +901,8 @@ int fiNetInterpolateClipHostU8(fiNet* net, const uint8_t* frames_host, int n_fra
     if (2 * channels_per_frame != net->n_channels)
         return fail(FI_ERR_INVALID, "2 x %d channels per frame != n_channels %d", channels_per_frame, net->n_channels);
     if (n_frames < 2 || H <= 0 || W <= 0 || pairs_per_batch < 1) return fail(FI_ERR_INVALID, "empty clip or batch");
-    int rc = set_device(net->device);
-    if (rc) return rc;
+    ON_DEVICE(net->device);
+    int rc = FI_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int B = pairs_per_batch;
     const size_t frame_bytes = static_cast<size_t>(channels_per_frame) * H * W;
@@ -942,8 +978,8 @@ int fiNetInterpolateClipHostU8(fiNet* net, const uint8_t* frames_host, int n_fra
 int fiNetForwardCost(fiNet* net, int N, int H, int W, double* flops, int* launches) {
     if (!net) return fail(FI_ERR_INVALID, "net is null");
     if (!net->loaded) return fail(FI_ERR_STATE, "fiNetLoadWeights has not been called");
-    int rc = set_device(net->device);
-    if (rc) return rc;
+    ON_DEVICE(net->device);
+    int rc = FI_OK;
     if ((rc = build_plan(net, N, H, W))) return rc;
     if (flops) *flops = net->plan().flops * N;
     if (launches) *launches = static_cast<int>(net->plan().steps.size());
@@ -971,8 +1007,8 @@ int fiNetReadActivation(fiNet* net, const char* name, float* out_host, int64_t c
     const Act& a = it->second;
     const int64_t n = static_cast<int64_t>(pl.last_n) * a.C * a.H * a.W;
     if (capacity < n) return fail(FI_ERR_INVALID, "buffer too small: need %lld floats", static_cast<long long>(n));
-    int rc = set_device(net->device);
-    if (rc) return rc;
+    ON_DEVICE(net->device);
+    int rc = FI_OK;
     std::vector<uint16_t> raw(static_cast<size_t>(n)), raw_lo;
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(raw.data(), static_cast<char*>(pl.arena.p) + a.off, raw.size() * 2, cudaMemcpyDeviceToHost));

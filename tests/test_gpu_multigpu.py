@@ -53,6 +53,9 @@ def test_second_device_in_one_process(two_gpus, checkpoint):
         net.load_state_dict(sd)
         outs.append(net.interpolate_clip_host_u8(fr, 2))
         net.close()
+        # the library restores the caller's current device on every exit path (a leaked cudaSetDevice would re-target
+        # the caller's next "cuda" tensor / FrameInterpolator(..., "cuda"))
+        assert torch.cuda.current_device() == 0
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
     ref = O.postprocess(O.unet_forward(sd, torch.cat([O.preprocess_u8(fr[:-1]), O.preprocess_u8(fr[1:])], 1)))
     assert np.abs(outs[1].astype(int) - ref.astype(int)).max() <= 6

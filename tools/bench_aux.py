@@ -23,6 +23,9 @@ if pk.exists():
 
 
 def timed(fn, iters=20, warm=5):
+    import os
+    iters = int(os.environ.get("FI_AUX_ITERS", iters))   # ncu captures: FI_AUX_ITERS=1 FI_AUX_WARM=0 (one launch each)
+    warm = int(os.environ.get("FI_AUX_WARM", warm))
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
