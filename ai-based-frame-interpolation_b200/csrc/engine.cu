@@ -1222,6 +1222,12 @@ int fiWgrad(const void* dz, const void* x0, int c0, const void* x1, int c1, int 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     TRAIN_CALL(fi::wgrad_launch(dz, x0, c0, x1, c1, N, H, W, cout, dW, sms, ST));
 }
+int fiWgradPointwise(const void* dz, const void* x, int cin, int N, int H, int W, int cout, float* dW, void* stream) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    TRAIN_CALL(fi::wgrad_launch(dz, x, cin, nullptr, 0, N, H, W, cout, dW, sms, ST, 1));
+}
 int fiBnFinalize(const float* sum, const float* sumsq, int C, int64_t P, float eps, float momentum, const float* gamma,
                  const float* beta, float* mean, float* rstd, float* scale, float* shift, float* running_mean,
                  float* running_var, void* stream) {

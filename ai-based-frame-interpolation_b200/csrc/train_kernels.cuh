@@ -39,6 +39,6 @@ const char* pack_conv_launch(const float* w, int co, int ci, void* fwd, void* bw
 // wgrad_gemm.cu: dW[tap][co][ci] += sum_q dz[q][co] * x[q + tap][ci], x = channel concat of x0 | x1, all bf16 NHWC
 // (tcgen05 GEMM over the pixel dimension with MN-major operands straight from NHWC, split-K, fp32 atomics)
 const char* wgrad_launch(const void* dz, const void* x0, int c0, const void* x1, int c1, int N, int H, int W, int cout,
-                         float* dW, int num_sms, cudaStream_t st);
+                         float* dW, int num_sms, cudaStream_t st, int taps = 9);
 
 }  // namespace fi

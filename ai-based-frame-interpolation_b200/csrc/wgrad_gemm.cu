@@ -32,13 +32,14 @@ struct WgradParams {
     int cout, cin, c0;                          // c0 = channels of the first x source (concat layers have two)
     int co_blocks, ci_blocks;                   // 64-channel blocks
     int stacked;                                // 1: cout == 64, rows = two column shifts of dz
+    int taps;                                   // 9 (conv3x3) or 1 (pointwise: dW[co][ci] = sum_q dz[q][co] x[q][ci])
     int m_tiles, n_tiles;
     int k_chunks, chunk_slabs, total_slabs;     // split of the pixel slabs over work items
     int tiles_w, tiles_h, bw, bh;               // a slab is a bw x bh pixel box of one image
     float* dW;
 };
 
-__host__ __device__ constexpr int wg_stages(int n_blocks) { return n_blocks == 4 ? 4 : 5; }
+__host__ __device__ constexpr int wg_stages(int n_blocks) { return n_blocks == 4 ? 4 : (n_blocks == 3 ? 5 : 6); }
 __host__ __device__ constexpr int wg_smem(int n_blocks) {
     return 1024 + wg_stages(n_blocks) * (WG_A_BYTES + n_blocks * WG_BLOCK_BYTES) + 256;
 }
@@ -58,7 +59,9 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 __device__ __forceinline__ void decode_col_block(const WgradParams& p, int nb, int& dy, int& dx, int& cb) {
     const int sidx = nb / p.ci_blocks;
     cb = nb - sidx * p.ci_blocks;
-    if (p.stacked) {
+    if (p.taps == 1) {
+        dy = dx = 0;
+    } else if (p.stacked) {
         dy = sidx / 2 - 1;
         dx = sidx % 2 - 1;   // -1, 0
     } else {
@@ -208,7 +211,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
                 decode_col_block(p, nt * N_BLOCKS + (c >> 1), dy, dx, cb);
                 const bool duplicate = adx == 1 && dx == -1;               // tap.dx = 0 is produced by (0, 0)
                 if (co < p.cout && !duplicate) {
-                    const int tap = (dy + 1) * 3 + (dx + adx + 1);
+                    const int tap = p.taps == 1 ? 0 : (dy + 1) * 3 + (dx + adx + 1);
                     float* out = p.dW + (static_cast<size_t>(tap) * p.cout + co) * p.cin + cb * 64 + (c & 1) * 32;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -253,8 +256,9 @@ const char* encode_pixels(CUtensorMap* map, const void* base, int N, int H, int 
 }  // namespace
 
 const char* wgrad_launch(const void* dz, const void* x0, int c0, const void* x1, int c1, int N, int H, int W, int cout,
-                         float* dW, int num_sms, cudaStream_t st) {
+                         float* dW, int num_sms, cudaStream_t st, int taps) {
     if (!dz || !x0 || !dW || (c1 > 0 && !x1)) return "wgrad: null operand";
+    if (taps != 9 && taps != 1) return "wgrad: taps must be 9 or 1";
     if (N <= 0 || H <= 0 || W <= 0) return "wgrad: empty shape";
     if (c0 <= 0 || c0 % 64 || c1 < 0 || c1 % 64 || cout <= 0 || cout % 64)
         return "wgrad: channel counts must be multiples of 64";
@@ -267,10 +271,12 @@ const char* wgrad_launch(const void* dz, const void* x0, int c0, const void* x1,
     p.dW = dW;
     p.co_blocks = cout / 64;
     p.ci_blocks = cin / 64;
-    p.stacked = cout == 64 ? 1 : 0;
+    p.taps = taps;
+    p.stacked = (cout == 64 && taps == 9) ? 1 : 0;
     p.m_tiles = p.stacked ? 1 : (p.co_blocks + 1) / 2;
-    const int col_blocks = (p.stacked ? 6 : 9) * p.ci_blocks;      // always a multiple of 3
-    const int n_blocks = col_blocks % 4 == 0 ? 4 : 3;
+    const int col_blocks = (taps == 1 ? 1 : (p.stacked ? 6 : 9)) * p.ci_blocks;   // 3x3: always a multiple of 3
+    const int n_blocks = col_blocks % 4 == 0 ? 4 : (col_blocks % 3 == 0 ? 3 : (col_blocks % 2 == 0 ? 2 : 1));
+    if (n_blocks == 1) return "wgrad: pointwise mode needs an even number of 64-channel input blocks";
     p.n_tiles = col_blocks / n_blocks;
     // pixel slab: the 64-pixel box shape that wastes the fewest out-of-bounds pixels
     long long best = -1;
@@ -300,7 +306,8 @@ const char* wgrad_launch(const void* dz, const void* x0, int c0, const void* x1,
     if ((e = encode_pixels(&maps[2], c1 > 0 ? x1 : x0, N, H, W, c1 > 0 ? c1 : c0, p.bw, p.bh))) return e;
     const long long total = static_cast<long long>(base_items) * p.k_chunks;
     const int grid = static_cast<int>(total < num_sms ? total : num_sms);
-    return n_blocks == 4 ? launch_wgrad<4>(maps, p, grid, st) : launch_wgrad<3>(maps, p, grid, st);
+    return n_blocks == 4 ? launch_wgrad<4>(maps, p, grid, st)
+                         : (n_blocks == 3 ? launch_wgrad<3>(maps, p, grid, st) : launch_wgrad<2>(maps, p, grid, st));
 }
 
 }  // namespace fi

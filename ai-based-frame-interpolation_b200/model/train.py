@@ -10,7 +10,9 @@ What runs where
 PyTorch holds the fp32 master parameters (the module's own nn.Parameters), the flat gradient / Adam buffers and does
 per-channel vector arithmetic of BatchNorm (C-sized tensors); every per-pixel FLOP is in the library.
 
-Scope: FrameInterpolationUNet / UNet with bilinear=True (what the reference's train.py builds, model/train.py:299),
+Scope: FrameInterpolationUNet / UNet with either decoder — bilinear=True (what the reference's train.py builds,
+model/train.py:299) or the class default ConvTranspose2d (model/unet.py:43: forward = the EPI_CONVT GEMM, data gradient =
+a per-pixel GEMM on the output gradient viewed as [N,h,w,(ky,kx,co)], weight gradient = fiWgradPointwise) —
 H and W multiples of 16 (the reference trains at 256x256, model/train.py:138), bf16 activations and activation
 gradients, fp32 master parameters / gradients / Adam state. Loss: criterion=None is the fused MSE kernel (BASELINE
 config 5); a CombinedLoss instance (the reference's 0.5*MSE + 0.5*(1-SSIM), model/train.py:75-87) is the fused
@@ -70,8 +72,10 @@ class TrainStep:
         self._graphs, self._eager_steps = {}, 0
         self.keep_activations = False
         unet = model.unet if isinstance(model, FrameInterpolationUNet) else model
-        if not isinstance(unet, UNet) or not unet.bilinear:
-            raise E.FiError("the B200 training step covers the bilinear UNet (what reference train.py builds)")
+        if not isinstance(unet, UNet):
+            raise E.FiError("TrainStep needs a UNet / FrameInterpolationUNet")
+        # decoder variant: nn.Upsample (what reference train.py:299 builds) or the class default ConvTranspose2d
+        self.convt = not unet.bilinear
         self.model, self.unet = model, unet
         self.lr, self.betas, self.eps, self.step_count = lr, betas, eps, 0
         p0 = next(model.parameters())
@@ -112,6 +116,7 @@ class TrainStep:
             L.append(_Layer(f"up{i}.0", blk[0], blk[1], skips[i - 1], f"up{i}.up"))
             L.append(_Layer(f"up{i}.3", blk[3], blk[4], f"up{i}.0"))
         self.layers = L
+        self.up_mods = {f"up{i}.0": up.up for i, up in enumerate((u.up1, u.up2, u.up3, u.up4), 1)}
         self.lib = E.lib()
         self._side = torch.cuda.Stream(device=self.device)
         self._sync_replicas()
@@ -169,17 +174,20 @@ class TrainStep:
         self.lr, self.betas, self.eps = g["lr"], tuple(g["betas"]), g["eps"]
 
     # ------------------------------------------------------------------------------------------------ helpers
-    def _conv(self, src, wpack, n_total, src1=None):
-        """bf16 NHWC conv3x3 (no bias, no ReLU) through the tcgen05 kernels."""
+    def _conv(self, src, wpack, n_total, src1=None, taps=9, mode=E.EPI_STORE, bias=None):
+        """bf16 NHWC conv3x3 (no bias, no ReLU) through the tcgen05 kernels. taps=1: a per-pixel GEMM (the transposed
+        conv's data gradient); mode=EPI_CONVT: ConvTranspose2d(k=2, s=2) with its bias, n_total = 4*Cout columns ordered
+        (ky, kx, co), output [N, 2H, 2W, Cout]."""
         n, h, w, c0 = src.shape
         d = E.ConvDesc()
         d.src0, d.c0, d.N, d.H, d.W = src.data_ptr(), c0, n, h, w
         if src1 is not None:
             d.src1, d.c1, d.h1, d.w1 = src1.data_ptr(), src1.shape[3], src1.shape[1], src1.shape[2]
-        dst = torch.empty((n, h, w, n_total), dtype=torch.bfloat16, device=self.device)
-        zero = self._zero_bias(n_total)
-        d.wpack, d.bias, d.n_total, d.taps, d.mode, d.relu, d.dst = (wpack.data_ptr(), zero.data_ptr(), n_total, 9,
-                                                                     E.EPI_STORE, 0, dst.data_ptr())
+        shape = (n, 2 * h, 2 * w, n_total // 4) if mode == E.EPI_CONVT else (n, h, w, n_total)
+        dst = torch.empty(shape, dtype=torch.bfloat16, device=self.device)
+        b = bias if bias is not None else self._zero_bias(n_total)
+        d.wpack, d.bias, d.n_total, d.taps, d.mode, d.relu, d.dst = (wpack.data_ptr(), b.data_ptr(), n_total, taps,
+                                                                     mode, 0, dst.data_ptr())
         E.check(self.lib.fiConvGemm(C.byref(d), E.current_stream()))
         return dst
 
@@ -314,8 +322,18 @@ class TrainStep:
                     if l.src1 is not None:
                         lo = acts[self.layers[self.layers.index(l) - 1].name]
                         ln, lh, lw, lc = lo.shape
-                        up = torch.empty((ln, 2 * lh, 2 * lw, lc), dtype=torch.bfloat16, device=self.device)
-                        E.check(lib.fiUpsample2x(_ptr(lo), _ptr(up), ln, lh, lw, lc, st()))
+                        if self.convt:
+                            # nn.ConvTranspose2d(lc, lc/2, 2, 2) (reference model/unet.py:43): weight [ci, co, ky, kx]
+                            # -> GEMM rows (ky, kx, co) for the forward, rows ci / K = (ky, kx, co) for the data gradient
+                            tw = self.up_mods[l.name].weight.detach()
+                            cup = tw.shape[1]
+                            fwd_t = tw.permute(2, 3, 1, 0).reshape(4 * cup, lc).to(torch.bfloat16).contiguous()
+                            packs[l.src1] = tw.permute(0, 2, 3, 1).reshape(lc, 4 * cup).to(torch.bfloat16).contiguous()
+                            bias4 = self.up_mods[l.name].bias.detach().float().repeat(4).contiguous()
+                            up = self._conv(lo, fwd_t, 4 * cup, taps=1, mode=E.EPI_CONVT, bias=bias4)
+                        else:
+                            up = torch.empty((ln, 2 * lh, 2 * lw, lc), dtype=torch.bfloat16, device=self.device)
+                            E.check(lib.fiUpsample2x(_ptr(lo), _ptr(up), ln, lh, lw, lc, st()))
                         acts[l.src1] = up
                     z = self._conv(acts[l.src], packs[l.name][0], l.cout, acts.get(l.src1) if l.src1 else None)
                 zs[l.name] = z
@@ -392,8 +410,25 @@ class TrainStep:
                     d_up = self._conv(dz, bwd[c0:], l.cin - c0)
                     below = self.layers[self.layers.index(l) - 1].name   # the tensor that was upsampled
                     bn_, bh, bw_, bc = acts[below].shape
-                    d_lo = torch.empty_like(acts[below])
-                    E.check(lib.fiUpsample2xBackward(_ptr(d_up), _ptr(d_lo), bn_, bh, bw_, bc, st()))
+                    if self.convt:
+                        # ConvTranspose2d backward. Per low-resolution pixel the output gradient is a vector over
+                        # (ky, kx, co): d_lo = that vector times W (a per-pixel GEMM, K = 4*Cout), dW = sum over pixels
+                        # of the outer product with the layer input (fiWgradPointwise), dbias = per-channel sum.
+                        tmod = self.up_mods[l.name]
+                        cup = d_up.shape[3]
+                        d_s2d = d_up.view(bn_, bh, 2, bw_, 2, cup).permute(0, 1, 3, 2, 4, 5).contiguous().view(
+                            bn_, bh, bw_, 4 * cup)
+                        d_lo = self._conv(d_s2d, packs[l.src1], bc, taps=1)
+                        sumsq = torch.zeros(cup, dtype=torch.float32, device=self.device)
+                        E.check(lib.fiBnStats(_ptr(d_up), bn_ * bh * bw_ * 4, cup, _ptr(self.grad_view[tmod.bias]),
+                                              _ptr(sumsq), st()))
+                        dwt = torch.zeros((4 * cup, bc), dtype=torch.float32, device=self.device)
+                        E.check(lib.fiWgradPointwise(_ptr(d_s2d), _ptr(acts[below]), bc, bn_, bh, bw_, 4 * cup, _ptr(dwt),
+                                                     st()))
+                        self.grad_view[tmod.weight].add_(dwt.view(2, 2, cup, bc).permute(3, 2, 0, 1))
+                    else:
+                        d_lo = torch.empty_like(acts[below])
+                        E.check(lib.fiUpsample2xBackward(_ptr(d_up), _ptr(d_lo), bn_, bh, bw_, bc, st()))
                     grads[below] = d_lo
                     grads["skip:" + l.src] = d_src       # joins the encoder-side gradient at the pool backward
                 elif l.src.startswith("pool"):

@@ -230,6 +230,10 @@ int fiUpsample2xBackward(const void* d_up, void* d_lo, int N, int h, int w, int 
 int fiWgrad(const void* dz, const void* x0, int c0, const void* x1, int c1, int N, int H, int W, int cout, float* dW,
             void* stream);
 int fiStemWgrad(const void* dz, const float* x, int N, int H, int W, int cin, float* dW, void* stream);
+/* The same GEMM over the pixel dimension without taps: dW[cout][cin] (fp32, ACCUMULATED into) = sum over the N*H*W
+ * pixels q of dz[q][cout] * x[q][cin]. This is the weight gradient of nn.ConvTranspose2d(k=2, s=2) (Up, model/unet.py:43)
+ * once its output gradient is viewed per low-resolution pixel as [N,h,w,(ky,kx,co)] (cout = 4*Cout); cin/64 even. */
+int fiWgradPointwise(const void* dz, const void* x, int cin, int N, int H, int W, int cout, float* dW, void* stream);
 /* Batch sums -> mean, rstd = 1/sqrt(var + eps), scale = gamma * rstd, shift = beta - mean * scale (C floats each), and
  * the nn.BatchNorm2d running estimates updated in place (momentum, unbiased variance; either may be NULL). */
 int fiBnFinalize(const float* sum, const float* sumsq, int C, int64_t P, float eps, float momentum, const float* gamma,

@@ -41,9 +41,12 @@ def main():
     out["loss_value"], out["loss_grad"] = np.float64(loss.item()), pred.grad.numpy()
     out["ssim_loss_value"] = np.float64(ref_train.SSIMLoss()(pred.detach(), target).item())
     # ---- one training step, both criteria
-    for tag, crit in (("combined", ref_train.CombinedLoss()), ("mse", nn.MSELoss())):
+    # "mse_convt": the class-default ConvTranspose2d decoder (model/unet.py:99), which reference train.py never builds but
+    # its model file defines; same recipe
+    for tag, crit, bilinear in (("combined", ref_train.CombinedLoss(), True), ("mse", nn.MSELoss(), True),
+                                ("mse_convt", nn.MSELoss(), False)):
         torch.manual_seed(0)
-        model = ref_unet.FrameInterpolationUNet(bilinear=True).train()
+        model = ref_unet.FrameInterpolationUNet(bilinear=bilinear).train()
         opt = torch.optim.Adam(model.parameters(), lr=1e-4)
         f0, f1, gt = batch(21, 2, 32, 32)
         opt.zero_grad()
@@ -55,14 +58,17 @@ def main():
         out[f"{tag}_loss"] = np.float64(l.item())
         out[f"{tag}_output"] = y.detach().numpy()
         out[f"{tag}_grad_norms"] = np.array([grads[k].norm().item() for k in grads], dtype=np.float64)
-        for k in ("unet.outc.conv.weight", "unet.outc.conv.bias", "unet.up4.conv.double_conv.4.weight",
-                  "unet.up4.conv.double_conv.4.bias", "unet.up4.conv.double_conv.3.weight"):
+        keys = ["unet.outc.conv.weight", "unet.outc.conv.bias", "unet.up4.conv.double_conv.4.weight",
+                "unet.up4.conv.double_conv.4.bias", "unet.up4.conv.double_conv.3.weight"]
+        if not bilinear:
+            keys += ["unet.up4.up.weight", "unet.up4.up.bias"]
+        for k in keys:
             out[f"{tag}_grad:{k}"] = grads[k].numpy()
         sd = model.state_dict()
         out[f"{tag}_after:unet.outc.conv.weight"] = sd["unet.outc.conv.weight"].numpy()
         out[f"{tag}_after:unet.inc.double_conv.1.running_mean"] = sd["unet.inc.double_conv.1.running_mean"].numpy()
         out[f"{tag}_after:unet.inc.double_conv.1.running_var"] = sd["unet.inc.double_conv.1.running_var"].numpy()
-    out["param_names"] = np.array([k for k, _ in model.named_parameters()])
+        out[f"{tag}_param_names"] = np.array([k for k, _ in model.named_parameters()])
     path = ROOT / "tests" / "golden" / "train_golden.npz"
     np.savez_compressed(path, **out)
     print(f"wrote {path} ({path.stat().st_size} bytes)")

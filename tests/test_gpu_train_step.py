@@ -28,7 +28,7 @@ class _RoundBf16(torch.autograd.Function):
 
 
 def ref_forward_train(model, x, emulate_bf16=False, training=True):
-    """The reference network's forward (model/unet.py:84-95, bilinear=True) in training mode, plain torch ops.
+    """The reference network's forward (model/unet.py:84-95, either decoder) in training mode, plain torch ops.
     emulate_bf16=True rounds weights, pre-BN outputs, activations and their gradients to bf16 the way any bf16
     training step stores them: the distance between the two torch results is the noise floor of the precision."""
     u = model.unet
@@ -48,14 +48,17 @@ def ref_forward_train(model, x, emulate_bf16=False, training=True):
         feats.append(dconv(d.maxpool_conv[1], F.max_pool2d(feats[-1], 2)))
     y = feats[4]
     for i, up in enumerate((u.up1, u.up2, u.up3, u.up4)):
-        y = R(F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=True))
+        if isinstance(up.up, nn.ConvTranspose2d):   # class default decoder, model/unet.py:43
+            y = R(F.conv_transpose2d(y, R(up.up.weight), up.up.bias, stride=2))
+        else:
+            y = R(F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=True))
         y = dconv(up.conv, torch.cat([feats[3 - i], y], 1))
     return u.outc.conv(y)
 
 
-def make_model(seed):
+def make_model(seed, bilinear=True):
     torch.manual_seed(seed)
-    m = FrameInterpolationUNet(bilinear=True)
+    m = FrameInterpolationUNet(bilinear=bilinear)
     g = torch.Generator().manual_seed(seed + 1)
     for mod in m.modules():  # non-trivial affine parameters so that their gradients are exercised
         if isinstance(mod, nn.BatchNorm2d):
@@ -64,8 +67,9 @@ def make_model(seed):
     return m
 
 
+@pytest.mark.parametrize("bilinear", [True, False], ids=["bilinear", "convt"])
 @pytest.mark.parametrize("n,h,w", [(2, 32, 32), (3, 48, 64)])
-def test_gradients_match_autograd(cuda_device, n, h, w):
+def test_gradients_match_autograd(cuda_device, n, h, w, bilinear):
     """Loss, output, every parameter gradient and the BatchNorm running statistics against fp32 torch autograd.
 
     The step stores activations and activation gradients in bf16. Through 18 BatchNorm+ReLU stages that rounding
@@ -73,7 +77,7 @@ def test_gradients_match_autograd(cuda_device, n, h, w):
     to ~50 % relative L2 on the first layers' gradients at random initialisation). The bar is therefore the noise
     floor itself: per tensor, our distance to fp32 autograd must not exceed 1.5x the distance of a torch emulation
     of the same bf16 stores (+0.03). The kernels on their own are held to 1 bf16 ulp in test_gpu_train_kernels.py."""
-    ref = make_model(0).train()
+    ref = make_model(0, bilinear).train()
     emu = copy.deepcopy(ref)
     ours = copy.deepcopy(ref).to(cuda_device).train()
     g = torch.Generator().manual_seed(5)
@@ -107,10 +111,11 @@ def test_gradients_match_autograd(cuda_device, n, h, w):
             assert int(b) == 1
 
 
-def test_adam_steps_follow_torch(cuda_device):
+@pytest.mark.parametrize("bilinear", [True, False], ids=["bilinear", "convt"])
+def test_adam_steps_follow_torch(cuda_device, bilinear):
     """The optimiser: after one step every parameter equals torch.optim.Adam applied to OUR gradient (exact check of
     the update), and three steps reduce the loss along the torch trajectory (within the bf16 drift)."""
-    ref = make_model(3).train()
+    ref = make_model(3, bilinear).train()
     ours = copy.deepcopy(ref).to(cuda_device).train()
     shadow = copy.deepcopy(ref)
     opt = torch.optim.Adam(ref.parameters(), lr=1e-4)
@@ -145,7 +150,7 @@ def test_adam_steps_follow_torch(cuda_device):
     assert (y.cpu() - y_ref).abs().max() < 0.25   # parameters differ by the drift above; same function family
 
 
-@pytest.mark.parametrize("tag", ["mse", "combined"])
+@pytest.mark.parametrize("tag", ["mse", "combined", "mse_convt"])
 def test_one_step_against_reference_golden(cuda_device, tag):
     """One optimisation step of the UNMODIFIED reference (tests/golden/train_golden.npz, made by
     oracle/make_train_golden.py: default init seed 0, batch 2x32x32, Adam lr 1e-4) — loss, output, the gradients next
@@ -155,7 +160,8 @@ def test_one_step_against_reference_golden(cuda_device, tag):
     from model.train import CombinedLoss
     gold = np.load(os.path.join(GOLDEN_DIR, "train_golden.npz"))
     torch.manual_seed(0)
-    model = FrameInterpolationUNet(bilinear=True).to(cuda_device).train()
+    model = FrameInterpolationUNet(bilinear=tag != "mse_convt").to(cuda_device).train()
+    assert [k for k, _ in model.named_parameters()] == list(gold[f"{tag}_param_names"])
     g = torch.Generator().manual_seed(21)
     f0, f1 = torch.rand(2, 1, 32, 32, generator=g), torch.rand(2, 1, 32, 32, generator=g)
     gt = ((f0 + f1) / 2 + 0.05 * torch.randn(2, 1, 32, 32, generator=g)).clamp(0, 1)
@@ -166,7 +172,7 @@ def test_one_step_against_reference_golden(cuda_device, tag):
     assert ((step.last_output.cpu() - out_ref).norm() / out_ref.norm()).item() < 0.08
     params = dict(model.named_parameters())
     for key in gold.files:
-        if key.startswith(f"{tag}_grad:"):
+        if key.startswith(f"{tag}_grad:"):   # "mse_grad:" does not prefix "mse_convt_grad:"
             name = key.split(":", 1)[1]
             g_ref = torch.from_numpy(gold[key])
             rel = ((step.grad_view[params[name]].cpu() - g_ref).norm() / g_ref.norm()).item()
@@ -180,8 +186,9 @@ def test_one_step_against_reference_golden(cuda_device, tag):
                            gold[f"{tag}_after:unet.inc.double_conv.1.{k}"], rtol=2e-2, atol=2e-3)
 
 
-@pytest.mark.parametrize("criterion", ["mse", "combined"])
-def test_cuda_graph_replay_matches_eager(cuda_device, criterion):
+@pytest.mark.parametrize("criterion,bilinear", [("mse", True), ("combined", True), ("mse", False)],
+                         ids=["mse", "combined", "mse-convt"])
+def test_cuda_graph_replay_matches_eager(cuda_device, criterion, bilinear):
     """cuda_graph=True captures the step after two eager ones; replayed steps follow the eager trajectory, and the
     learning rate / step count reach the Adam kernel through device memory (lr = 0 after capture freezes the weights).
 
@@ -190,7 +197,7 @@ def test_cuda_graph_replay_matches_eager(cuda_device, criterion):
     so trajectories are compared loosely (25 %), the first step (same starting state) to 1 %."""
     from model.train import CombinedLoss
     crit = (lambda: CombinedLoss()) if criterion == "combined" else (lambda: None)
-    eager_model = make_model(7).to(cuda_device).train()
+    eager_model = make_model(7, bilinear).to(cuda_device).train()
     graph_model = copy.deepcopy(eager_model)
     eager = TrainStep(eager_model, lr=1e-4, criterion=crit())
     graphed = TrainStep(graph_model, lr=1e-4, criterion=crit(), cuda_graph=True)
