@@ -120,9 +120,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
     pdl_launch_dependents();  // the next layer may run its prologue on SMs this grid vacates
     pdl_wait();               // the previous layer's output is complete and visible from here on
 
-    const int total_tiles = p.n_blocks * p.n_img * p.tiles_y * p.tiles_x;
+    // work item = (output tile, K split): ksplit CTAs share a tile, each reducing a contiguous range of the taps
+    const int ksplit = p.ksplit;
+    const int total_tiles = p.n_blocks * p.n_img * p.tiles_y * p.tiles_x * ksplit;
     const int slabs = p.slabs;
-    const int k_iters = p.taps * slabs;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (warp converged, one lane issues)
@@ -130,8 +131,9 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile(t, p);
-                for (int tap = 0; tap < p.taps; ++tap) {
+                const int tile = t / ksplit, ks = t - tile * ksplit;
+                const TileCoord tc = decode_tile(tile, p);
+                for (int tap = ks * p.taps / ksplit; tap < (ks + 1) * p.taps / ksplit; ++tap) {
                     const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
                     const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
                     int seg = 0, left = p.seg_slabs[0];
@@ -166,6 +168,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
             uint32_t phase = 0;
             int it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int ks = t % ksplit;
+                const int k_iters = ((ks + 1) * p.taps / ksplit - ks * p.taps / ksplit) * slabs;
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
@@ -203,16 +207,60 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKernelParams p
         int buf = 0;
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-            const TileCoord tc = decode_tile(t, p);
+            const int tile = t / ksplit, ks = t - tile * ksplit;
+            const TileCoord tc = decode_tile(tile, p);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+            if (ksplit == 1) {
 #pragma unroll 1
-            for (int c = set; c < BLOCK_N / 64; c += EPI_SETS) {
-                epilogue_chunk_8x16<BLOCK_N, MODE, SPLIT, !EIGHT>(maps, p, EpiTile{tc.nb, tc.img, tc.y0, tc.x0}, taddr, c,
-                                                                   q, lane, my_stage, my_pool, buf, true);
+                for (int c = set; c < BLOCK_N / 64; c += EPI_SETS) {
+                    epilogue_chunk_8x16<BLOCK_N, MODE, SPLIT, !EIGHT>(maps, p, EpiTile{tc.nb, tc.img, tc.y0, tc.x0}, taddr,
+                                                                       c, q, lane, my_stage, my_pool, buf, true);
+                }
+            }
+            if constexpr (!SPLIT && (MODE == EPI_STORE || MODE == EPI_STORE_POOL)) {
+                if (ksplit > 1) {
+                    // Split K: park this CTA's partial rows (warp q owns accumulator rows 32q..32q+31) in global
+                    // memory; the last of the ksplit warps to arrive sums all partials and runs the real epilogue.
+                    const size_t part = static_cast<size_t>(BLOCK_M) * BLOCK_N;    // floats per (tile, split)
+                    float* mine = p.split_ws + (static_cast<size_t>(tile) * ksplit + ks) * part +
+                                  static_cast<size_t>(q * 32 + lane) * BLOCK_N;
+#pragma unroll 1
+                    for (int c = set; c < BLOCK_N / 64; c += EPI_SETS) {
+                        uint32_t v[32];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            tmem_ld_32x32b_x32(taddr + c * 64 + 32 * h, v);
+                            tmem_ld_wait();
+                            float4* dst4 = reinterpret_cast<float4*>(mine + c * 64 + 32 * h);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                __stcg(dst4 + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                        }
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    unsigned int arrived = 0;
+                    unsigned int* cnt = p.split_cnt + (static_cast<size_t>(tile) * 4 + q) * EPI_SETS + set;
+                    if (lane == 0) arrived = atomicAdd(cnt, 1u);
+                    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+                    if (arrived == static_cast<unsigned int>(ksplit - 1)) {
+                        if (lane == 0) *cnt = 0u;   // left zero for the next launch that uses the scratch
+                        __threadfence();
+                        const float* first = p.split_ws + static_cast<size_t>(tile) * ksplit * part +
+                                             static_cast<size_t>(q * 32 + lane) * BLOCK_N;
+#pragma unroll 1
+                        for (int c = set; c < BLOCK_N / 64; c += EPI_SETS) {
+                            epilogue_chunk_8x16<BLOCK_N, MODE, SPLIT, !EIGHT>(maps, p, EpiTile{tc.nb, tc.img, tc.y0, tc.x0},
+                                                                               taddr, c, q, lane, my_stage, my_pool, buf,
+                                                                               true, first + c * 64, ksplit, part);
+                        }
+                    }
+                }
             }
             // All TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back to the MMA warp.
             tc_fence_before();
@@ -350,15 +398,17 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
         block_n = d.n_total;
     }
     if (!l.halo && (d.mode == EPI_STORE || d.mode == EPI_STORE_POOL)) {
-        // Column-block width of the per-tap kernel. N = 256 is the efficient shape (an M128 x N256 MMA is tensor-bound,
-        // N = 128 / 64 are increasingly bound by the A-operand reads: ~128 / ~70 / ~51 cycles per K16 step, measured
-        // with tools/probe/mma_probe.cu), but a small frame gives a wide layer very few tiles: down4.conv.3 of ONE
-        // 256x256 pair is 2 pixel tiles x 4 column blocks = 8 CTAs on 148 SMs. Narrower blocks multiply the CTA count;
-        // pick the width with the smallest (waves x cycles per K step). Large frames keep 256. FI_BLOCK_N forces one.
+        // Column-block width of the per-tap kernel. N = 256 is the efficient shape (tensor-bound M128/M256 x N256 MMAs,
+        // CTA pairs halve the weight traffic: 1500-1600 TFLOP/s), narrower blocks are bound by the A-operand reads
+        // (~56 % tensor-pipe activity at N = 128 under ncu). But a small frame gives a wide layer very few tiles:
+        // down4.conv.3 of ONE 256x256 pair is 2 pixel tiles x 4 column blocks = 8 CTAs on 148 SMs. Only when the
+        // 256-wide tiling cannot even fill one wave are narrower blocks considered, by (waves x cycles per K16 step:
+        // 128 / 80 / 56); anything with a full wave of 256-wide tiles keeps 256. FI_BLOCK_N forces one.
         const long long m_tiles = static_cast<long long>(d.N) * ((d.H + TILE_H - 1) / TILE_H) * ((d.W + TILE_W - 1) / TILE_W);
         const int widths[3] = {256, 128, 64};
-        const double cycles[3] = {128.0, 70.0, 51.0};
+        const double cycles[3] = {128.0, 80.0, 56.0};
         const char* force = getenv("FI_BLOCK_N");
+        const bool small = d.n_total % 256 != 0 || m_tiles * (d.n_total / 256) < num_sms;
         double best = 0;
         for (int i = 0; i < 3; ++i) {
             if (d.n_total % widths[i]) continue;
@@ -366,9 +416,10 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
                 block_n = widths[i];
                 break;
             }
+            if (force && atoi(force) > 0) continue;
             const long long tiles = m_tiles * (d.n_total / widths[i]);
             const double est = static_cast<double>((tiles + num_sms - 1) / num_sms) * cycles[i];
-            if (best == 0 || est < best * 0.999) {
+            if (best == 0 || (small && est < best * 0.999)) {
                 best = est;
                 block_n = widths[i];
             }
@@ -463,8 +514,29 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     l.block_n = block_n;
     l.mode = d.mode;
     l.split = precise ? 1 : 0;
-    const long long total = static_cast<long long>(p.n_blocks) * p.n_img * p.tiles_y * p.tiles_x;
+    long long total = static_cast<long long>(p.n_blocks) * p.n_img * p.tiles_y * p.tiles_x;
     if (total > 0x7fffffffLL) return "conv: too many tiles";
+    // Split K (the nine taps) over several CTAs when the layer has too few tiles to occupy the GPU and a long K loop:
+    // the deep layers of one small frame (down4.conv.3 of a 256x256 pair: 32 tiles, 144 K steps each, and the loop is
+    // bound by the latency of its TMA loads, not by the tensor pipe). Needs the caller's scratch (fiNet plans have one).
+    p.ksplit = 1;
+    p.split_ws = d.split_ws;
+    p.split_cnt = d.split_cnt;
+    {
+        const char* ks = getenv("FI_KSPLIT");   // 0 = never split, n = force n-way where eligible
+        const int forced = ks ? atoi(ks) : -1;
+        const bool eligible = !l.halo && !l.pair && !precise && d.taps == 9 && d.split_ws && d.split_cnt &&
+                              (d.mode == EPI_STORE || d.mode == EPI_STORE_POOL) && forced != 0;
+        if (eligible && total > 0) {
+            int want = forced > 0 ? forced : static_cast<int>(num_sms / total);
+            if (forced < 0 && (2 * total > num_sms || d.taps * p.slabs < 36)) want = 1;
+            if (want > d.taps) want = d.taps;
+            const size_t per_split = static_cast<size_t>(total) * BLOCK_M * block_n * sizeof(float);
+            while (want > 1 && (per_split * want > d.split_ws_bytes || total * 8 > d.split_cnt_count)) --want;
+            if (want > 1) p.ksplit = want;
+        }
+    }
+    total *= p.ksplit;
     l.grid = static_cast<int>(total < num_sms ? total : num_sms);
     if (l.pair) {
         const long long m_tiles = static_cast<long long>(p.n_img) * p.tiles_y * p.tiles_x;

@@ -48,6 +48,12 @@ struct ConvDesc {
     const void* src1_lo;
     void* dst_lo;       // lo halves of dst / dst_pool (EPI_STORE*, EPI_CONVT)
     void* dst_pool_lo;
+    // optional scratch for splitting K (the taps) of a layer with very few tiles over several CTAs (small frames):
+    // fp32 partial tiles + one arrival counter per (tile, epilogue warp); counters must be zero and are left zero
+    float* split_ws;
+    size_t split_ws_bytes;
+    unsigned int* split_cnt;
+    int split_cnt_count;
 };
 
 constexpr int MAX_SEGS = 6;
@@ -65,6 +71,9 @@ struct ConvKernelParams {
     int H, W;
     int n_classes;
     int prefetch_dist;  // halo kernel: L2-prefetch the halo boxes of the tile this many grid strides ahead (0 = off)
+    int ksplit;         // per-tap kernel: CTAs sharing one output tile, each reducing a range of taps (1 = off)
+    float* split_ws;    // [tile][split][128 rows][BLOCK_N] fp32 partial accumulators
+    unsigned int* split_cnt;  // [tile][4 epilogue warps] arrivals
     const float* bias;
     const float* head_w;
     const float* head_b;

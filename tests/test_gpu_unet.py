@@ -282,11 +282,14 @@ def test_building_blocks_stand_alone(cuda_device):
 
 
 @pytest.mark.parametrize("env", [{"FI_CTA2": "0"}, {"FI_CTA2": "0", "FI_NO_HALO": "1"}, {"FI_HALO_PREFETCH": "0"},
-                                 {"FI_BLOCK_N": "256"}, {"FI_BLOCK_N": "128"}, {"FI_BLOCK_N": "64"}, {"FI_PDL": "0"}])
+                                 {"FI_BLOCK_N": "256"}, {"FI_BLOCK_N": "128"}, {"FI_BLOCK_N": "64"}, {"FI_PDL": "0"},
+                                 {"FI_KSPLIT": "0"}, {"FI_KSPLIT": "3"}, {"FI_KSPLIT": "9", "FI_BLOCK_N": "128"},
+                                 {"FI_KSPLIT": "2", "FI_BLOCK_N": "256", "FI_CTA2": "0"}])
 def test_kernel_selection_fallbacks_give_same_network(cuda_device, monkeypatch, env):
     """The single-CTA kernels (FI_CTA2=0), the per-tap kernel for narrow layers (FI_NO_HALO=1), the halo kernel
-    without L2 prefetch, every column-block width of the per-tap kernel (the default picks it from the tile count) and
-    plain stream order instead of programmatic dependent launch compute the same network as the default selection (CTA pairs + halo reuse): identical per-layer
+    without L2 prefetch, every column-block width of the per-tap kernel (the default picks it from the tile count), K split
+    over 2 / 3 / 9 CTAs per tile (or never) and plain stream order instead of programmatic dependent launch compute
+    the same network as the default selection (CTA pairs + halo reuse): identical per-layer
     inputs and fp32 accumulation orders differ only in how K is walked, so outputs agree to bf16 noise."""
     from model import _engine as E
     sd = O.init_state_dict(0, 2, 1, False)
