@@ -517,8 +517,10 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     long long total = static_cast<long long>(p.n_blocks) * p.n_img * p.tiles_y * p.tiles_x;
     if (total > 0x7fffffffLL) return "conv: too many tiles";
     // Split K (the nine taps) over several CTAs when the layer has too few tiles to occupy the GPU and a long K loop:
-    // the deep layers of one small frame (down4.conv.3 of a 256x256 pair: 32 tiles, 144 K steps each, and the loop is
-    // bound by the latency of its TMA loads, not by the tensor pipe). Needs the caller's scratch (fiNet plans have one).
+    // the deepest layers of one small frame (down4.conv.3 of a 256x256 pair: 32 tiles, 144 K steps each). Measured on
+    // B200 (profiles/r02_small_profile*.json): the split costs ~8 us (partial tiles through L2, fence, arrival counter,
+    // the last CTA's sum), so it pays at 144 K steps (down4.conv.3 40 -> 31 us, up1.conv.0 41 -> 35 us) and loses at 72
+    // (25 -> 33 us): the threshold is 144. Needs the caller's scratch (fiNet plans have one).
     p.ksplit = 1;
     p.split_ws = d.split_ws;
     p.split_cnt = d.split_cnt;
@@ -529,7 +531,7 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
                               (d.mode == EPI_STORE || d.mode == EPI_STORE_POOL) && forced != 0;
         if (eligible && total > 0) {
             int want = forced > 0 ? forced : static_cast<int>(num_sms / total);
-            if (forced < 0 && (2 * total > num_sms || d.taps * p.slabs < 36)) want = 1;
+            if (forced < 0 && (2 * total > num_sms || d.taps * p.slabs < 144)) want = 1;
             if (want > d.taps) want = d.taps;
             const size_t per_split = static_cast<size_t>(total) * BLOCK_M * block_n * sizeof(float);
             while (want > 1 && (per_split * want > d.split_ws_bytes || total * 8 > d.split_cnt_count)) --want;

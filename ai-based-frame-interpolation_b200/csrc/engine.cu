@@ -914,6 +914,15 @@ int fiNetInterpolateHostU8(fiNet* net, const uint8_t* frame1_host, const uint8_t
 
 int fiNetInterpolateClipHostU8(fiNet* net, const uint8_t* frames_host, int n_frames, int channels_per_frame,
                                uint8_t* out_host, int H, int W, int pairs_per_batch, void* stream) {
+    if (!net) return fail(FI_ERR_INVALID, "null argument");
+    return fiNetInterpolateClipHostU8Strided(net, frames_host, static_cast<int64_t>(channels_per_frame) * H * W, n_frames,
+                                             channels_per_frame, out_host, static_cast<int64_t>(net->n_classes) * H * W, H,
+                                             W, pairs_per_batch, stream);
+}
+
+int fiNetInterpolateClipHostU8Strided(fiNet* net, const uint8_t* frames_host, int64_t frame_stride, int n_frames,
+                                      int channels_per_frame, uint8_t* out_host, int64_t out_stride, int H, int W,
+                                      int pairs_per_batch, void* stream) {
     if (!net || !frames_host || !out_host) return fail(FI_ERR_INVALID, "null argument");
     if (2 * channels_per_frame != net->n_channels)
         return fail(FI_ERR_INVALID, "2 x %d channels per frame != n_channels %d", channels_per_frame, net->n_channels);
@@ -925,6 +934,8 @@ int fiNetInterpolateClipHostU8(fiNet* net, const uint8_t* frames_host, int n_fra
     const size_t frame_bytes = static_cast<size_t>(channels_per_frame) * H * W;
     const size_t outf_bytes = static_cast<size_t>(net->n_classes) * H * W;
     const size_t in_bytes = (B + 1) * frame_bytes, out_bytes = B * outf_bytes;
+    if (frame_stride < static_cast<int64_t>(frame_bytes) || out_stride < static_cast<int64_t>(outf_bytes))
+        return fail(FI_ERR_INVALID, "frame strides are smaller than a frame");
     if (!net->clip_h2d) {
         CUDA_TRY(cudaStreamCreateWithFlags(&net->clip_h2d, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&net->clip_d2h, cudaStreamNonBlocking));
@@ -960,7 +971,13 @@ int fiNetInterpolateClipHostU8(fiNet* net, const uint8_t* frames_host, int n_fra
         CUDA_TRY(cudaEventSynchronize(c.out_ready));
         const int first = b * B;
         const int cnt = n_pairs - first < B ? n_pairs - first : B;
-        memcpy(out_host + static_cast<size_t>(first) * outf_bytes, c.pin_out, cnt * outf_bytes);
+        if (out_stride == static_cast<int64_t>(outf_bytes)) {
+            memcpy(out_host + static_cast<size_t>(first) * outf_bytes, c.pin_out, cnt * outf_bytes);
+        } else {
+            for (int i = 0; i < cnt; ++i)
+                memcpy(out_host + static_cast<int64_t>(first + i) * out_stride,
+                       static_cast<const char*>(c.pin_out) + i * outf_bytes, outf_bytes);
+        }
         return FI_OK;
     };
     for (int b = 0; b < n_batches; ++b) {
@@ -968,7 +985,13 @@ int fiNetInterpolateClipHostU8(fiNet* net, const uint8_t* frames_host, int n_fra
         const int first = b * B;
         const int cnt = n_pairs - first < B ? n_pairs - first : B;
         // slot reuse is safe: batch b-2 was collected (host-synchronised) in iteration b-1
-        memcpy(c.pin_in, frames_host + static_cast<size_t>(first) * frame_bytes, (cnt + 1) * frame_bytes);
+        if (frame_stride == static_cast<int64_t>(frame_bytes)) {
+            memcpy(c.pin_in, frames_host + static_cast<size_t>(first) * frame_bytes, (cnt + 1) * frame_bytes);
+        } else {
+            for (int i = 0; i <= cnt; ++i)
+                memcpy(static_cast<char*>(c.pin_in) + i * frame_bytes, frames_host + static_cast<int64_t>(first + i) * frame_stride,
+                       frame_bytes);
+        }
         CUDA_TRY(cudaMemcpyAsync(c.dev_in, c.pin_in, (cnt + 1) * frame_bytes, cudaMemcpyHostToDevice, net->clip_h2d));
         CUDA_TRY(cudaEventRecord(c.in_ready, net->clip_h2d));
         CUDA_TRY(cudaStreamWaitEvent(st, c.in_ready, 0));

@@ -62,6 +62,8 @@ _SIGNATURES = {
                                          C.c_int, C.c_void_p]),
     "fiNetInterpolateClipHostU8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                              C.c_int, C.c_void_p]),
+    "fiNetInterpolateClipHostU8Strided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                                    C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fiNetForwardCost": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "fiNetPlanStats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_size_t)]),
     "fiNetReadActivation": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int),
@@ -233,19 +235,32 @@ class Net:
 
     def interpolate_clip_host_u8(self, frames, pairs_per_batch=4, out=None):
         """numpy uint8 [F,C,H,W] host clip in, numpy uint8 [F-1,n_classes,H,W] midpoints out; copies and compute are
-        pipelined inside the library. `out`: optional preallocated C-contiguous result array (e.g. this GPU's slice of a
-        clip-wide buffer when the pairs are sharded across GPUs)."""
+        pipelined inside the library. `out`: optional preallocated result array (e.g. this GPU's slice of a clip-wide
+        buffer when the pairs are sharded across GPUs). Both arrays may be strided along the frame axis (every frame
+        itself contiguous), e.g. `seq[0::2]` in and `seq[1::2]` out of one interleaved sequence."""
         import numpy as np
-        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        frames = np.asarray(frames)
+        if frames.dtype != np.uint8 or frames.ndim != 4:
+            raise FiError("frames must be a uint8 array [F,C,H,W]")
         f, c, h, w = frames.shape
+
+        def frame_contiguous(a):   # every frame a[i] is C-contiguous (strides of length-1 axes do not matter)
+            want = (a.shape[2] * a.shape[3], a.shape[3], 1)
+            inner = all(a.shape[k + 1] == 1 or a.strides[k + 1] == want[k] for k in range(3))
+            return inner and (a.shape[0] == 1 or a.strides[0] >= a.shape[1] * a.shape[2] * a.shape[3])
+
+        if not frame_contiguous(frames):
+            frames = np.ascontiguousarray(frames)
         if out is None:
             out = np.empty((f - 1, self.n_classes, h, w), dtype=np.uint8)
-        elif (out.dtype != np.uint8 or out.shape != (f - 1, self.n_classes, h, w) or not out.flags.c_contiguous
-              or not out.flags.writeable):
-            raise FiError(f"out must be a writable C-contiguous uint8 array of shape {(f - 1, self.n_classes, h, w)}")
+        elif (out.dtype != np.uint8 or out.shape != (f - 1, self.n_classes, h, w) or not out.flags.writeable
+              or (f > 1 and not frame_contiguous(out))):
+            raise FiError(f"out must be a writable uint8 array of shape {(f - 1, self.n_classes, h, w)} whose frames "
+                          "are contiguous")
         with torch.cuda.device(self.device):
-            check(lib().fiNetInterpolateClipHostU8(self._h, frames.ctypes.data, f, c, out.ctypes.data, h, w,
-                                                   pairs_per_batch, current_stream()))
+            check(lib().fiNetInterpolateClipHostU8Strided(self._h, frames.ctypes.data, frames.strides[0], f, c,
+                                                          out.ctypes.data, out.strides[0] if f > 1 else 0, h, w,
+                                                          pairs_per_batch, current_stream()))
         return out
 
     def set_profiling(self, on):

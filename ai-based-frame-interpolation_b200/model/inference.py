@@ -237,18 +237,19 @@ class FrameInterpolator:
     def interpolate_clip(self, frames, out=None):
         """Midpoint of every consecutive pair of a clip held in ONE uint8 array: [F,H,W] grey or [F,H,W,3] BGR ->
         [F-1,H,W] / [F-1,H,W,3]. `out` may be a preallocated result array (re-used across calls by the video loop and by
-        bench.py; a fresh 1 GB result array costs page faults comparable to the GPU time of a short clip)."""
+        bench.py; a fresh 1 GB result array costs page faults comparable to the GPU time of a short clip). Grey clips
+        and their `out` may be strided along the frame axis (`seq[0::2]` -> `seq[1::2]`)."""
         arr = np.asarray(frames)
         if arr.dtype != np.uint8 or arr.ndim not in (3, 4) or arr.shape[0] < 2:
             raise ValueError("expected a uint8 clip [F,H,W] or [F,H,W,C] with at least two frames")
         if out is None:
             out = np.empty((arr.shape[0] - 1,) + arr.shape[1:], dtype=np.uint8)
-        elif out.shape != (arr.shape[0] - 1,) + arr.shape[1:] or out.dtype != np.uint8 or not out.flags.c_contiguous:
-            raise ValueError("out must be a C-contiguous uint8 array with one frame less than the clip")
-        if arr.ndim == 3:                                   # grey frames
+        elif out.shape != (arr.shape[0] - 1,) + arr.shape[1:] or out.dtype != np.uint8:
+            raise ValueError("out must be a uint8 array with one frame less than the clip")
+        if arr.ndim == 3:                                   # grey frames: may be strided along the frame axis
             if self.n_channels != 2:
                 raise _E.FiError(f"model expects {self.n_channels} input channels, frames are grey")
-            self._clip_call(np.ascontiguousarray(arr)[:, None], out[:, None])
+            self._clip_call(arr[:, None], out[:, None])
             return out
         c = arr.shape[3]
         if self.n_channels == 2:                            # grey model: every colour plane is its own clip
@@ -276,15 +277,21 @@ class FrameInterpolator:
         if factor < 2 or len(frames) < 2:
             return list(frames)
         if factor & (factor - 1) == 0:
-            seq = frames                                    # an ndarray clip is used as it lies (no stacking copy)
-            while factor > 1:
-                mids = self._sequence_midpoints(seq)
-                merged = []
-                for f, m in zip(seq[:-1], mids):
-                    merged += [f, m]
-                seq = merged + [seq[-1]]
-                factor //= 2
-            return seq
+            # Bisection in place: the source frames go to every `factor`-th slot of one result array; each level reads
+            # the frames already present (stride `step`) and writes their midpoints between them (the library takes
+            # strided frame arrays), so no level gathers or re-stacks frames.
+            first = np.asarray(frames[0])
+            seq = np.empty(((len(frames) - 1) * factor + 1,) + first.shape, dtype=np.uint8)
+            if isinstance(frames, np.ndarray):
+                seq[::factor] = frames
+            else:
+                for i, fr in enumerate(frames):
+                    seq[i * factor] = fr
+            step = factor
+            while step > 1:
+                self.interpolate_clip(seq[::step], out=seq[step // 2::step])
+                step //= 2
+            return list(seq)
         mids = self._sequence_midpoints(frames)
         frames = list(frames)
         out = []

@@ -93,6 +93,13 @@ int fiNetInterpolateHostU8(fiNet* net, const uint8_t* frame1_host, const uint8_t
 int fiNetInterpolateClipHostU8(fiNet* net, const uint8_t* frames_host, int n_frames, int channels_per_frame,
                                uint8_t* out_host, int H, int W, int pairs_per_batch, void* stream);
 
+/* The same with the frames frame_stride bytes and the results out_stride bytes apart (each frame itself contiguous):
+ * lets FrameInterpolator.interpolate_sequence (factor 2^k bisection, reference main.py:128 `--factor`) read every other
+ * frame of an interleaved sequence and write the new midpoints straight between them, without gathering copies. */
+int fiNetInterpolateClipHostU8Strided(fiNet* net, const uint8_t* frames_host, int64_t frame_stride, int n_frames,
+                                      int channels_per_frame, uint8_t* out_host, int64_t out_stride, int H, int W,
+                                      int pairs_per_batch, void* stream);
+
 /* Algorithmic FLOPs (2*MACs, no padding) of one forward at this shape, and the number of kernel launches it makes. */
 int fiNetForwardCost(fiNet* net, int N, int H, int W, double* flops, int* launches);
 /* Measurement hook for bench.py: when enabled, every launch of the following forwards is bracketed by a CUDA event

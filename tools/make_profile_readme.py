@@ -31,6 +31,16 @@ def col(hdr, prefix):
     return [i for i, n in enumerate(hdr) if n.startswith(prefix)][0]
 
 
+_SCALE = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6,                      # -> microseconds
+          "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}          # -> megabytes
+
+
+def val(hdr, row, i):
+    """Cell i of an ncu raw-page row in canonical units (us / MB): ncu picks the unit per report, e.g. [ms] or [us]."""
+    m = re.search(r"\[(\w+)\]", hdr[i])
+    return float(row[i]) * _SCALE.get(m.group(1), 1.0) if m else float(row[i])
+
+
 def kernel_name(s):
     m = re.search(r"(\w+_kernel(?:<[^>]*>)?)", s)
     return m.group(1) if m else s[:60]
@@ -95,9 +105,9 @@ def main():
         dram, n_conv = 0.0, 0
         for i, r in enumerate(rows):
             name = kernel_name(r[ik])
-            w(f"| {i} | `{name}` | {float(r[it]):.1f} | {float(r[ir]):.1f} | {float(r[iw]):.1f} | {float(r[idr]):.0f} | {float(r[itn]):.1f} | {float(r[il2]):.1f} |")
+            w(f"| {i} | `{name}` | {val(h, r, it):.1f} | {val(h, r, ir):.1f} | {val(h, r, iw):.1f} | {float(r[idr]):.0f} | {float(r[itn]):.1f} | {float(r[il2]):.1f} |")
             if "stem" not in name:
-                dram += (float(r[ir]) + float(r[iw])) * 1e6
+                dram += (val(h, r, ir) + val(h, r, iw)) * 1e6
                 n_conv += 1
         algo = sum(p["bytes"] for p in prof if p["kind"] == 1) / bench["config"]["pairs_per_step"]
         w("")
@@ -124,8 +134,10 @@ def main():
               f"{bound_ms / a['ms'] * 100:.0f} % | {a['note']} |")
         w("")
     for title, name in (("Non-GEMM kernels under ncu", f"{R}_aux_ncu_full.csv"),
-                        ("Training kernels under ncu (one eager step, batch 16 x 256²; first 48 BatchNorm / weight-gradient launches)",
-                         f"{R}_train_ncu_full.csv")):
+                        ("Training kernels under ncu, forward BatchNorm (one eager step, batch 16 x 256²)",
+                         f"{R}_train_ncu_full.csv"),
+                        ("Training kernels under ncu, weight gradient and BatchNorm backward (same step)",
+                         f"{R}_train_bwd_ncu_full.csv")):
         h, rows = ncu_rows(name)
         if not h:
             continue
@@ -137,18 +149,18 @@ def main():
         seen = {}
         for r in rows:
             name_k = kernel_name(r[ik])
-            us = float(r[it])
+            us = val(h, r, it)
             key = (name_k, round(us, -1))
-            if name.endswith("train_ncu_full.csv"):   # keep the largest launch of every kernel
+            if "train" in name:   # keep the largest launch of every kernel
                 if name_k in seen and seen[name_k][0] >= us:
                     continue
                 seen[name_k] = (us, r)
                 continue
-            gbs = (float(r[ir]) + float(r[iw])) * 1e6 / (us * 1e-6) / 1e9
-            w(f"| `{name_k}` | {us:.1f} | {float(r[ir]):.1f} | {float(r[iw]):.1f} | {gbs:.0f} | {float(r[idr]):.0f} | {float(r[ism]):.0f} | {float(r[itn]):.1f} |")
+            gbs = (val(h, r, ir) + val(h, r, iw)) * 1e6 / (us * 1e-6) / 1e9
+            w(f"| `{name_k}` | {us:.1f} | {val(h, r, ir):.1f} | {val(h, r, iw):.1f} | {gbs:.0f} | {float(r[idr]):.0f} | {float(r[ism]):.0f} | {float(r[itn]):.1f} |")
         for name_k, (us, r) in seen.items():
-            gbs = (float(r[ir]) + float(r[iw])) * 1e6 / (us * 1e-6) / 1e9
-            w(f"| `{name_k}` (largest launch) | {us:.1f} | {float(r[ir]):.1f} | {float(r[iw]):.1f} | {gbs:.0f} | {float(r[idr]):.0f} | {float(r[ism]):.0f} | {float(r[itn]):.1f} |")
+            gbs = (val(h, r, ir) + val(h, r, iw)) * 1e6 / (us * 1e-6) / 1e9
+            w(f"| `{name_k}` (largest launch) | {us:.1f} | {val(h, r, ir):.1f} | {val(h, r, iw):.1f} | {gbs:.0f} | {float(r[idr]):.0f} | {float(r[ism]):.0f} | {float(r[itn]):.1f} |")
         w("")
     for name, title in ((f"{R}_small_profile.json", "ConvTranspose2d decoder"), (f"{R}_small_profile_bilinear.json", "bilinear decoder")):
         f = P / name
