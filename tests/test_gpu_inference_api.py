@@ -288,3 +288,32 @@ def test_http_concurrent_requests_are_batched(cuda_device, checkpoints, tmp_path
         other = ref.interpolate_frames(moving_disc(i + 3, 256, 256), moving_disc(i + 5, 256, 256))
         err = np.abs(frames[1].astype(int) - want.astype(int)).mean()
         assert err < 6 and err < np.abs(frames[1].astype(int) - other.astype(int)).mean()
+
+
+def test_strided_clip_and_in_place_bisection(cuda_device, checkpoints):
+    """fiNetInterpolateClipHostU8Strided: frames / results strided along the frame axis (seq[0::2] -> seq[1::2]) give the
+    bytes of the contiguous call, and interpolate_sequence(factor 4) built on it equals pair-by-pair bisection."""
+    from model import _engine as E
+    from model.inference import FrameInterpolator
+    path, sd = checkpoints[False]
+    frames = np.stack([moving_disc(i, 48, 64) for i in range(6)])
+    net = E.Net(cuda_device, 2, 1, False)
+    net.load_state_dict(sd)
+    ref = net.interpolate_clip_host_u8(frames[:, None], 2)
+    seq = np.zeros((11, 1, 48, 64), np.uint8)
+    seq[0::2] = frames[:, None]
+    got = net.interpolate_clip_host_u8(seq[0::2], 2, out=seq[1::2])
+    assert np.array_equal(seq[1::2], ref) and np.array_equal(seq[0::2], frames[:, None]) and got.base is not None
+    with pytest.raises(E.FiError):          # result frames must be contiguous
+        net.interpolate_clip_host_u8(frames[:, None], 2, out=np.zeros((5, 1, 48, 128), np.uint8)[..., ::2])
+    net.close()
+    fi = FrameInterpolator(path, "cuda", pairs_per_batch=2)
+    out = fi.interpolate_sequence(list(frames), 4)
+    assert len(out) == 21
+    for i in range(5):
+        mid = fi.interpolate_frames(frames[i], frames[i + 1])
+        assert np.array_equal(out[4 * i + 2], mid)
+        assert np.array_equal(out[4 * i + 1], fi.interpolate_frames(frames[i], mid))
+        assert np.array_equal(out[4 * i + 3], fi.interpolate_frames(mid, frames[i + 1]))
+        assert np.array_equal(out[4 * i], frames[i])
+    assert np.array_equal(out[20], frames[5])
