@@ -8,6 +8,7 @@
 #include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges are no-ops unless a profiler is attached
 
 #include <cmath>
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -104,6 +105,7 @@ struct Plan {
     std::map<std::string, Act> acts;
     std::vector<Step> steps;
     int head_step = -1;
+    bool reuse = false;  // arena placed with liveness reuse: intermediate tensors are overwritten during the forward
     int last_n = 0;    // batch of the most recent forward
     double flops = 0;  // per image
     void reset() {
@@ -364,43 +366,81 @@ int fill_plan(fiNet* net, Plan& pl, int N, int H, int W) {
         hs[i] = hs[i - 1] / 2;
         ws[i] = ws[i - 1] / 2;
     }
-    size_t cursor = 0;
-    auto add = [&](const std::string& name, int C, int h, int w) {
-        Act a;
-        a.off = cursor;
-        a.C = C;
-        a.H = h;
-        a.W = w;
-        cursor = align_up(cursor + a.bytes(N), 1024);
-        if (net->precise) {
-            a.off_lo = cursor;
-            cursor = align_up(cursor + a.bytes(N), 1024);
-        }
-        pl.acts[name] = a;
+    // Activation tensors with the schedule steps that write / last read them (step numbering: 0 stem, 1 inc.3,
+    // 2i / 2i+1 the two convs of down_i, 10+3k / +1 / +2 = up, conv.0, conv.3 of up_{k+1}).
+    struct Item {
+        std::string name;
+        int C, h, w, first, last;
+    };
+    std::vector<Item> items;
+    auto add = [&](const std::string& name, int C, int h, int w, int first, int last) {
+        items.push_back({name, C, h, w, first, last});
     };
     const int enc_c[5] = {64, cs[2].cout, cs[4].cout, cs[6].cout, cs[8].cout};
-    add("inc.mid", 64, hs[0], ws[0]);
-    add("inc", 64, hs[0], ws[0]);
+    add("inc.mid", 64, hs[0], ws[0], 0, 1);
+    add("inc", 64, hs[0], ws[0], 1, 20);
     for (int i = 1; i <= 4; ++i) {
         char nm[32];
         snprintf(nm, sizeof nm, "pool%d", i);
-        add(nm, enc_c[i - 1], hs[i], ws[i]);
+        add(nm, enc_c[i - 1], hs[i], ws[i], 2 * i - 1, 2 * i);
         snprintf(nm, sizeof nm, "down%d.mid", i);
-        add(nm, enc_c[i], hs[i], ws[i]);
+        add(nm, enc_c[i], hs[i], ws[i], 2 * i, 2 * i + 1);
         snprintf(nm, sizeof nm, "down%d", i);
-        add(nm, enc_c[i], hs[i], ws[i]);
+        add(nm, enc_c[i], hs[i], ws[i], 2 * i + 1, i == 4 ? 10 : 10 + 3 * (3 - i) + 1);  // skip read by up_{4-i}.conv.0
     }
     for (int i = 0; i < 4; ++i) {
         char nm[32];
         const int lvl = 3 - i;  // skip level of up(i+1)
+        const int base = 10 + 3 * i;
         snprintf(nm, sizeof nm, "up%d.up", i + 1);
-        add(nm, upc[i][1], 2 * hs[lvl + 1], 2 * ws[lvl + 1]);
+        add(nm, upc[i][1], 2 * hs[lvl + 1], 2 * ws[lvl + 1], base, base + 1);
         snprintf(nm, sizeof nm, "up%d.mid", i + 1);
-        add(nm, cs[9 + 2 * i].cout, hs[lvl], ws[lvl]);
+        add(nm, cs[9 + 2 * i].cout, hs[lvl], ws[lvl], base + 1, base + 2);
         if (i < 3) {
             snprintf(nm, sizeof nm, "up%d", i + 1);
-            add(nm, cs[10 + 2 * i].cout, hs[lvl], ws[lvl]);
+            add(nm, cs[10 + 2 * i].cout, hs[lvl], ws[lvl], base + 2, base + 3);
         }
+    }
+    // Placement. Default: every tensor has its own memory (fiNetReadActivation can tap any of them after the forward).
+    // Liveness reuse (FI_ARENA_REUSE=1, or automatically when the plain layout would exceed 16 GiB — 4K frames x 8 pairs
+    // is 74 GB): a tensor may take the memory of tensors whose last reader ran in an earlier step. Kernels of
+    // consecutive steps never overlap in their memory accesses (programmatic dependent launch waits for the previous grid
+    // to complete before touching memory), so step granularity is exact. First fit over the tensors alive in between.
+    const size_t mult = net->precise ? 2 : 1;
+    auto bytes_of = [&](const Item& it) { return align_up(static_cast<size_t>(N) * it.h * it.w * it.C * 2, 1024); };
+    size_t plain = 0;
+    for (const Item& it : items) plain += mult * bytes_of(it);
+    const char* reuse_env = getenv("FI_ARENA_REUSE");
+    pl.reuse = reuse_env ? reuse_env[0] == '1' : plain > (size_t(16) << 30);
+    size_t cursor = 0;
+    struct Placed {
+        size_t off, bytes;
+        int first, last;
+    };
+    std::vector<Placed> placed;
+    for (const Item& it : items) {
+        const size_t bytes = mult * bytes_of(it);
+        size_t off = cursor;
+        if (pl.reuse) {
+            std::vector<Placed> live;
+            for (const Placed& q : placed)
+                if (!(q.last < it.first || it.last < q.first)) live.push_back(q);
+            std::sort(live.begin(), live.end(), [](const Placed& a, const Placed& b) { return a.off < b.off; });
+            off = 0;
+            for (const Placed& q : live) {
+                if (off + bytes <= q.off) break;
+                if (q.off + q.bytes > off) off = q.off + q.bytes;
+            }
+        }
+        placed.push_back({off, bytes, it.first, it.last});
+        if (off + bytes > cursor) cursor = off + bytes;
+        Act a;
+        a.off = off;
+        a.off_lo = net->precise ? off + bytes_of(it) : 0;
+        a.C = it.C;
+        a.H = it.h;
+        a.W = it.w;
+        pl.acts[it.name] = a;
     }
     {
         void* p = nullptr;
@@ -1044,6 +1084,9 @@ int fiNetReadActivation(fiNet* net, const char* name, float* out_host, int64_t c
     Plan& pl = net->plan();
     auto it = pl.acts.find(name);
     if (!pl.arena.p || it == pl.acts.end()) return fail(FI_ERR_INVALID, "no activation named '%s' in the current plan", name);
+    if (pl.reuse)
+        return fail(FI_ERR_STATE, "activation taps are unavailable: this plan's arena re-uses the memory of dead tensors "
+                                  "(FI_ARENA_REUSE=0 keeps every tensor)");
     const Act& a = it->second;
     const int64_t n = static_cast<int64_t>(pl.last_n) * a.C * a.H * a.W;
     if (capacity < n) return fail(FI_ERR_INVALID, "buffer too small: need %lld floats", static_cast<long long>(n));

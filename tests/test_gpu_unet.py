@@ -375,3 +375,27 @@ def test_plan_cache_keeps_alternating_shapes(cuda_device, monkeypatch):
     small.forward(*inputs[shapes[0]])          # evicted earlier: rebuilt, same result
     assert small.plan_stats()[:2] == (2, 4)
     assert torch.equal(small.forward(*inputs[shapes[0]], want_f32=True)[0], first[shapes[0]])
+
+
+@pytest.mark.parametrize("bilinear,precision", [(False, "bf16"), (True, "bf16"), (False, "fp32")])
+def test_arena_liveness_reuse(cuda_device, monkeypatch, bilinear, precision):
+    """FI_ARENA_REUSE=1 (automatic for plans above 16 GiB: 4K frames x 8 pairs) places dead tensors' memory under later
+    ones: same bytes out, a much smaller arena, and the debug taps refuse to read overwritten tensors."""
+    from model import _engine as E
+    sd = O.init_state_dict(0, 2, 1, bilinear)
+    f1, f2 = frames(71, 3, 1, 70, 118).to(cuda_device), frames(72, 3, 1, 70, 118).to(cuda_device)
+    plain = E.Net(cuda_device, 2, 1, bilinear, precision)
+    plain.load_state_dict(sd)
+    want_f, want_u = plain.forward(f1, f2, want_f32=True, want_u8=True)
+    plain_bytes = plain.plan_stats()[2]
+    monkeypatch.setenv("FI_ARENA_REUSE", "1")
+    lean = E.Net(cuda_device, 2, 1, bilinear, precision)
+    lean.load_state_dict(sd)
+    for _ in range(2):      # the second forward runs over an arena full of the first one's leftovers
+        got_f, got_u = lean.forward(f1, f2, want_f32=True, want_u8=True)
+        assert torch.equal(got_f, want_f) and torch.equal(got_u, want_u)
+    lean_bytes = lean.plan_stats()[2]
+    assert lean_bytes < 0.55 * plain_bytes, (lean_bytes, plain_bytes)
+    with pytest.raises(E.FiError, match="taps are unavailable"):
+        lean.read_activation("inc", 3)
+    assert plain.read_activation("inc", 3).shape == (3, 64, 70, 118)
