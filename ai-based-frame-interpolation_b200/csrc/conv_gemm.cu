@@ -516,22 +516,26 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     l.split = precise ? 1 : 0;
     long long total = static_cast<long long>(p.n_blocks) * p.n_img * p.tiles_y * p.tiles_x;
     if (total > 0x7fffffffLL) return "conv: too many tiles";
-    // Split K (the nine taps) over several CTAs when the layer has too few tiles to occupy the GPU and a long K loop:
-    // the deepest layers of one small frame (down4.conv.3 of a 256x256 pair: 32 tiles, 144 K steps each). Measured on
-    // B200 (profiles/r02_small_profile*.json): the split costs ~8 us (partial tiles through L2, fence, arrival counter,
-    // the last CTA's sum), so it pays at 144 K steps (down4.conv.3 40 -> 31 us, up1.conv.0 41 -> 35 us) and loses at 72
-    // (25 -> 33 us): the threshold is 144. Needs the caller's scratch (fiNet plans have one).
+    // Split K (the nine taps) over several CTAs of a layer that has too few tiles to occupy the GPU and a long K loop:
+    // the deepest layers of one small frame (down4.conv.3 of a 256x256 pair: 32 tiles, 144 K steps each). OPT-IN
+    // (FI_KSPLIT=n forces n-way where eligible, FI_KSPLIT=auto picks num_sms / tiles for layers with >= 144 K steps):
+    // measured on B200 (profiles/r02_small_profile*.json) the split costs ~8 us per layer (partial tiles through L2,
+    // fence, arrival counter, the last warp's sum), so it pays at 144 K steps (down4.conv.3 40 -> 31 us, up1.conv.0
+    // 41 -> 35 us, forward 0.329 -> 0.314 ms) and loses at 72 (25 -> 33 us) — and, unlike every other kernel choice, it
+    // changes the summation order, so results would depend on the plan's batch capacity in the last bf16 bit. A 5 %
+    // gain on one-pair latency does not buy that: the default keeps K in one CTA. Needs the caller's scratch.
     p.ksplit = 1;
     p.split_ws = d.split_ws;
     p.split_cnt = d.split_cnt;
     {
-        const char* ks = getenv("FI_KSPLIT");   // 0 = never split, n = force n-way where eligible
-        const int forced = ks ? atoi(ks) : -1;
+        const char* ks = getenv("FI_KSPLIT");
+        const bool automatic = ks && ks[0] == 'a';
+        const int forced = (ks && !automatic) ? atoi(ks) : 0;
         const bool eligible = !l.halo && !l.pair && !precise && d.taps == 9 && d.split_ws && d.split_cnt &&
-                              (d.mode == EPI_STORE || d.mode == EPI_STORE_POOL) && forced != 0;
+                              (d.mode == EPI_STORE || d.mode == EPI_STORE_POOL) && (automatic || forced > 1);
         if (eligible && total > 0) {
-            int want = forced > 0 ? forced : static_cast<int>(num_sms / total);
-            if (forced < 0 && (2 * total > num_sms || d.taps * p.slabs < 144)) want = 1;
+            int want = forced > 1 ? forced : static_cast<int>(num_sms / total);
+            if (automatic && (2 * total > num_sms || d.taps * p.slabs < 144)) want = 1;
             if (want > d.taps) want = d.taps;
             const size_t per_split = static_cast<size_t>(total) * BLOCK_M * block_n * sizeof(float);
             while (want > 1 && (per_split * want > d.split_ws_bytes || total * 8 > d.split_cnt_count)) --want;

@@ -216,8 +216,20 @@ class Ranks:
         self.dist, self.torch, self.host = dist, torch, None
         if self.world > 1:
             os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")      # one node: the container hostname may not resolve
-            dist.init_process_group("nccl", device_id=self.dev)
-            self.host = dist.new_group(backend="gloo")
+            # NCCL announces its version on STDOUT when the first communicator comes up; stdout carries exactly one
+            # JSON line, so file descriptor 1 points at stderr while the groups are created
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=self.dev)
+                self.host = dist.new_group(backend="gloo")
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
 
     def barrier(self):
         if self.world > 1:
