@@ -282,11 +282,19 @@ class FrameInterpolator:
             # strided frame arrays), so no level gathers or re-stacks frames.
             first = np.asarray(frames[0])
             seq = np.empty(((len(frames) - 1) * factor + 1,) + first.shape, dtype=np.uint8)
-            if isinstance(frames, np.ndarray):
-                seq[::factor] = frames
+            def place(lo, hi):                                # numpy copies release the GIL
+                for i in range(lo, hi):
+                    seq[i * factor] = frames[i]
+
+            n_src = len(frames)
+            if n_src * first.nbytes > (256 << 20):           # a 4K clip is gigabytes: fault in / copy with several threads
+                import concurrent.futures
+                workers = min(8, os.cpu_count() or 1, n_src)
+                bounds = [n_src * k // workers for k in range(workers + 1)]
+                with concurrent.futures.ThreadPoolExecutor(workers) as ex:
+                    list(ex.map(place, bounds[:-1], bounds[1:]))
             else:
-                for i, fr in enumerate(frames):
-                    seq[i * factor] = fr
+                place(0, n_src)
             step = factor
             while step > 1:
                 self.interpolate_clip(seq[::step], out=seq[step // 2::step])
