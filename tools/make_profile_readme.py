@@ -177,7 +177,10 @@ def main():
     for name, cmd in ((f"{R}_api256.json", "python bench.py --workload api256"),
                       (f"{R}_4k_eval.json", "python bench.py --workload 4k_eval --steps 10"),
                       (f"{R}_train1.json", "python bench.py --workload train"),
-                      (f"{R}_train2.json", "torchrun --nproc-per-node 2 bench.py --gpus 2 --workload train")):
+                      (f"{R}_train2.json", "torchrun --nproc-per-node 2 bench.py --gpus 2 --workload train"),
+                      (f"{R}_train_8gpu.json", "torchrun --nproc-per-node 8 bench.py --gpus 8 --workload train"),
+                      (f"{R}_4k_eval_2gpu.json", "torchrun --nproc-per-node 2 bench.py --gpus 2 --workload 4k_eval --steps 10"),
+                      (f"{R}_4k_eval_8gpu.json", "torchrun --nproc-per-node 8 bench.py --gpus 8 --workload 4k_eval --steps 10")):
         d = load_json(name)
         if d:
             e = d.get("e2e") or {}
@@ -185,6 +188,14 @@ def main():
               f"e2e {e.get('value', float('nan')):.1f} {e.get('unit', '')}; whole-step {d['roofline']['achieved']:.0f} TFLOP/s "
               f"= {d['roofline']['frac']*100:.0f} % of the burst peak. {d['config']['workload']}.")
     w("")
+    vid = load_json(f"{R}_video_path.json")
+    if vid:
+        w(f"File-to-file video path (`{R}_video_path.json` = `python tools/bench_video.py`, {vid['clip']}, {vid['host_cores']} host "
+          f"cores): cv2 decode {vid['decode_frames_per_s']} frames/s, cv2 `mp4v` encode {vid['encode_frames_per_s']} frames/s, GPU "
+          f"stage on decoded BGR frames (grey model: 3 forwards per new frame, planes split / merged on the host) "
+          f"{vid['gpu_stage_new_bgr_frames_per_s']} new frames/s; `interpolate_video` end to end "
+          f"{vid['interpolate_video_output_frames_per_s']} output frames/s — bound by the software encoder, which the three "
+          "pipelined stages hide everything else behind.\n")
     pp = [(k, load_json(f"{R}_bench_p{k}.json")) for k in (4, 6, 8)]
     if all(d for _, d in pp):
         w("Pairs per forward (`bench.py --pairs K`): " + ", ".join(f"K={k}: {d['value']:.1f} frames/s" for k, d in pp) + ".\n")
