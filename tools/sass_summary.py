@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Opcode evidence for the tensor-core / TMA claims: disassembles libfi_b200.so (cuobjdump -sass, runs without a GPU)
 and writes, per kernel, how many tcgen05 MMA (UTCHMMA, .2CTA = cta_group::2), TMA load/store/prefetch (UTMALDG /
-UTMASTG / UTMAPF), TMEM load (LDTM), TMEM alloc (UTCATOMSWS), commit/barrier (UTCBAR, SYNCS) and legacy-MMA (HMMA:
-must be 0) instructions it contains.
+UTMASTG / UTMAPF), TMEM load (LDTM), TMEM alloc (UTCATOMSWS), commit/barrier (UTCBAR, SYNCS), programmatic-dependent-launch
+(PREEXIT = griddepcontrol.launch_dependents, ACQBULK = griddepcontrol.wait) and legacy-MMA (HMMA: must be 0)
+instructions it contains.
 
     python tools/sass_summary.py > profiles/sass_summary.txt
 """
@@ -14,8 +15,8 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "ai-based-frame-interpolation_b200" / "libfi_b200.so"
-KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMASTG", "UTMAPF", "LDTM", "UTCATOMSWS", "UTCBAR", "SYNCS", "HMMA",
-        "FFMA", "IDP", "ATOM", "RED"]
+KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMASTG", "UTMAPF", "LDTM", "UTCATOMSWS", "UTCBAR", "SYNCS", "PREEXIT",
+        "ACQBULK", "HMMA", "FFMA", "IDP", "ATOM", "RED"]
 
 
 def main():
@@ -47,7 +48,9 @@ def main():
     for fn, c in per.items():
         total.update(c)
         name = demangle.get(fn, fn)
-        name = re.sub(r"\(.*\)$", "", name)
+        # drop the parameter list, keep template arguments such as <(int)256, (int)2, (bool)0>
+        name = name[:name.rfind(">(") + 1] if ">(" in name else re.sub(r"\(.*\)$", "", name)
+        name = name.replace("(int)", "").replace("(bool)", "")
         print(" ".join(f"{c.get(k, 0):6d}" for k in KEYS) + f" | {c['_total']:7d} | {name}")
     print("# library totals")
     print(" ".join(f"{total.get(k, 0):6d}" for k in KEYS) + f" | {total['_total']:7d} | ALL")
