@@ -113,6 +113,11 @@ const char* encode_bf16_map_public(CUtensorMap* map, const void* base, int rank,
 const char* conv_pair_launch(const ConvLaunch& l, cudaStream_t stream);
 const char* conv_halo_pair_launch(const ConvLaunch& l, cudaStream_t stream);
 
+// conv_inc_fused.cu: inc.double_conv.0 (stem) computed inside inc.double_conv.3's kernel (grey network, bf16 mode)
+struct StemDesc;
+bool inc_fused_eligible(int cin, const ConvLaunch& conv);
+const char* inc_fused_launch(const StemDesc& d, const ConvLaunch& conv, int n_img, int num_sms, cudaStream_t stream);
+
 // conv_halo.cu
 bool conv_halo_eligible(const ConvDesc& d);
 void conv_halo_geometry(int* tile, int* box_w, int* box_h, int* out_w, int* out_h, int* pool_w, int* pool_h);

@@ -83,7 +83,7 @@ struct Act {  // bf16 NHWC activation inside the arena (precise mode: a second, 
     size_t bytes(int N) const { return static_cast<size_t>(N) * H * W * C * 2; }
 };
 
-enum StepKind { STEP_STEM, STEP_CONV, STEP_UPSAMPLE };
+enum StepKind { STEP_STEM, STEP_CONV, STEP_UPSAMPLE, STEP_INC_FUSED };
 struct Step {
     StepKind kind;
     fi::ConvLaunch conv;        // STEP_CONV
@@ -377,7 +377,12 @@ int fill_plan(fiNet* net, Plan& pl, int N, int H, int W) {
         items.push_back({name, C, h, w, first, last});
     };
     const int enc_c[5] = {64, cs[2].cout, cs[4].cout, cs[6].cout, cs[8].cout};
-    add("inc.mid", 64, hs[0], ws[0], 0, 1);
+    // grey network in bf16 mode: inc.double_conv.0 is computed inside inc.double_conv.3's kernel, inc.mid does not exist
+    const char* fuse_env = getenv("FI_FUSE_INC");
+    const char* no_halo_env = getenv("FI_NO_HALO");
+    const bool fuse_inc = net->n_channels <= 2 && !net->precise && !(fuse_env && fuse_env[0] == '0') &&
+                          !(no_halo_env && no_halo_env[0] == '1');
+    if (!fuse_inc) add("inc.mid", 64, hs[0], ws[0], 0, 1);
     add("inc", 64, hs[0], ws[0], 1, 20);
     for (int i = 1; i <= 4; ++i) {
         char nm[32];
@@ -442,6 +447,7 @@ int fill_plan(fiNet* net, Plan& pl, int N, int H, int W) {
         a.W = it.w;
         pl.acts[it.name] = a;
     }
+    if (fuse_inc) pl.acts["inc.mid"] = pl.acts.at("inc");   // only to describe the layer; the fused kernel never reads it
     {
         void* p = nullptr;
         cudaError_t e = cudaMalloc(&p, cursor);
@@ -546,6 +552,23 @@ int fill_plan(fiNet* net, Plan& pl, int N, int H, int W) {
         pl.steps.push_back(s);
     }
     if ((rc = conv3(0, "inc.mid", "", "inc", "pool1", fi::EPI_STORE_POOL))) return rc;
+    {
+        // Grey network, bf16 mode: the stem is computed inside inc.double_conv.3's kernel (conv_inc_fused.cu), inc.mid
+        // never reaches HBM. FI_FUSE_INC=0 keeps the two separate launches (tests compare the two bit for bit).
+        Step& conv_step = pl.steps.back();
+        if (fuse_inc && !fi::inc_fused_eligible(net->n_channels, conv_step.conv))
+            return fail(FI_ERR_STATE, "internal: inc.double_conv.3 was not prepared as the resident halo kernel");
+        if (fuse_inc) {
+            Step fused = conv_step;
+            fused.kind = STEP_INC_FUSED;
+            snprintf(fused.name, sizeof fused.name, "inc.double_conv.0+3");
+            fused.flops += pl.steps[0].flops;
+            const double px = static_cast<double>(H) * W;
+            fused.bytes = px * (stem.cin * 4.0 + 64 * 2 * 1.25);   // raw planes in, inc + pool1 out
+            pl.steps.clear();
+            pl.steps.push_back(fused);
+        }
+    }
     for (int i = 1; i <= 4; ++i) {
         char pool[32], mid[32], out[32], nextpool[32];
         snprintf(pool, sizeof pool, "pool%d", i);
@@ -835,6 +858,19 @@ int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dt
             d.dst = s.dst;
             d.dst_lo = s.dst_lo;
             KERNEL_TRY(fi::stem_conv_launch(d, st));
+        } else if (s.kind == STEP_INC_FUSED) {
+            fi::StemDesc d;
+            memset(&d, 0, sizeof d);
+            d.src[0] = to_src(in0);
+            d.src[1] = to_src(in1);
+            d.is_u8 = in_dtype == FI_IN_U8;
+            d.cin = net->n_channels;
+            d.N = N;
+            d.H = H;
+            d.W = W;
+            d.wpack = net->stem_w.p;
+            d.bias = static_cast<const float*>(net->stem_b.p);
+            KERNEL_TRY(fi::inc_fused_launch(d, s.conv, N, net->num_sms, st));
         } else if (s.kind == STEP_UPSAMPLE) {
             KERNEL_TRY(fi::upsample2x_launch(s.src, s.dst, N, s.h, s.w, s.C, st, s.src_lo, s.dst_lo));
         } else {
@@ -885,7 +921,7 @@ int fiNetGetProfile(fiNet* net, fiLaunchProfile* out, int capacity, int* count) 
         const Step& s = pl.steps[i];
         memset(&out[i], 0, sizeof out[i]);
         snprintf(out[i].name, sizeof out[i].name, "%s", s.name);
-        out[i].kind = s.kind == STEP_CONV ? 1 : (s.kind == STEP_STEM ? 0 : 2);
+        out[i].kind = (s.kind == STEP_CONV || s.kind == STEP_INC_FUSED) ? 1 : (s.kind == STEP_STEM ? 0 : 2);
         out[i].flops = s.flops * pl.last_n;
         out[i].bytes = s.bytes * pl.last_n + s.weight_bytes;
         out[i].calls = net->prof_calls;

@@ -194,7 +194,8 @@ def test_batch_sizes_share_one_plan(cuda_device):
     assert torch.equal(one[0], full[2]) and torch.equal(two, full[1:3])
     fl4, launches = net.cost(4, 48, 80)
     fl1, _ = net.cost(1, 48, 80)
-    assert abs(fl4 - 4 * fl1) < 1 and abs(fl1 - O.flops_per_forward(1, 48, 80)) < 1 and launches == 22
+    # 21 launches: the grey bf16 network computes inc.double_conv.0 inside inc.double_conv.3's kernel (22 without)
+    assert abs(fl4 - 4 * fl1) < 1 and abs(fl1 - O.flops_per_forward(1, 48, 80)) < 1 and launches == 21
     again = net.forward(f[:4], f[1:5], want_f32=True)[0]
     assert torch.equal(again, full)
 
@@ -399,3 +400,33 @@ def test_arena_liveness_reuse(cuda_device, monkeypatch, bilinear, precision):
     with pytest.raises(E.FiError, match="taps are unavailable"):
         lean.read_activation("inc", 3)
     assert plain.read_activation("inc", 3).shape == (3, 64, 70, 118)
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 16, 16), (3, 70, 118), (2, 135, 240), (1, 257, 97)])
+def test_fused_inc_kernel_is_bit_identical_to_stem_plus_conv(cuda_device, monkeypatch, n, h, w):
+    """conv_inc_fused.cu (stem computed inside inc.double_conv.3's kernel, inc.mid never in HBM) against the two separate
+    kernels (FI_FUSE_INC=0): same arithmetic in the same order, so the `inc` tensor, the pooled tensor's consumer
+    (`down1`) and the network output must be bit-identical — u8 and fp32 inputs, partial tiles on every border."""
+    from model import _engine as E
+    sd = O.stress_state_dict(O.init_state_dict(0, 2, 1, False), seed=3)
+    f1, f2 = frames(81, n, 1, h, w).to(cuda_device), frames(82, n, 1, h, w).to(cuda_device)
+    x1 = O.preprocess_u8(f1.cpu().numpy()).to(cuda_device)
+    x2 = O.preprocess_u8(f2.cpu().numpy()).to(cuda_device)
+    fused = E.Net(cuda_device, 2, 1, False)
+    fused.load_state_dict(sd)
+    assert fused.cost(n, h, w)[1] == 21
+    got_u8 = fused.forward(f1, f2, want_f32=True, want_u8=True)
+    taps_fused = {k: fused.read_activation(k, n) for k in ("inc", "down1")}
+    got_f32 = fused.forward(x1, x2, want_f32=True)[0].clone()
+    monkeypatch.setenv("FI_FUSE_INC", "0")
+    plain = E.Net(cuda_device, 2, 1, False)
+    plain.load_state_dict(sd)
+    assert plain.cost(n, h, w)[1] == 22
+    want_u8 = plain.forward(f1, f2, want_f32=True, want_u8=True)
+    for k, v in taps_fused.items():
+        assert torch.equal(v, plain.read_activation(k, n)), f"tap {k} differs"
+    assert torch.equal(got_u8[0], want_u8[0]) and torch.equal(got_u8[1], want_u8[1])
+    assert torch.equal(got_f32, plain.forward(x1, x2, want_f32=True)[0])
+    # and both agree with the oracle
+    ref = O.unet_forward(sd, torch.cat([x1.cpu(), x2.cpu()], 1))
+    assert ((got_f32.cpu() - ref).norm() / ref.norm()).item() < 2e-2
