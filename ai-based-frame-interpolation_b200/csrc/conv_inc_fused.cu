@@ -10,9 +10,18 @@
 //   halo[2]    2 x 36 KB   10 x 18 pixels at pitch 16 (slot = hy*16 + hx, 128 swizzled bytes per pixel), double buffered
 //   conv W     72 KB       nine [64 x 64] tap slabs, resident        stem W   8 KB    one [64 x 64] hi/lo-split slab
 //   stem A     2 x 16 KB   im2col rows of the two stem M tiles       input    4 KB    (8+4) x (16+4) raw pixels x C_in
-// Warp roles (544 threads): 0..7 im2col producers (thread = halo pixel), 8 TMEM owner + MMA issuer + weight loads,
-// 9..12 mid epilogue (stem accumulator -> bias, ReLU, bf16 -> halo buffer; zero outside the image = the conv padding),
-// 13..16 final epilogue (conv accumulator -> bias, ReLU, bf16, 2x2 max pool -> TMA stores), TMEM: 2 x 64 conv + 2 x 64 stem.
+// Warp roles (544 threads): 0..3 im2col producers (thread = two halo pixels, one per stem M tile), 4 TMEM owner + MMA
+// issuer + weight loads, 5..8 mid epilogue (stem accumulator -> bias, ReLU, bf16 -> halo buffer; zero outside the image
+// = the conv padding), 9..16 final epilogue in two sets that alternate tiles (conv accumulator -> bias, ReLU, bf16, 2x2
+// max pool -> TMA stores). TMEM: 2 x 64 conv + 2 x 64 stem columns. First measurement (8 producer warps, one final
+// set): every role waited ~80 % of the time except the two epilogues, each busy ~3 000 cycles per tile against 2 235
+// cycles of MMAs (profiles/r02_fused_inc.md) — hence two final sets, the stem bias in shared memory, fewer producers.
+// STATUS: correct (bit-identical, tests/test_gpu_unet.py) but NOT faster — 1.06 ms for four 1080p pairs against 0.37 ms
+// (stem) + 0.59 ms (conv) for the two separate launches, so the schedule uses it only with FI_FUSE_INC=1. With the
+// issuer decoupled (two stem accumulator sets) every role still waits most of the time: the tile period (~4 500 cycles)
+// is set by the latency chain stem MMA -> mid epilogue (~2 500 cycles for two M tiles at 96 registers per thread, with
+// spills) -> conv MMAs, not by any unit's throughput; 17 warps leave 96 registers per thread. Next step: one mid-epilogue
+// warp set per stem M tile and setmaxnreg to move registers from the producers to the epilogues.
 // The issuer runs one tile ahead with the stem: stem(t+1) is issued before conv(t), so the halo of tile t+1 is built
 // (mid epilogue) while the tensor pipe works through the 36 MMAs of tile t.
 #include "aux_kernels.cuh"
@@ -34,13 +43,15 @@ constexpr int FH_BYTES = FH_PITCH * FH_H * 128;          // 36864
 constexpr int FIN_W = FT_W + 4, FIN_H = FT_H + 4;        // raw input tile: 12 x 20
 constexpr int FIN_PITCH = 13;
 constexpr int F_THREADS = 17 * 32;
-constexpr int F_PRODUCERS = 256;
-constexpr int F_TMEM_COLS = 256;
-constexpr int F_STEM_COL = 128;                          // TMEM columns [128, 256): the two stem M tiles
+constexpr int F_PRODUCERS = 128;
+constexpr int F_SA1_ROWS = 64;                           // stem M tile 1 holds 52 valid rows: only 64 are backed by memory
+constexpr int F_TMEM_COLS = 512;
+constexpr int F_STEM_COL = 128;                          // TMEM columns [128, 384): two sets of the two stem M tiles
 
 __host__ __device__ constexpr int fused_in_bytes(int cin) { return 2 * cin * FIN_H * FIN_PITCH * 4; }
 __host__ __device__ constexpr int fused_smem_bytes(int cin) {
-    return 1024 + 2 * FH_BYTES + 9 * 8192 + 8192 + 2 * 16384 + 4 * (4096 + 1024) + 256 + 1040 + fused_in_bytes(cin);
+    return 1024 + 2 * FH_BYTES + 9 * 8192 + 8192 + (16384 + F_SA1_ROWS * 128) + 8 * (4096 + 1024) + 256 + 1040 + 256 +
+           fused_in_bytes(cin);
 }
 
 struct FusedParams {
@@ -83,22 +94,26 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     const uint32_t smem_cw = smem_halo + 2 * FH_BYTES;
     const uint32_t smem_sw = smem_cw + 9 * 8192;
     const uint32_t smem_sa = smem_sw + 8192;
-    const uint32_t smem_stage = smem_sa + 2 * 16384;
-    const uint32_t smem_pool = smem_stage + 4 * 4096;
-    const uint32_t smem_bar = smem_pool + 4 * 1024;
+    // stem A tile 1 is backed by 64 rows only; the MMA's rows 64..127 read whatever follows (staging) into accumulator
+    // lanes that nobody reads (halo pixels 180..255 do not exist)
+    const uint32_t smem_stage = smem_sa + 16384 + F_SA1_ROWS * 128;
+    const uint32_t smem_pool = smem_stage + 8 * 4096;
+    const uint32_t smem_bar = smem_pool + 8 * 1024;
     const uint32_t bar_sa_full = smem_bar;            // 2: stem A tile mt built (4 producer warps each)
     const uint32_t bar_sa_empty = smem_bar + 16;      // 2: stem MMAs of tile mt retired
-    const uint32_t bar_st_full = smem_bar + 32;       // 1: stem accumulators complete
-    const uint32_t bar_st_empty = smem_bar + 40;      // 1: mid epilogue has read them (4 warps)
-    const uint32_t bar_h_full = smem_bar + 48;        // 2: halo buffer written (4 mid-epilogue warps)
-    const uint32_t bar_h_empty = smem_bar + 64;       // 2: conv MMAs reading it retired
-    const uint32_t bar_t_full = smem_bar + 80;        // 2: conv accumulator complete
-    const uint32_t bar_t_empty = smem_bar + 96;       // 2: final epilogue has read it (4 warps)
-    const uint32_t bar_w = smem_bar + 112;            // 1: weights resident
-    const uint32_t tmem_slot = smem_bar + 120;
+    const uint32_t bar_st_full = smem_bar + 32;       // 2: stem accumulator set complete
+    const uint32_t bar_st_empty = smem_bar + 48;      // 2: mid epilogue has read it (4 warps)
+    const uint32_t bar_h_full = smem_bar + 64;        // 2: halo buffer written (4 mid-epilogue warps)
+    const uint32_t bar_h_empty = smem_bar + 80;       // 2: conv MMAs reading it retired
+    const uint32_t bar_t_full = smem_bar + 96;        // 2: conv accumulator complete
+    const uint32_t bar_t_empty = smem_bar + 112;      // 2: final epilogue has read it (4 warps)
+    const uint32_t bar_w = smem_bar + 128;            // 1: weights resident
+    const uint32_t tmem_slot = smem_bar + 136;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + (smem_bar + 256 - smem_u32(smem_raw)));
-    uint32_t* in_tile = lut + 260;
+    float* sbias = reinterpret_cast<float*>(lut + 260);          // stem bias: read per pixel by the mid epilogue
+    const uint32_t sbias_addr = smem_bar + 256 + 1040;
+    uint32_t* in_tile = lut + 260 + 64;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -109,7 +124,8 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         lut[threadIdx.x] = (h >> 16) | bf16_bits_fused(v - __uint_as_float(h));
         if (threadIdx.x == 0) lut[256] = 0u;
     }
-    if (threadIdx.x == 256) {
+    if (threadIdx.x >= 288 && threadIdx.x < 352) sbias[threadIdx.x - 288] = __ldg(fp.stem_bias + threadIdx.x - 288);
+    if (threadIdx.x == 128) {
         tma_prefetch_desc(&maps.b);
         tma_prefetch_desc(&map_stem_w);
         tma_prefetch_desc(&maps.out[0]);
@@ -121,13 +137,13 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             mbar_init(bar_h_empty + 8 * i, 1);
             mbar_init(bar_t_full + 8 * i, 1);
             mbar_init(bar_t_empty + 8 * i, 4);
+            mbar_init(bar_st_full + 8 * i, 1);
+            mbar_init(bar_st_empty + 8 * i, 4);
         }
-        mbar_init(bar_st_full, 1);
-        mbar_init(bar_st_empty, 4);
         mbar_init(bar_w, 1);
         fence_mbar_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, F_TMEM_COLS);
+    if (warp == 4) tmem_alloc(tmem_slot, F_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -144,13 +160,9 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         x0 = (r % fp.tiles_x) * FT_W;
     };
 
-    if (warp < 8) {
-        // ------------------------------------------------------------ im2col producers: thread = halo pixel (stem row)
-        const int pth = threadIdx.x;           // 0..255
-        const int mt = pth >> 7, m = pth & 127;
-        const int hpix = mt * 128 + m;         // halo pixel index, valid below FH_PIXELS
-        const bool row_valid = hpix < FH_PIXELS;
-        const int hy = hpix / FH_W, hx = hpix - hy * FH_W;
+    if (warp < 4) {
+        // ------------------------------------------------------------ im2col producers: thread = two halo pixels
+        const int m = threadIdx.x;             // 0..127: stem row m of both M tiles
         constexpr int PLANE = FIN_H * FIN_PITCH;
         constexpr int IN_ELEMS = CIN * FIN_H * FIN_W;
         constexpr int NLOAD = (IN_ELEMS + F_PRODUCERS - 1) / F_PRODUCERS;
@@ -160,7 +172,7 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             tile_origin(t, img, y0, x0);
 #pragma unroll
             for (int k = 0; k < NLOAD; ++k) {
-                const int i = pth + F_PRODUCERS * k;
+                const int i = m + F_PRODUCERS * k;
                 uint32_t v = U8 ? 256u : 0u;   // out of bounds -> zero padding of the stem conv
                 if (i < IN_ELEMS) {
                     const int c = i / (FIN_H * FIN_W);
@@ -186,7 +198,7 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             uint32_t* tile = in_tile + (it & 1) * CIN * PLANE;
 #pragma unroll
             for (int k = 0; k < NLOAD; ++k) {
-                const int i = pth + F_PRODUCERS * k;
+                const int i = m + F_PRODUCERS * k;
                 if (i < IN_ELEMS) {
                     const int c = i / (FIN_H * FIN_W);
                     const int rr = (i - c * FIN_H * FIN_W) / FIN_W;
@@ -205,38 +217,47 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             if (t + static_cast<int>(gridDim.x) < total_tiles) fetch(t + gridDim.x);
             // two input buffers: one barrier per tile (a thread re-writes buffer b only after every producer passed the
             // barrier of the tile in between, i.e. after all of them finished reading b)
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            uint32_t hl[KT];   // low half = bf16 hi part, high half = bf16 lo part of the normalised input
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+            for (int mt = 0; mt < 2; ++mt) {
+                const int hpix = mt * 128 + m;     // halo pixel of this row, valid below FH_PIXELS
+                const bool backed = mt == 0 || m < F_SA1_ROWS;
+                uint32_t hl[KT];   // low half = bf16 hi part, high half = bf16 lo part of the normalised input
 #pragma unroll
-            for (int e = 0; e < KT; ++e) hl[e] = 0u;
-            if (row_valid) {
-                const uint32_t* px = tile + hy * FIN_PITCH + hx;
+                for (int e = 0; e < KT; ++e) hl[e] = 0u;
+                if (hpix < FH_PIXELS) {
+                    const int hy = hpix / FH_W, hx = hpix - hy * FH_W;
+                    const uint32_t* px = tile + hy * FIN_PITCH + hx;
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap)
+                    for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-                    for (int c = 0; c < CIN; ++c) hl[tap * CIN + c] = px[c * PLANE + (tap / 3) * FIN_PITCH + (tap % 3)];
-            }
-            auto elem = [&](int e) -> uint32_t {   // 16-bit K element e of the row [x_hi | x_hi | x_lo | 0]
-                return e < KT ? (hl[e] & 0xffffu)
-                              : (e < 2 * KT ? (hl[e - KT] & 0xffffu) : (e < 3 * KT ? (hl[e - 2 * KT] >> 16) : 0u));
-            };
-            mbar_wait(bar_sa_empty + 8 * mt, (it & 1) ^ 1);
-            const uint32_t row = smem_sa + mt * 16384 + m * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                uint32_t wv[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int e = j * 8 + q * 2;
-                    wv[q] = elem(e) | (elem(e + 1) << 16);
+                        for (int c = 0; c < CIN; ++c)
+                            hl[tap * CIN + c] = px[c * PLANE + (tap / 3) * FIN_PITCH + (tap % 3)];
                 }
-                st_shared_v4(row + ((j ^ (m & 7)) << 4), wv[0], wv[1], wv[2], wv[3]);
+                auto elem = [&](int e) -> uint32_t {   // 16-bit K element e of the row [x_hi | x_hi | x_lo | 0]
+                    return e < KT ? (hl[e] & 0xffffu)
+                                  : (e < 2 * KT ? (hl[e - KT] & 0xffffu) : (e < 3 * KT ? (hl[e - 2 * KT] >> 16) : 0u));
+                };
+                mbar_wait(bar_sa_empty + 8 * mt, (it & 1) ^ 1);
+                if (backed) {
+                    const uint32_t row = smem_sa + mt * 16384 + m * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint32_t wv[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int e = j * 8 + q * 2;
+                            wv[q] = elem(e) | (elem(e + 1) << 16);
+                        }
+                        st_shared_v4(row + ((j ^ (m & 7)) << 4), wv[0], wv[1], wv[2], wv[3]);
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_sa_full + 8 * mt);
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_sa_full + 8 * mt);
         }
-    } else if (warp == 8) {
+    } else if (warp == 4) {
         // ------------------------------------------------------------ weights (once) + MMA issue
         if (elect_one()) {
             mbar_expect_tx(bar_w, 10 * 8192);
@@ -247,8 +268,9 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         mbar_wait(bar_w, 0);
         int stems = 0;
         auto issue_stem = [&]() {
-            const uint32_t par = stems & 1;
-            mbar_wait(bar_st_empty, par ^ 1);   // the mid epilogue has read the previous stem accumulators
+            const uint32_t par = stems & 1;     // stem A tiles: one use per tile
+            const int sset = stems & 1;         // stem accumulators: two sets, so the issuer never waits for the mid
+            mbar_wait(bar_st_empty + 8 * sset, ((stems >> 1) & 1) ^ 1);   // epilogue of the tile just before this one
             tc_fence_after();
             const uint64_t db = umma_desc_sw128(smem_sw);
             for (int smt = 0; smt < 2; ++smt) {
@@ -258,9 +280,9 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_bf16_ss(tmem_base + F_STEM_COL + smt * 64, da + 2 * k, db + 2 * k, IDESC, k != 0);
+                        umma_bf16_ss(tmem_base + F_STEM_COL + sset * 128 + smt * 64, da + 2 * k, db + 2 * k, IDESC, k != 0);
                     umma_commit(bar_sa_empty + 8 * smt);
-                    if (smt == 1) umma_commit(bar_st_full);
+                    if (smt == 1) umma_commit(bar_st_full + 8 * sset);
                 }
                 __syncwarp();
             }
@@ -292,22 +314,21 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
                 __syncwarp();
             }
         }
-    } else if (warp < 13) {
+    } else if (warp < 9) {
         // ------------------------------------------------------------ mid epilogue: stem accumulators -> halo buffer
         const int q = warp & 3;
-        const float4* bias4 = reinterpret_cast<const float4*>(fp.stem_bias);
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             int img, y0, x0;
             tile_origin(t, img, y0, x0);
             const int hs = it & 1;
-            mbar_wait(bar_st_full, it & 1);
+            mbar_wait(bar_st_full + 8 * hs, (it >> 1) & 1);
             mbar_wait(bar_h_empty + 8 * hs, ((it >> 1) & 1) ^ 1);   // conv MMAs of the tile before last retired
             tc_fence_after();
             const uint32_t hbuf = smem_halo + hs * FH_BYTES;
 #pragma unroll 1
             for (int smt = 0; smt < 2; ++smt) {
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + F_STEM_COL + smt * 64;
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + F_STEM_COL + hs * 128 + smt * 64;
                 uint32_t v0[32], v1[32];
                 tmem_ld_32x32b_x32(taddr, v0);
                 tmem_ld_32x32b_x32(taddr + 32, v1);
@@ -321,7 +342,11 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
                     const uint32_t rowaddr = hbuf + slot * 128;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {   // 16-byte chunk j = channels 8j .. 8j+7
-                        const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
+                        const uint4 c0 = ld_shared_v4(sbias_addr + 32 * j), c1 = ld_shared_v4(sbias_addr + 32 * j + 16);
+                        const float4 b0 = make_float4(__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z),
+                                                      __uint_as_float(c0.w));
+                        const float4 b1 = make_float4(__uint_as_float(c1.x), __uint_as_float(c1.y), __uint_as_float(c1.z),
+                                                      __uint_as_float(c1.w));
                         const uint32_t* v = j < 4 ? v0 : v1;
                         const int o = (j & 3) * 8;
                         uint32_t hw[4];
@@ -338,22 +363,25 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(bar_st_empty);
+                mbar_arrive(bar_st_empty + 8 * hs);
                 mbar_arrive(bar_h_full + 8 * hs);
             }
         }
     } else {
-        // ------------------------------------------------------------ final epilogue warps 13..16
+        // ------------------------------------------------------------ final epilogue warps 9..16: two sets, set s owns
+        // the tiles with (iteration & 1) == s and therefore conv accumulator s
         const int q = warp & 3;
-        const int ew = warp - 13;
+        const int ew = warp - 9;
+        const int set = ew >> 2;
         const uint32_t my_stage = smem_stage + ew * 4096;
         const uint32_t my_pool = smem_pool + ew * 1024;
         int buf = 0;
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            if ((it & 1) != set) continue;
             int img, y0, x0;
             tile_origin(t, img, y0, x0);
-            const int acc = it & 1;
+            const int acc = set;
             mbar_wait(bar_t_full + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 64;
@@ -369,7 +397,7 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 4) {
         tc_fence_after();
         tmem_dealloc(tmem_base, F_TMEM_COLS);
     }
