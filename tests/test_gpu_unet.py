@@ -433,3 +433,17 @@ def test_fused_inc_kernel_is_bit_identical_to_stem_plus_conv(cuda_device, monkey
     # and both agree with the oracle
     ref = O.unet_forward(sd, torch.cat([x1.cpu(), x2.cpu()], 1))
     assert ((got_f32.cpu() - ref).norm() / ref.norm()).item() < 2e-2
+
+
+@pytest.mark.parametrize("n_channels,n_classes,bilinear", [(1, 2, True), (1, 1, False), (4, 1, True), (3, 3, False)])
+def test_other_channel_counts(cuda_device, n_channels, n_classes, bilinear):
+    """UNet is channel-generic (reference model/unet.py:66): one input channel (the fused inc kernel's other
+    instantiation), three and four (the stand-alone stem kernel with two K slabs), several output classes."""
+    sd = O.init_state_dict(5, n_channels, n_classes, bilinear, prefix="")
+    m = build(sd, cuda_device, n_channels, n_classes, bilinear, wrapper=False)
+    x = O.preprocess_u8(frames(9, 2, n_channels, 37, 52).numpy())
+    ref = O.unet_forward(sd, x)
+    got = m(x.to(cuda_device)).cpu()
+    assert got.shape == (2, n_classes, 37, 52)
+    assert (got - ref).abs().max().item() / 2 <= 2e-2
+    assert ((got - ref).norm() / ref.norm()).item() < 2e-2
