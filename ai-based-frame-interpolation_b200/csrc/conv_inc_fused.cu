@@ -10,10 +10,10 @@
 //   halo[2]    2 x 36 KB   10 x 18 pixels at pitch 16 (slot = hy*16 + hx, 128 swizzled bytes per pixel), double buffered
 //   conv W     72 KB       nine [64 x 64] tap slabs, resident        stem W   8 KB    one [64 x 64] hi/lo-split slab
 //   stem A     2 x 16 KB   im2col rows of the two stem M tiles       input    4 KB    (8+4) x (16+4) raw pixels x C_in
-// Warp roles (672 threads): 0..3 im2col producers (thread = two halo pixels, one per stem M tile), 4 TMEM owner + MMA
-// issuer + weight loads, 5..12 mid epilogue, one set per stem M tile (stem accumulator -> bias, ReLU, bf16 -> halo buffer;
-// zero outside the image = the conv padding), 13..20 final epilogue in two sets that alternate tiles (conv accumulator
-// -> bias, ReLU, bf16, 2x2 max pool -> TMA stores). TMEM: 2 x 64 conv + 2 x 64 stem columns. First measurement (8 producer warps, one final
+// Warp roles (736 threads): 0..5 im2col producers (thread = one halo pixel: 4 warps for stem M tile 0, 2 for the 64 backed
+// rows of M tile 1), 6 TMEM owner + MMA issuer + weight loads, 7..14 mid epilogue, one set per stem M tile (stem
+// accumulator -> bias, ReLU, bf16 -> halo buffer; zero outside the image = the conv padding), 15..22 final epilogue in
+// two sets that alternate tiles (conv accumulator -> bias, ReLU, bf16, 2x2 max pool -> TMA stores). TMEM: 2 x 64 conv + 2 x 64 stem columns. First measurement (8 producer warps, one final
 // set): every role waited ~80 % of the time except the two epilogues, each busy ~3 000 cycles per tile against 2 235
 // cycles of MMAs (profiles/r02_fused_inc.md) — hence two final sets, the stem bias in shared memory, fewer producers.
 // Measured (B200, four 1080p pairs): 0.98 ms serialised against 0.37 (stem) + 0.59 (conv) for the two launches — no gain
@@ -43,8 +43,8 @@ constexpr int FH_PIXELS = FH_W * FH_H;                   // 180 stem rows
 constexpr int FH_BYTES = FH_PITCH * FH_H * 128;          // 36864
 constexpr int FIN_W = FT_W + 4, FIN_H = FT_H + 4;        // raw input tile: 12 x 20
 constexpr int FIN_PITCH = 13;
-constexpr int F_THREADS = 21 * 32;
-constexpr int F_PRODUCERS = 128;
+constexpr int F_THREADS = 23 * 32;
+constexpr int F_PRODUCERS = 192;                         // 4 warps: stem M tile 0, 2 warps: the 64 backed rows of M tile 1
 constexpr int F_SA1_ROWS = 64;                           // stem M tile 1 holds 52 valid rows: only 64 are backed by memory
 constexpr int F_TMEM_COLS = 512;
 constexpr int F_STEM_COL = 128;                          // TMEM columns [128, 384): two sets of the two stem M tiles
@@ -128,13 +128,13 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     }
     if (threadIdx.x >= 288 && threadIdx.x < 352) sbias[threadIdx.x - 288] = __ldg(fp.stem_bias + threadIdx.x - 288);
     if (threadIdx.x >= 352 && threadIdx.x < 416) sbias[threadIdx.x - 288] = __ldg(p.bias + threadIdx.x - 352);
-    if (threadIdx.x == 128) {
+    if (threadIdx.x == 192) {
         tma_prefetch_desc(&maps.b);
         tma_prefetch_desc(&map_stem_w);
         tma_prefetch_desc(&maps.out[0]);
         tma_prefetch_desc(&maps.pool[0]);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(bar_sa_full + 8 * i, 4);
+            mbar_init(bar_sa_full + 8 * i, i == 0 ? 4 : 2);
             mbar_init(bar_sa_empty + 8 * i, 1);
             mbar_init(bar_h_full + 8 * i, 8);
             mbar_init(bar_h_empty + 8 * i, 1);
@@ -146,7 +146,7 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         mbar_init(bar_w, 1);
         fence_mbar_init();
     }
-    if (warp == 4) tmem_alloc(tmem_slot, F_TMEM_COLS);
+    if (warp == 6) tmem_alloc(tmem_slot, F_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -163,9 +163,12 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         x0 = (r % fp.tiles_x) * FT_W;
     };
 
-    if (warp < 4) {
-        // ------------------------------------------------------------ im2col producers: thread = two halo pixels
-        const int m = threadIdx.x;             // 0..127: stem row m of both M tiles
+    if (warp < 6) {
+        // ------------------------------------------------------------ im2col producers: thread = one halo pixel (stem row).
+        // Warps 0..3 build stem M tile 0, warps 4..5 the 64 backed rows of M tile 1 (52 of them are halo pixels).
+        const int pth = threadIdx.x;           // 0..191
+        const int mt = pth >> 7, m = pth & 127;
+        const int hpix = mt * 128 + m;         // halo pixel of this row, valid below FH_PIXELS
         constexpr int PLANE = FIN_H * FIN_PITCH;
         constexpr int IN_ELEMS = CIN * FIN_H * FIN_W;
         constexpr int NLOAD = (IN_ELEMS + F_PRODUCERS - 1) / F_PRODUCERS;
@@ -175,7 +178,7 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             tile_origin(t, img, y0, x0);
 #pragma unroll
             for (int k = 0; k < NLOAD; ++k) {
-                const int i = m + F_PRODUCERS * k;
+                const int i = pth + F_PRODUCERS * k;
                 uint32_t v = U8 ? 256u : 0u;   // out of bounds -> zero padding of the stem conv
                 if (i < IN_ELEMS) {
                     const int c = i / (FIN_H * FIN_W);
@@ -201,7 +204,7 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             uint32_t* tile = in_tile + (it & 1) * CIN * PLANE;
 #pragma unroll
             for (int k = 0; k < NLOAD; ++k) {
-                const int i = m + F_PRODUCERS * k;
+                const int i = pth + F_PRODUCERS * k;
                 if (i < IN_ELEMS) {
                     const int c = i / (FIN_H * FIN_W);
                     const int rr = (i - c * FIN_H * FIN_W) / FIN_W;
@@ -220,47 +223,39 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             if (t + static_cast<int>(gridDim.x) < total_tiles) fetch(t + gridDim.x);
             // two input buffers: one barrier per tile (a thread re-writes buffer b only after every producer passed the
             // barrier of the tile in between, i.e. after all of them finished reading b)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll 1
-            for (int mt = 0; mt < 2; ++mt) {
-                const int hpix = mt * 128 + m;     // halo pixel of this row, valid below FH_PIXELS
-                const bool backed = mt == 0 || m < F_SA1_ROWS;
-                uint32_t hl[KT];   // low half = bf16 hi part, high half = bf16 lo part of the normalised input
+            asm volatile("bar.sync 1, 192;" ::: "memory");
+            uint32_t hl[KT];   // low half = bf16 hi part, high half = bf16 lo part of the normalised input
 #pragma unroll
-                for (int e = 0; e < KT; ++e) hl[e] = 0u;
-                if (hpix < FH_PIXELS) {
-                    const int hy = hpix / FH_W, hx = hpix - hy * FH_W;
-                    const uint32_t* px = tile + hy * FIN_PITCH + hx;
+            for (int e = 0; e < KT; ++e) hl[e] = 0u;
+            if (hpix < FH_PIXELS) {
+                const int hy = hpix / FH_W, hx = hpix - hy * FH_W;
+                const uint32_t* px = tile + hy * FIN_PITCH + hx;
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap)
+                for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-                        for (int c = 0; c < CIN; ++c)
-                            hl[tap * CIN + c] = px[c * PLANE + (tap / 3) * FIN_PITCH + (tap % 3)];
-                }
-                auto elem = [&](int e) -> uint32_t {   // 16-bit K element e of the row [x_hi | x_hi | x_lo | 0]
-                    return e < KT ? (hl[e] & 0xffffu)
-                                  : (e < 2 * KT ? (hl[e - KT] & 0xffffu) : (e < 3 * KT ? (hl[e - 2 * KT] >> 16) : 0u));
-                };
-                mbar_wait(bar_sa_empty + 8 * mt, (it & 1) ^ 1);
-                if (backed) {
-                    const uint32_t row = smem_sa + mt * 16384 + m * 128;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        uint32_t wv[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int e = j * 8 + q * 2;
-                            wv[q] = elem(e) | (elem(e + 1) << 16);
-                        }
-                        st_shared_v4(row + ((j ^ (m & 7)) << 4), wv[0], wv[1], wv[2], wv[3]);
-                    }
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_sa_full + 8 * mt);
+                    for (int c = 0; c < CIN; ++c) hl[tap * CIN + c] = px[c * PLANE + (tap / 3) * FIN_PITCH + (tap % 3)];
             }
+            auto elem = [&](int e) -> uint32_t {   // 16-bit K element e of the row [x_hi | x_hi | x_lo | 0]
+                return e < KT ? (hl[e] & 0xffffu)
+                              : (e < 2 * KT ? (hl[e - KT] & 0xffffu) : (e < 3 * KT ? (hl[e - 2 * KT] >> 16) : 0u));
+            };
+            mbar_wait(bar_sa_empty + 8 * mt, (it & 1) ^ 1);
+            const uint32_t row = smem_sa + mt * 16384 + m * 128;   // M tile 1: m < 64 (its producers are warps 4, 5)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t wv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = j * 8 + q * 2;
+                    wv[q] = elem(e) | (elem(e + 1) << 16);
+                }
+                st_shared_v4(row + ((j ^ (m & 7)) << 4), wv[0], wv[1], wv[2], wv[3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sa_full + 8 * mt);
         }
-    } else if (warp == 4) {
+    } else if (warp == 6) {
         // ------------------------------------------------------------ weights (once) + MMA issue
         if (elect_one()) {
             mbar_expect_tx(bar_w, 10 * 8192);
@@ -317,11 +312,11 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
                 __syncwarp();
             }
         }
-    } else if (warp < 13) {
-        // ------------------------------------------------------------ mid epilogue, warps 5..12: set (warp-5)/4 owns stem
+    } else if (warp < 15) {
+        // ------------------------------------------------------------ mid epilogue, warps 7..14: set (warp-7)/4 owns stem
         // M tile `smt`; 32 accumulator columns at a time (register budget: 80 per thread with 21 warps)
         const int q = warp & 3;
-        const int smt = (warp - 5) >> 2;
+        const int smt = (warp - 7) >> 2;
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             int img, y0, x0;
@@ -375,11 +370,11 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             }
         }
     } else {
-        // ------------------------------------------------------------ final epilogue warps 13..20: two sets, set s owns
+        // ------------------------------------------------------------ final epilogue warps 15..22: two sets, set s owns
         // the tiles with (iteration & 1) == s and therefore conv accumulator s. Same arithmetic as epilogue_chunk_halo
         // (bias, ReLU, one bf16 rounding, 2x2 max of the rounded values), 32 columns at a time.
         const int q = warp & 3;
-        const int ew = warp - 13;
+        const int ew = warp - 15;
         const int set = ew >> 2;
         const uint32_t sbuf = smem_stage + ew * 4096;
         const uint32_t pbuf = smem_pool + ew * 1024;
@@ -456,7 +451,7 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 6) {
         tc_fence_after();
         tmem_dealloc(tmem_base, F_TMEM_COLS);
     }
