@@ -116,7 +116,8 @@ const char* conv_halo_pair_launch(const ConvLaunch& l, cudaStream_t stream);
 // conv_inc_fused.cu: inc.double_conv.0 (stem) computed inside inc.double_conv.3's kernel (grey network, bf16 mode)
 struct StemDesc;
 bool inc_fused_eligible(int cin, const ConvLaunch& conv);
-const char* inc_fused_launch(const StemDesc& d, const ConvLaunch& conv, int n_img, int num_sms, cudaStream_t stream);
+const char* inc_fused_launch(const StemDesc& d, const ConvLaunch& conv, const float* host_bias, int n_img, int num_sms,
+                             cudaStream_t stream);
 
 // conv_halo.cu
 bool conv_halo_eligible(const ConvDesc& d);

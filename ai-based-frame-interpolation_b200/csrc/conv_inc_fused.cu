@@ -13,16 +13,20 @@
 // Warp roles (736 threads): 0..5 im2col producers (thread = one halo pixel: 4 warps for stem M tile 0, 2 for the 64 backed
 // rows of M tile 1), 6 TMEM owner + MMA issuer + weight loads, 7..14 mid epilogue, one set per stem M tile (stem
 // accumulator -> bias, ReLU, bf16 -> halo buffer; zero outside the image = the conv padding), 15..22 final epilogue in
-// two sets that alternate tiles (conv accumulator -> bias, ReLU, bf16, 2x2 max pool -> TMA stores). TMEM: 2 x 64 conv + 2 x 64 stem columns. First measurement (8 producer warps, one final
-// set): every role waited ~80 % of the time except the two epilogues, each busy ~3 000 cycles per tile against 2 235
-// cycles of MMAs (profiles/r02_fused_inc.md) — hence two final sets, the stem bias in shared memory, fewer producers.
-// Measured (B200, four 1080p pairs): 0.98 ms serialised against 0.37 (stem) + 0.59 (conv) for the two launches — no gain
-// in isolation — but +2.3 % frames/s for the whole forward at the sustained, power-capped clock (403 vs 394 frames/s, three
-// alternating runs of 60 steps): 1 GB less HBM traffic per step. Four iterations (profiles/README.md): 8 producer warps +
-// one epilogue set 1.19 ms -> two final-epilogue sets, stem bias in shared memory 1.14 -> two stem accumulator sets (the
-// issuer no longer waits for the mid epilogue) 1.06 -> one mid-epilogue set per stem M tile, 32-column epilogue passes
-// (80 registers, no spills) 0.98. The tile period (~4 200 cycles) is now set by the shared-memory port: 264 KB of MMA
-// operand reads + ~100 KB of row / halo / staging traffic per tile at 128 B/cycle = 2 900 cycles at best.
+// two sets that alternate tiles (conv accumulator -> bias, ReLU, bf16, 2x2 max pool -> TMA stores). TMEM: 2 x 64 conv
+// columns + 2 sets x 2 M tiles x 64 stem columns. Both biases travel as kernel parameters (constant-bank operands).
+// Measured (B200, four 1080p pairs): 0.89 ms serialised against 0.22 + 0.74 ms for the two launches at the same clock,
+// +3 % frames/s for the whole forward at the sustained, power-capped clock (409 vs 397 frames/s, alternating runs of 60
+// steps): 1 GB less HBM traffic per step. Six iterations, each read off the ncu source page (profiles/README.md):
+//   1.19 ms  8 producer warps, one epilogue set: both epilogues busy ~3 000 cycles per tile, everything else waiting
+//   1.14     two final-epilogue sets, biases in shared memory
+//   1.06     two stem accumulator sets: the issuer no longer waits for the mid epilogue
+//   0.98     one mid-epilogue set per stem M tile, 32-column epilogue passes (80 registers, no spills)
+//   0.886    six producer warps, one halo pixel per thread: the issuer was waiting for the stem A tiles
+//   0.889    biases as constant-bank operands: -36 % shared-memory wavefronts, same time — the limit is bytes, not
+//            wavefronts: the issuer's barrier waits all succeed at once and every other role waits for it
+// The tile period (~3 300 cycles) is now 88 % of the shared-memory-port floor: 264 KB of MMA operand reads + ~100 KB of
+// row / halo / staging traffic per tile at 128 B/cycle = 2 900 cycles.
 // The issuer runs one tile ahead with the stem: stem(t+1) is issued before conv(t), so the halo of tile t+1 is built
 // (mid epilogue) while the tensor pipe works through the 36 MMAs of tile t.
 #include "aux_kernels.cuh"
@@ -58,7 +62,12 @@ __host__ __device__ constexpr int fused_smem_bytes(int cin) {
 struct FusedParams {
     PlaneSrc src[2];
     int N, H, W, tiles_x, tiles_y;
-    const float* stem_bias;
+};
+// Folded BatchNorm shifts by value: the epilogues read them as constant-bank operands of the FADDs (no shared-memory
+// loads: the per-pixel bias reads were 36 % of the kernel's shared-memory wavefronts and slowed the MMA operand fetch).
+struct FusedBias {
+    float stem[64];
+    float conv[64];
 };
 
 __device__ __forceinline__ float norm_u8_fused(uint8_t u) {
@@ -84,7 +93,7 @@ __device__ __forceinline__ uint64_t fused_halo_desc(uint32_t smem_addr) {
 template <int CIN, bool U8>
 __global__ void __launch_bounds__(F_THREADS, 1)
 inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CUtensorMap map_stem_w,
-                 const ConvKernelParams p, const FusedParams fp) {
+                 const ConvKernelParams p, const FusedParams fp, const FusedBias fb) {
     constexpr int KT = 9 * CIN;
     static_assert(3 * KT <= 64, "fused inc kernel: the hi/lo-split stem row must fit one 64-element K slab");
     constexpr uint32_t IDESC = umma_idesc_bf16(128, 64);
@@ -112,9 +121,6 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     const uint32_t tmem_slot = smem_bar + 136;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + (smem_bar + 256 - smem_u32(smem_raw)));
-    float* sbias = reinterpret_cast<float*>(lut + 260);          // stem bias (64) + conv bias (64): read per pixel
-    const uint32_t sbias_addr = smem_bar + 256 + 1040;           // by the mid / final epilogues
-    const uint32_t cbias_addr = sbias_addr + 256;
     uint32_t* in_tile = lut + 260 + 128;
 
     const int warp = threadIdx.x >> 5;
@@ -126,8 +132,6 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         lut[threadIdx.x] = (h >> 16) | bf16_bits_fused(v - __uint_as_float(h));
         if (threadIdx.x == 0) lut[256] = 0u;
     }
-    if (threadIdx.x >= 288 && threadIdx.x < 352) sbias[threadIdx.x - 288] = __ldg(fp.stem_bias + threadIdx.x - 288);
-    if (threadIdx.x >= 352 && threadIdx.x < 416) sbias[threadIdx.x - 288] = __ldg(p.bias + threadIdx.x - 352);
     if (threadIdx.x == 192) {
         tma_prefetch_desc(&maps.b);
         tma_prefetch_desc(&map_stem_w);
@@ -335,8 +339,8 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
                 const bool inside = yy >= 0 && yy < fp.H && xx >= 0 && xx < fp.W;   // outside: the conv's zero padding
                 const int slot = hy * FH_PITCH + hx;
                 const uint32_t rowaddr = hbuf + slot * 128;
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {   // unrolled: the bias indices below are compile-time constants
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + 32 * half, v);
                     tmem_ld_wait();
@@ -344,17 +348,12 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {   // 16-byte chunk j = channels 8j .. 8j+7
                             const int j = 4 * half + jj;
-                            const uint4 c0 = ld_shared_v4(sbias_addr + 32 * j), c1 = ld_shared_v4(sbias_addr + 32 * j + 16);
                             const int o = jj * 8;
                             uint32_t hw[4];
-                            hw[0] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 0]) + __uint_as_float(c0.x), 0.f),
-                                                fmaxf(__uint_as_float(v[o + 1]) + __uint_as_float(c0.y), 0.f));
-                            hw[1] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 2]) + __uint_as_float(c0.z), 0.f),
-                                                fmaxf(__uint_as_float(v[o + 3]) + __uint_as_float(c0.w), 0.f));
-                            hw[2] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 4]) + __uint_as_float(c1.x), 0.f),
-                                                fmaxf(__uint_as_float(v[o + 5]) + __uint_as_float(c1.y), 0.f));
-                            hw[3] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 6]) + __uint_as_float(c1.z), 0.f),
-                                                fmaxf(__uint_as_float(v[o + 7]) + __uint_as_float(c1.w), 0.f));
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                hw[e] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 2 * e]) + fb.stem[8 * j + 2 * e], 0.f),
+                                                    fmaxf(__uint_as_float(v[o + 2 * e + 1]) + fb.stem[8 * j + 2 * e + 1], 0.f));
                             if (!inside) hw[0] = hw[1] = hw[2] = hw[3] = 0u;
                             st_shared_v4(rowaddr + ((j ^ (slot & 7)) << 4), hw[0], hw[1], hw[2], hw[3]);
                         }
@@ -390,7 +389,7 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
             if (elect_one()) tma_store_wait_read<0>();   // the previous tile's stores have read the staging tiles
             __syncwarp();
             const uint32_t row = sbuf + lane * 128;      // lane = (row in 0..3) * 8 + column
-#pragma unroll 1
+#pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + 32 * half, v);
@@ -398,17 +397,12 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const int j = 4 * half + jj;
-                    const uint4 c0 = ld_shared_v4(cbias_addr + 32 * j), c1 = ld_shared_v4(cbias_addr + 32 * j + 16);
                     const int o = jj * 8;
                     uint32_t hw[4];
-                    hw[0] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 0]) + __uint_as_float(c0.x), 0.f),
-                                        fmaxf(__uint_as_float(v[o + 1]) + __uint_as_float(c0.y), 0.f));
-                    hw[1] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 2]) + __uint_as_float(c0.z), 0.f),
-                                        fmaxf(__uint_as_float(v[o + 3]) + __uint_as_float(c0.w), 0.f));
-                    hw[2] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 4]) + __uint_as_float(c1.x), 0.f),
-                                        fmaxf(__uint_as_float(v[o + 5]) + __uint_as_float(c1.y), 0.f));
-                    hw[3] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 6]) + __uint_as_float(c1.z), 0.f),
-                                        fmaxf(__uint_as_float(v[o + 7]) + __uint_as_float(c1.w), 0.f));
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        hw[e] = pack_bf16x2(fmaxf(__uint_as_float(v[o + 2 * e]) + fb.conv[8 * j + 2 * e], 0.f),
+                                            fmaxf(__uint_as_float(v[o + 2 * e + 1]) + fb.conv[8 * j + 2 * e + 1], 0.f));
                     st_shared_v4(row + ((j ^ (lane & 7)) << 4), hw[0], hw[1], hw[2], hw[3]);
                 }
             }
@@ -458,14 +452,14 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
 }
 
 template <int CIN, bool U8>
-const char* launch_fused_inst(const ConvLaunch& conv, const CUtensorMap& map_stem_w, const FusedParams& fp, int grid,
-                              cudaStream_t stream) {
+const char* launch_fused_inst(const ConvLaunch& conv, const CUtensorMap& map_stem_w, const FusedParams& fp,
+                              const FusedBias& fb, int grid, cudaStream_t stream) {
     auto k = inc_fused_kernel<CIN, U8>;
     constexpr int smem = fused_smem_bytes(CIN);
     static_assert(smem <= 232448, "fused inc kernel exceeds the 227 KB shared memory limit");
     static std::atomic<uint64_t> configured{0};
     if (!smem_opt_in(k, smem, configured)) return "inc(fused): cudaFuncSetAttribute failed";
-    const cudaError_t e = launch_kernel(k, dim3(grid), dim3(F_THREADS), smem, stream, conv.maps, map_stem_w, conv.p, fp);
+    const cudaError_t e = launch_kernel(k, dim3(grid), dim3(F_THREADS), smem, stream, conv.maps, map_stem_w, conv.p, fp, fb);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -477,10 +471,15 @@ bool inc_fused_eligible(int cin, const ConvLaunch& conv) {
 }
 
 // d: the stem description (dst unused); conv: the prepared launch of inc.double_conv.3 (its A tensor map is not used).
-const char* inc_fused_launch(const StemDesc& d, const ConvLaunch& conv, int n_img, int num_sms, cudaStream_t stream) {
+// host_bias: the folded shifts of both layers on the HOST, stem[64] then conv[64] (they travel as kernel parameters).
+const char* inc_fused_launch(const StemDesc& d, const ConvLaunch& conv, const float* host_bias, int n_img, int num_sms,
+                             cudaStream_t stream) {
     if (!inc_fused_eligible(d.cin, conv)) return "inc(fused): layer is not eligible";
     if (d.src[0].channels + d.src[1].channels != d.cin) return "inc(fused): plane sources do not add up to cin";
-    if (!d.wpack || !d.bias || !d.src[0].ptr) return "inc(fused): null operand";
+    if (!d.wpack || !host_bias || !d.src[0].ptr) return "inc(fused): null operand";
+    FusedBias fb;
+    memcpy(fb.stem, host_bias, sizeof fb.stem);
+    memcpy(fb.conv, host_bias + 64, sizeof fb.conv);
     FusedParams fp;
     memset(&fp, 0, sizeof fp);
     fp.src[0] = d.src[0];
@@ -490,7 +489,6 @@ const char* inc_fused_launch(const StemDesc& d, const ConvLaunch& conv, int n_im
     fp.W = d.W;
     fp.tiles_x = (d.W + FT_W - 1) / FT_W;
     fp.tiles_y = (d.H + FT_H - 1) / FT_H;
-    fp.stem_bias = d.bias;
     const long long tiles = static_cast<long long>(n_img) * fp.tiles_x * fp.tiles_y;
     if (tiles > 0x7fffffffLL) return "inc(fused): too many tiles";
     alignas(64) CUtensorMap map_w;
@@ -503,10 +501,10 @@ const char* inc_fused_launch(const StemDesc& d, const ConvLaunch& conv, int n_im
         if (e) return e;
     }
     const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
-    if (d.cin == 1) return d.is_u8 ? launch_fused_inst<1, true>(conv, map_w, fp, grid, stream)
-                                   : launch_fused_inst<1, false>(conv, map_w, fp, grid, stream);
-    return d.is_u8 ? launch_fused_inst<2, true>(conv, map_w, fp, grid, stream)
-                   : launch_fused_inst<2, false>(conv, map_w, fp, grid, stream);
+    if (d.cin == 1) return d.is_u8 ? launch_fused_inst<1, true>(conv, map_w, fp, fb, grid, stream)
+                                   : launch_fused_inst<1, false>(conv, map_w, fp, fb, grid, stream);
+    return d.is_u8 ? launch_fused_inst<2, true>(conv, map_w, fp, fb, grid, stream)
+                   : launch_fused_inst<2, false>(conv, map_w, fp, fb, grid, stream);
 }
 
 }  // namespace fi

@@ -74,6 +74,7 @@ struct ConvW {     // one conv3x3+BN (or the transposed conv) after folding/pack
     int n_total = 0;
     DevBuf w;      // bf16 [n_total][taps*cin]
     DevBuf b;      // fp32 [n_total]
+    std::vector<float> b_host;  // the same shifts on the host (conv3x3 only)
 };
 
 struct Act {  // bf16 NHWC activation inside the arena (precise mode: a second, lo tensor at off_lo)
@@ -130,6 +131,7 @@ struct fiNet {
     int num_sms = 148;
     bool loaded = false;
     DevBuf stem_w, stem_b;  // bf16 [64][stem_packed_k] hi/lo split, fp32 [64]
+    float inc_bias_host[128] = {};  // folded shifts of inc.double_conv.0 and .3 for the fused kernel's parameters
     ConvW convs[17];        // inc.3, down{1-4}.{0,3}, up{1-4}.{0,3}
     ConvW upT[4];           // ConvTranspose2d of up1..up4 (bilinear=False)
     DevBuf head_w, head_b;  // fp32 [n_classes][64], [n_classes]
@@ -294,6 +296,7 @@ int load_conv3x3(const StateDict& sd, const std::string& key, int cin, int cout,
     out->n_total = cout;
     CUDA_TRY(out->w.upload(packed.data(), packed.size() * 2));
     CUDA_TRY(out->b.upload(shift.data(), shift.size() * 4));
+    out->b_host = shift;
     return FI_OK;
 }
 
@@ -782,6 +785,7 @@ int fiNetLoadWeights(fiNet* net, const char* const* names, const float* const* d
         fi::stem_pack_weights(ws.data(), stem.cin, packed.data());
         CUDA_TRY(net->stem_w.upload(packed.data(), packed.size() * 2));
         CUDA_TRY(net->stem_b.upload(shift.data(), shift.size() * 4));
+        memcpy(net->inc_bias_host, shift.data(), 64 * sizeof(float));
     }
     for (int i = 0; i < 17; ++i) {
         // up{k}.conv.double_conv.0 (indices 9, 11, 13, 15) reads [skip | up]: two K blocks of cin/2 channels each
@@ -789,6 +793,7 @@ int fiNetLoadWeights(fiNet* net, const char* const* names, const float* const* d
         if ((rc = load_conv3x3(sd, conv_prefix(i), cs[i].cin, cs[i].cout, &net->convs[i], net->precise != 0, split_at)))
             return rc;
     }
+    if (net->convs[0].b_host.size() == 64) memcpy(net->inc_bias_host + 64, net->convs[0].b_host.data(), 64 * sizeof(float));
     if (!net->bilinear) {
         for (int i = 0; i < 4; ++i) {
             char key[32];
@@ -872,7 +877,7 @@ int fiNetForward(fiNet* net, const fiPlanes* in0, const fiPlanes* in1, int in_dt
             d.W = W;
             d.wpack = net->stem_w.p;
             d.bias = static_cast<const float*>(net->stem_b.p);
-            KERNEL_TRY(fi::inc_fused_launch(d, s.conv, N, net->num_sms, st));
+            KERNEL_TRY(fi::inc_fused_launch(d, s.conv, net->inc_bias_host, N, net->num_sms, st));
         } else if (s.kind == STEP_UPSAMPLE) {
             KERNEL_TRY(fi::upsample2x_launch(s.src, s.dst, N, s.h, s.w, s.C, st, s.src_lo, s.dst_lo));
         } else {
