@@ -214,6 +214,26 @@ class TrainStep:
 
     # ------------------------------------------------------------------------------------------------ one step
     @torch.no_grad()
+    def loss_value(self, y, target):
+        """The criterion on a finished network output (validation loop of reference model/train.py:204-219) as a 1-element
+        device tensor: the same fused loss kernel as the training step (its gradient output goes to a scratch buffer),
+        no host synchronisation."""
+        lib, st = E.lib(), lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+        y, tgt = y.contiguous().float(), target.contiguous().float()
+        crit = self.criterion
+        fused = (isinstance(crit, CombinedLoss) and crit.ssim_loss.window_size == 11 and crit.ssim_loss.size_average)
+        if crit is not None and not fused:
+            return crit(y, tgt).detach().reshape(1).float()
+        loss, dy = torch.zeros(1, dtype=torch.float32, device=y.device), torch.empty_like(y)
+        if crit is None:
+            E.check(lib.fiMseLossGrad(_ptr(y), _ptr(tgt), y.numel(), _ptr(loss), _ptr(dy), st()))
+        else:
+            n, c, h, w = y.shape
+            E.check(lib.fiCombinedLossGrad(_ptr(y), _ptr(tgt), n * c, h, w, float(crit.mse_weight),
+                                           float(crit.ssim_weight), _ptr(loss), _ptr(dy), st()))
+        return loss
+
+    @torch.no_grad()
     def __call__(self, frame1, frame2, target):
         self.step_count += 1
         with torch.cuda.device(self.device):
@@ -574,7 +594,6 @@ def train_model(model, train_loader, val_loader, num_epochs=100, device="cuda", 
     data; gradients are averaged by TrainStep, the validation loss is averaged over ranks, and rank 0 alone prints and
     writes the checkpoint."""
     crit = CombinedLoss() if criterion == "combined" else (None if criterion == "mse" else criterion)
-    val_crit = crit if crit is not None else nn.MSELoss()
     step = TrainStep(model, lr=lr, criterion=crit, cuda_graph=cuda_graph)
     sched = _PlateauSchedule(step)
     distributed = TrainStep._distributed()
@@ -603,11 +622,12 @@ def train_model(model, train_loader, val_loader, num_epochs=100, device="cuda", 
         train_losses.append(mean_over_ranks(total.item(), len(train_loader)))
         step.average_bn_buffers()
         model.eval()
-        total = 0.0
+        total = torch.zeros(1, dtype=torch.float32, device=device)
         with torch.no_grad():
             for f0, f1, gt in val_loader:
-                total += val_crit(model(f0.to(device), f1.to(device)), gt.to(device)).item()
-        val_losses.append(mean_over_ranks(total, len(val_loader)))
+                total += step.loss_value(model(f0.to(device, non_blocking=True), f1.to(device, non_blocking=True)),
+                                         gt.to(device, non_blocking=True))
+        val_losses.append(mean_over_ranks(total.item(), len(val_loader)))
         sched.step(val_losses[-1])
         say(f"Epoch {epoch + 1}/{num_epochs}:\n  Train Loss: {train_losses[-1]:.6f}\n  Val Loss: {val_losses[-1]:.6f}\n"
             f"  Learning Rate: {step.lr:.2e}")

@@ -326,3 +326,20 @@ def test_optimizer_state_round_trip(cuda_device):
     before = resumed.flat_param.clone()
     resumed(f1, f2, (f1 + f2) / 2)
     assert resumed.step_count == 3 and (resumed.flat_param - before).abs().max() <= 3e-4 * 1.5
+
+
+@pytest.mark.parametrize("criterion", ["mse", "combined", "l1"])
+def test_validation_loss_matches_torch_criterion(cuda_device, criterion):
+    """TrainStep.loss_value (the validation loss of train_model, reference model/train.py:204-219) against the torch
+    criterion on the same tensors; a criterion the library has no kernel for is evaluated by torch itself."""
+    from model.train import CombinedLoss
+
+    crit = {"mse": None, "combined": CombinedLoss(), "l1": nn.L1Loss()}[criterion]
+    step = TrainStep(make_model(3).to(cuda_device), criterion=crit)
+    g = torch.Generator().manual_seed(11)
+    y = torch.rand(3, 1, 40, 56, generator=g).to(cuda_device)
+    t = (y.cpu() * 0.7 + 0.3 * torch.rand(3, 1, 40, 56, generator=g)).to(cuda_device)
+    got = step.loss_value(y, t)
+    assert got.shape == (1,) and got.device.type == "cuda"
+    want = (crit if crit is not None else nn.MSELoss())(y, t)
+    assert abs(got.item() - want.item()) <= 2e-5 * max(1.0, abs(want.item()))
