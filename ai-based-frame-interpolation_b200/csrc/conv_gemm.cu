@@ -391,13 +391,19 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
         pool_w = TILE_W / 2, pool_h = 1;
     const char* no_halo = getenv("FI_NO_HALO");
     l.halo = conv_halo_eligible(d) && !(no_halo && no_halo[0] == '1');
+    l.rows = l.halo && conv_rows_eligible(d);
+    if (l.rows) {
+        l.halo = 0;   // 64-channel layers without a pooled output: filter rows stacked along N (conv_rows.cu)
+        conv_rows_geometry(&tile_w, &tile_h, &box_w, &box_h);
+        block_n = d.n_total;
+    }
     if (l.halo) {
         int t;
         conv_halo_geometry(&t, &box_w, &box_h, &out_w, &out_h, &pool_w, &pool_h);
         tile_w = tile_h = t;
         block_n = d.n_total;
     }
-    if (!l.halo && (d.mode == EPI_STORE || d.mode == EPI_STORE_POOL)) {
+    if (!l.halo && !l.rows && (d.mode == EPI_STORE || d.mode == EPI_STORE_POOL)) {
         // Column-block width of the per-tap kernel. N = 256 is the efficient shape (tensor-bound M128/M256 x N256 MMAs,
         // CTA pairs halve the weight traffic: 1500-1600 TFLOP/s), narrower blocks are bound by the A-operand reads
         // (~56 % tensor-pipe activity at N = 128 under ncu). But a small frame gives a wide layer very few tiles:
@@ -444,7 +450,7 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
         const char* cta2 = getenv("FI_CTA2");
         const bool want = cta2 ? cta2[0] != '0' : true;
         const bool narrow_resident = l.halo && d.n_total == 64 && kmul * (d.c0 + d.c1) == BLOCK_K;
-        l.pair = want && ((l.halo && !narrow_resident) || (!l.halo && block_n == 256 && d.mode != EPI_HEAD &&
+        l.pair = want && !l.rows && ((l.halo && !narrow_resident) || (!l.halo && block_n == 256 && d.mode != EPI_HEAD &&
                                                             (d.mode != EPI_CONVT || d.c0 >= 1024)));
     }
     {
@@ -511,6 +517,7 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
     p.head_b = d.head_b;
     p.out_f32 = d.out_f32;
     p.out_u8 = d.out_u8;
+    p.dst = d.dst;
     l.block_n = block_n;
     l.mode = d.mode;
     l.split = precise ? 1 : 0;
@@ -531,7 +538,7 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
         const char* ks = getenv("FI_KSPLIT");
         const bool automatic = ks && ks[0] == 'a';
         const int forced = (ks && !automatic) ? atoi(ks) : 0;
-        const bool eligible = !l.halo && !l.pair && !precise && d.taps == 9 && d.split_ws && d.split_cnt &&
+        const bool eligible = !l.halo && !l.rows && !l.pair && !precise && d.taps == 9 && d.split_ws && d.split_cnt &&
                               (d.mode == EPI_STORE || d.mode == EPI_STORE_POOL) && (automatic || forced > 1);
         if (eligible && total > 0) {
             int want = forced > 1 ? forced : static_cast<int>(num_sms / total);
@@ -557,6 +564,7 @@ const char* conv_prepare(const ConvDesc& d, int num_sms, ConvLaunch* out) {
 }
 
 const char* conv_launch(const ConvLaunch& l, cudaStream_t stream) {
+    if (l.rows) return conv_rows_launch(l, stream);
     if (l.halo) return l.pair ? conv_halo_pair_launch(l, stream) : conv_halo_launch(l, stream);
     if (l.pair) return conv_pair_launch(l, stream);
     switch (l.block_n * 4 + l.mode) {

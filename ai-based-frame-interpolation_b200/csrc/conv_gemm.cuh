@@ -79,6 +79,7 @@ struct ConvKernelParams {
     const float* head_b;
     float* out_f32;
     uint8_t* out_u8;
+    void* dst;          // row-stacked kernel (conv_rows.cu): bf16 NHWC destination written with plain global stores
 };
 
 // A fully prepared launch: tensor maps are encoded once per (layer, shape) and reused every forward.
@@ -96,6 +97,7 @@ struct ConvLaunch {
     int mode;
     int split;  // 1: precise mode, epilogue writes hi + lo tensors
     int halo;  // 1: conv_halo.cu (halo-reuse kernel for Cout 64/128), 0: conv_gemm.cu
+    int rows;  // 1: conv_rows.cu (filter rows stacked along N for Cout = 64 without a pooled output)
     int pair;  // 1: conv_gemm2.cu (CTA-pair kernel, cta_group::2) for Cout multiples of 256
     int grid;
     double flops;  // algorithmic FLOPs of this launch (2*MACs, no padding counted)
@@ -118,6 +120,11 @@ struct StemDesc;
 bool inc_fused_eligible(int cin, const ConvLaunch& conv);
 const char* inc_fused_launch(const StemDesc& d, const ConvLaunch& conv, const float* host_bias, int n_img, int num_sms,
                              cudaStream_t stream);
+
+// conv_rows.cu
+bool conv_rows_eligible(const ConvDesc& d);
+void conv_rows_geometry(int* tile_w, int* tile_h, int* box_w, int* box_h);
+const char* conv_rows_launch(const ConvLaunch& l, cudaStream_t stream);
 
 // conv_halo.cu
 bool conv_halo_eligible(const ConvDesc& d);

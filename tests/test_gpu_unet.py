@@ -284,7 +284,7 @@ def test_building_blocks_stand_alone(cuda_device):
 
 @pytest.mark.parametrize("env", [{"FI_CTA2": "0"}, {"FI_CTA2": "0", "FI_NO_HALO": "1"}, {"FI_HALO_PREFETCH": "0"},
                                  {"FI_BLOCK_N": "256"}, {"FI_BLOCK_N": "128"}, {"FI_BLOCK_N": "64"}, {"FI_PDL": "0"},
-                                 {"FI_FUSE_INC": "0"},
+                                 {"FI_FUSE_INC": "0"}, {"FI_ROWS": "1"}, {"FI_ROWS": "2"},
                                  {"FI_KSPLIT": "auto"}, {"FI_KSPLIT": "3"}, {"FI_KSPLIT": "9", "FI_BLOCK_N": "128"},
                                  {"FI_KSPLIT": "2", "FI_BLOCK_N": "256", "FI_CTA2": "0"}])
 def test_kernel_selection_fallbacks_give_same_network(cuda_device, monkeypatch, env):
