@@ -199,6 +199,16 @@ def main():
     pp = [(k, load_json(f"{R}_bench_p{k}.json")) for k in (4, 6, 8)]
     if all(d for _, d in pp):
         w("Pairs per forward (`bench.py --pairs K`): " + ", ".join(f"K={k}: {d['value']:.1f} frames/s" for k, d in pp) + ".\n")
+    notes = [(f"{R}_fused_inc.md", "fused `inc` kernel: ncu source-page reading (per-role wait shares, shared-memory port)"),
+             (f"{R}_rows.md", "row-stacked conv kernel (`FI_ROWS`): parity-green, measured slower than the halo kernels, why"),
+             ("sass_summary.txt", "opcode counts per kernel from `cuobjdump -sass` (tcgen05 MMA, TMA, TMEM, PDL; no legacy HMMA)"),
+             ("ncu_traffic.json", "DRAM bytes per conv launch from the `--set full` capture (the `roofline.traffic` source of bench.py)")]
+    notes = [(f, t) for f, t in notes if (P / f).exists()]
+    if notes:
+        w("## Kernel write-ups and evidence files\n")
+        for f, t in notes:
+            w(f"* `{f}` — {t}")
+        w("")
     (P / "README.md").write_text("\n".join(out) + "\n")
     print("\n".join(out)[:2500])
 
