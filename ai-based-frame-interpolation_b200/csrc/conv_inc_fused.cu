@@ -121,7 +121,7 @@ inc_fused_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     const uint32_t tmem_slot = smem_bar + 136;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + (smem_bar + 256 - smem_u32(smem_raw)));
-    uint32_t* in_tile = lut + 260 + 128;
+    uint32_t* in_tile = lut + 260 + 128;   // 128 words after the table are unused (they held the biases, now parameters)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
